@@ -1,0 +1,171 @@
+"""ctypes bindings for the checkers in oracle/ (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; nothing under phasetype_b200/ does.
+
+Two libraries:
+  * oracle/_build/libphtoracle.so -- the CPU restatement (pht_oracle.c), built by `make oracle`;
+  * oracle/_ref/libphtref.so      -- the unmodified reference C + R stand-in, built by `make ref`
+                                     where /root/reference exists (prebuilt file travels to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "libphtoracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libphtref.so")
+REFERENCE_ROOT = "/root/reference"
+
+N_COUNTERS = 16
+COUNTER_NAMES = ["paths", "attempts", "jumps", "dens_evals", "env_updates", "brent_evals",
+                 "arms_calls", "metrop_rejects", "nonfinite"]
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_up = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+def build(target="all"):
+    """Compile the checkers (gcc).  `ref` is skipped when the reference tree is absent."""
+    targets = ["oracle"]
+    if target in ("all", "ref") and os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        targets.append("ref")
+    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def embedded(S, s):
+    """P, Pfull exactly as src/PHT_MCMC_Aslett.c:280-297 (column-major n*n and n*(n+1))."""
+    lib = oracle()
+    S = _f64(S); s = _f64(s); n = s.shape[0]
+    P = np.zeros(n * n); Pfull = np.zeros(n * (n + 1))
+    lib.pho_embedded(n, S, s, P, Pfull)
+    return P, Pfull
+
+
+class _Lib:
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " is missing: run `make -C oracle`")
+        self.path = path
+        self.lib = C.CDLL(path)
+
+    def __getattr__(self, name):
+        return getattr(self.lib, name)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        o = _Lib(ORACLE_SO)
+        L = o.lib
+        L.pho_exp.restype = C.c_double; L.pho_exp.argtypes = [C.c_double]
+        L.pho_log.restype = C.c_double; L.pho_log.argtypes = [C.c_double]
+        L.pho_unif_at.restype = C.c_double
+        L.pho_unif_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.pho_rgamma_at.restype = C.c_double
+        L.pho_rgamma_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_double]
+        L.pho_embedded.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        L.pho_mhrs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                     _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _up]
+        for f in ("pho_dcs_paths", "pho_ecs_paths", "pho_eigen", "pho_gibbs", "pho_sweep_stats", "pho_update",
+                  "pho_choose_zbits"):
+            if not hasattr(L, f):
+                continue
+        if hasattr(L, "pho_eigen"):
+            L.pho_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp]
+        if hasattr(L, "pho_dcs_paths"):
+            L.pho_dcs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, C.c_int,
+                                        _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _up]
+        if hasattr(L, "pho_ecs_paths"):
+            L.pho_ecs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                        _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _up]
+        if hasattr(L, "pho_choose_zbits"):
+            L.pho_choose_zbits.restype = C.c_int; L.pho_choose_zbits.argtypes = [C.c_double]
+        if hasattr(L, "pho_gibbs"):
+            L.pho_gibbs.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp,
+                                    _dp, C.c_long, _ip, _dp, _dp, _up]
+        if hasattr(L, "pho_sweep_stats"):
+            L.pho_sweep_stats.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp,
+                                          _dp, _dp, C.c_long, _ip, C.c_int, C.c_int, C.c_int, _lp, _lp, _lp, _up]
+        if hasattr(L, "pho_update"):
+            L.pho_update.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, _dp, _dp, _ip, _dp, C.c_int,
+                                     _lp, _lp, _dp]
+        _oracle = o
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        r = _Lib(REF_SO)
+        L = r.lib
+        L.phtref_mhrs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                        _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _up]
+        L.phtref_ecs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                       _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, _up]
+        L.phtref_dcs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                       _dp, _dp, _dp, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, _up]
+        L.phtref_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        L.phtref_gibbs.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
+                                   _ip, _dp, _dp, C.c_int, _ip, _dp, _dp]
+        _ref = r
+    return _ref
+
+
+def _out(count, n, want):
+    if not want:
+        return None, None, None
+    return (np.zeros(count, dtype=np.int32), np.zeros(count * n * n, dtype=np.int32),
+            np.zeros(count * n, dtype=np.float64))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _counters(c):
+    return {k: int(c[i]) for i, k in enumerate(COUNTER_NAMES)}
+
+
+def mhrs_paths(impl, seed, it, y, cens, S, s, mhit=1, obs0=0, stride=1, want=True):
+    """Per-observation (B[count], N[count,n*n], z[count,n]) + counters from `impl` in {"oracle","ref"}."""
+    y = _f64(y); cens = _i32(cens); S = _f64(S); s = _f64(s)
+    n = s.shape[0]; count = y.shape[0]
+    P, Pfull = embedded(S, s)
+    cnt = np.zeros(N_COUNTERS, dtype=np.uint64)
+    B, N, z = _out(count, n, want)
+    if impl == "oracle":
+        if B is None:
+            B, N, z = _out(count, n, True)
+        rc = oracle().pho_mhrs_paths(seed, it, obs0, stride, count, y, cens, n, S, s, Pfull, mhit, B, N, z, cnt)
+        counters = _counters(cnt)
+    else:
+        rc = ref().phtref_mhrs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), Pfull, mhit,
+                                     _ptr(B), _ptr(N), _ptr(z), cnt)
+        counters = {"paths": count, "attempts": int(cnt[1]), "jumps": int(cnt[4]), "uniforms": int(cnt[0])}
+    if rc != 0:
+        raise RuntimeError("%s mhrs_paths failed rc=%d" % (impl, rc))
+    if B is None:
+        return None, None, None, counters
+    return B, N.reshape(count, n * n), z.reshape(count, n), counters
