@@ -1,0 +1,119 @@
+/*
+ * pht_b200.h -- C ABI of libpht_b200.so, the B200-native Gibbs engine that sits
+ * behind PhaseType's native entry point.  Plain pointers and sizes only.
+ *
+ * Layer 1 is the drop-in: the exact routine the R package registers
+ * (reference src/PHT_MCMC_Aslett.h:1-3, registered as a 15-argument .C routine
+ * in src/Registrations.c:6-14 and called from R/phtMCMC.R:83, R/phtMCMC2.R:73).
+ * Layer 2 is the engine API LJMA_Gibbs itself is written on; tests and
+ * bench.py use it to keep data resident, shard observations over GPUs and read
+ * per-observation statistics for parity checks.
+ *
+ * There is no CPU fallback: every entry point fails (non-zero return and a
+ * message from pht_last_error()) when no CUDA device is usable.
+ */
+#ifndef PHT_B200_H
+#define PHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ layer 1 */
+
+/* Replaces reference src/PHT_MCMC_Aslett.c:104 (same name, same 15 arguments,
+ * same meaning: documented at src/PHT_MCMC_Aslett.c:72-103).  `res` (it x m,
+ * column-major) is fully overwritten; row 0 is the start value.  Diagnostics go
+ * through Rprintf; nothing is signalled (void), as in the reference.
+ * Engine knobs that have no slot in the 15 arguments come from the environment:
+ *   PHT_B200_SEED   (decimal/hex uint64; default: drawn from unif_rand())
+ *   PHT_B200_DEVICE (CUDA ordinal, default 0)
+ *   PHT_B200_GPUS   (single-process multi-GPU count, default 1)                */
+void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, double *zeta,
+                int *T, double *C, double *y, int *l, int *censored, double *start,
+                int *silent, double *res);
+
+/* ------------------------------------------------------------------ layer 2 */
+
+#define PHT_METHOD_MHRS 1   /* reference src/PHT_MCMC_Aslett.c:69-71 */
+#define PHT_METHOD_ECS  2
+#define PHT_METHOD_DCS  4
+#define PHT_MAX_PHASES  32
+
+typedef struct pht_engine pht_engine;
+
+typedef struct pht_config {
+    int n;                /* transient phases, 1..PHT_MAX_PHASES */
+    int m;                /* number of rate parameters */
+    int method;           /* bit mask as in the reference; priority MHRS > DCS > ECS */
+    int mhit;             /* Metropolis-Hastings proposals per exact observation (MHRS) */
+    const int *T;         /* (n+1)^2 column-major: 0 = structural zero, v>=1 = parameter index */
+    const double *C;      /* (n+1)^2 constant multipliers */
+    const double *nu;     /* m Gamma shapes */
+    const double *zeta;   /* m Gamma rates */
+    uint64_t seed;        /* Philox key of the chain */
+    int device;           /* CUDA ordinal */
+    int rank, world;      /* this engine holds observations rank, rank+world, ... of the global set */
+    int zbits;            /* fractional bits of the fixed-point sojourn totals (pht_choose_zbits) */
+    int mhrs_cap;         /* attempts a lane tries before handing an observation to the cooperative tail; 0 = default */
+    int use_graph;        /* capture the sweep in a CUDA graph (1) or launch kernels directly (0) */
+} pht_config;
+
+const char *pht_last_error(void);
+int pht_device_count(void);
+
+/* 62 - ceil(log2(16 * sum_y)): every per-state total fits an int64 with headroom */
+int pht_choose_zbits(double sum_y_global);
+
+/* y_local / cens_local: host arrays of the l_local observations this rank owns
+ * (global index of local k is rank + k*world); copied to the device. */
+int pht_engine_create(pht_engine **out, const pht_config *cfg, const double *y_local,
+                      const int *cens_local, long l_local);
+void pht_engine_destroy(pht_engine *e);
+
+/* multi-GPU, one process per GPU: rank 0 calls pht_comm_unique_id, the 128 bytes
+ * travel over the launcher's own channel, every rank calls pht_engine_comm_init. */
+int pht_comm_unique_id(void *id128);
+int pht_engine_comm_init(pht_engine *e, const void *id128);
+
+/* parameter vector (length m) the next sweep starts from, and the index that sweep gets */
+int pht_engine_set_theta(pht_engine *e, const double *theta, uint32_t next_iter);
+int pht_engine_get_theta(pht_engine *e, double *theta);
+
+/* run `nsweeps` Gibbs sweeps; row r of out (nsweeps x m, row-major) is the draw of sweep r.
+ * out may be NULL (results stay on the device; fetch later with pht_engine_get_theta). */
+int pht_engine_run(pht_engine *e, int nsweeps, double *out);
+/* asynchronous halves of pht_engine_run for timing with CUDA events */
+int pht_engine_enqueue(pht_engine *e, int nsweeps);
+int pht_engine_sync(pht_engine *e);
+/* device time in ms of the sweeps enqueued by the last pht_engine_enqueue (after sync) */
+int pht_engine_last_ms(pht_engine *e, float *total_ms, float *path_kernel_ms);
+
+/* parity hooks ------------------------------------------------------------- */
+/* sufficient statistics of ONE sweep at the current parameters without updating them:
+ * N (n*n), B (n) counts and z (n) totals of this rank's shard (before any all-reduce) */
+int pht_engine_sweep_stats(pht_engine *e, long long *N, long long *B, long long *zfix);
+/* per-observation statistics for local observations [first, first+count): B[count],
+ * N[count*n*n] (int32), z[count*n]; same kernels, recording to memory instead of reducing */
+int pht_engine_paths(pht_engine *e, long first, long count, int *B, int *N, double *z);
+/* override the spectral data the ECS/DCS kernels use (evals n, Q n*n, Qinv n*n); NULL restores the device solver */
+int pht_engine_set_spectral(pht_engine *e, const double *evals, const double *Q, const double *Qinv);
+/* current model matrices as the kernels see them (each may be NULL) */
+int pht_engine_get_model(pht_engine *e, double *S, double *s, double *P, double *Pfull,
+                         double *evals, double *Q, double *Qinv);
+/* event counters accumulated since creation (index meaning: PHT_CNT_*) */
+enum { PHT_CNT_PATHS = 0, PHT_CNT_ATTEMPTS, PHT_CNT_JUMPS, PHT_CNT_DENS_EVALS, PHT_CNT_ENV_UPDATES,
+       PHT_CNT_BRENT_EVALS, PHT_CNT_ARMS_CALLS, PHT_CNT_METROP_REJECTS, PHT_CNT_NONFINITE,
+       PHT_CNT_DEFERRED, PHT_CNT_TAIL_ROUNDS, PHT_CNT_ERRORS, PHT_CNT_LAUNCHES, PHT_CNT_COUNT = 16 };
+int pht_engine_counters(pht_engine *e, unsigned long long *out);
+
+/* measurement helpers ------------------------------------------------------- */
+/* dependent-chain FP64 FMA microbenchmark: achieved FMA instructions per second (all SMs) */
+int pht_fp64_fma_rate(int device, double *fma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHT_B200_H */

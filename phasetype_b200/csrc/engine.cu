@@ -1,0 +1,438 @@
+/*
+ * engine.cu -- lifecycle and sweep orchestration of the B200 Gibbs engine (layer 2 of
+ * include/pht_b200.h).  One engine = one GPU = one shard of the observations.
+ *
+ * A sweep is the body of the reference's iteration loop (src/PHT_MCMC_Aslett.c:268-405):
+ *     k_assemble -> [k_spectral] -> path kernel of the selected method -> [all-reduce of
+ *     the statistics block over NCCL] -> k_update
+ * enqueued on one stream with no host synchronisation in between, and captured once into
+ * a CUDA graph that is replayed per sweep (the sweep index lives in device memory).
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+#include <vector>
+#include <dlfcn.h>
+#include "engine_internal.h"
+
+/* ---------------------------------------------------------------- errors */
+static thread_local char g_err[512] = "";
+static int fail(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
+extern "C" const char *pht_last_error(void) { return g_err; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+/* ---------------------------------------------------------------- NCCL (loaded lazily) */
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.h) return 0;
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char *nm : names) { g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+    if (!g_nccl.h) return fail("NCCL not found: %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail("NCCL symbols missing");
+    return 0;
+}
+static const int NCCL_INT64 = 4, NCCL_SUM = 0;     /* ncclInt64, ncclSum (stable enum values of nccl.h) */
+
+/* ---------------------------------------------------------------- engine */
+struct pht_engine {
+    pht_config cfg;
+    std::vector<int> T; std::vector<double> C, nu, zeta;
+    long l_local = 0;
+    cudaStream_t stream = nullptr;
+    /* device buffers */
+    double *d_y = nullptr; uint8_t *d_cens = nullptr;
+    double *d_model = nullptr; long long *d_stats = nullptr; DevState *d_state = nullptr;
+    int *d_T = nullptr; double *d_C = nullptr, *d_nu = nullptr, *d_zeta = nullptr;
+    int *d_var_ptr = nullptr, *d_cell_i = nullptr, *d_cell_j = nullptr;
+    TailItem *d_items = nullptr; uint32_t *d_pend0 = nullptr, *d_pend1 = nullptr, *d_done = nullptr;
+    unsigned long long *d_found = nullptr; uint32_t item_cap = 0;
+    double *d_res = nullptr; int res_rows = 0;
+    ModelLayout L;
+    int grid_blocks = 0;
+    /* graph */
+    cudaGraphExec_t graph_exec = nullptr; int graph_res_rows = -1; double *graph_res = nullptr;
+    /* nccl */
+    ncclComm_t comm = nullptr;
+    /* timing */
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> kev; int kev_used = 0;
+    unsigned long long launches = 0;
+};
+
+extern "C" int pht_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+extern "C" int pht_choose_zbits(double sum_y) {
+    if (!(sum_y > 0.0) || !std::isfinite(sum_y)) return 30;
+    int b = 62 - (int)std::ceil(std::log2(16.0 * sum_y + 1.0));
+    if (b > 52) b = 52;
+    if (b < 0) b = 0;
+    return b;
+}
+
+static SweepParams sweep_params(pht_engine *e) {
+    SweepParams p; memset(&p, 0, sizeof(p));
+    p.y = e->d_y; p.cens = e->d_cens; p.l_local = e->l_local;
+    p.obs_rank = (uint32_t)e->cfg.rank; p.obs_world = (uint32_t)e->cfg.world;
+    p.model = e->d_model; p.stats = e->d_stats; p.state = e->d_state;
+    p.n = e->cfg.n; p.m = e->cfg.m; p.mhit = e->cfg.mhit; p.zbits = e->cfg.zbits;
+    p.k0 = (uint32_t)e->cfg.seed; p.k1 = (uint32_t)(e->cfg.seed >> 32);
+    p.items = e->d_items; p.pend0 = e->d_pend0; p.pend1 = e->d_pend1; p.done = e->d_done; p.found = e->d_found;
+    p.item_cap = e->item_cap; p.mhrs_cap = e->cfg.mhrs_cap;
+    return p;
+}
+static UpdateParams update_params(pht_engine *e, double *res, int res_rows) {
+    UpdateParams u; memset(&u, 0, sizeof(u));
+    u.model = e->d_model; u.stats = e->d_stats; u.state = e->d_state; u.res = res; u.res_rows = res_rows;
+    u.T = e->d_T; u.C = e->d_C; u.nu = e->d_nu; u.zeta = e->d_zeta;
+    u.var_ptr = e->d_var_ptr; u.cell_i = e->d_cell_i; u.cell_j = e->d_cell_j;
+    u.n = e->cfg.n; u.m = e->cfg.m; u.zbits = e->cfg.zbits;
+    u.k0 = (uint32_t)e->cfg.seed; u.k1 = (uint32_t)(e->cfg.seed >> 32);
+    return u;
+}
+
+static int method_of(const pht_config &c) {       /* dispatch priority of src/PHT_MCMC_Aslett.c:325-337 */
+    if (c.method & PHT_METHOD_MHRS) return PHT_METHOD_MHRS;
+    if (c.method & PHT_METHOD_DCS) return PHT_METHOD_DCS;
+    if (c.method & PHT_METHOD_ECS) return PHT_METHOD_ECS;
+    return 0;
+}
+
+/* enqueue the path kernel of the configured method */
+static int enqueue_paths(pht_engine *e, const SweepParams &p) {
+    switch (method_of(e->cfg)) {
+    case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->stream)); break;
+    default: return fail("sampling method %d has no kernel in this build", e->cfg.method);
+    }
+    e->launches++;
+    return 0;
+}
+
+static int enqueue_sweep(pht_engine *e, double *res, int res_rows, bool time_kernel) {
+    UpdateParams u = update_params(e, res, res_rows);
+    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    SweepParams p = sweep_params(e);
+    if (time_kernel && e->kev_used + 2 <= (int)e->kev.size()) CU(cudaEventRecord(e->kev[e->kev_used++], e->stream));
+    if (enqueue_paths(e, p)) return -1;
+    if (time_kernel && (e->kev_used & 1)) CU(cudaEventRecord(e->kev[e->kev_used++], e->stream));
+    if (e->comm) {
+        int rc = g_nccl.AllReduce(e->d_stats, e->d_stats, (size_t)stats_len(e->cfg.n), NCCL_INT64, NCCL_SUM, e->comm, e->stream);
+        if (rc != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    }
+    CU(pht_launch_update(u, e->stream)); e->launches++;
+    return 0;
+}
+
+extern "C" void pht_engine_destroy(pht_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    void *bufs[] = { e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res };
+    for (void *b : bufs) if (b) cudaFree(b);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const double *y_local,
+                                 const int *cens_local, long l_local) {
+    if (!out || !cfg) return fail("null argument");
+    *out = nullptr;
+    const int n = cfg->n, m = cfg->m, n1 = n + 1;
+    if (n < 1 || n > PHT_MAX_PHASES) return fail("n = %d outside 1..%d", n, PHT_MAX_PHASES);
+    if (m < 1 || m > n * n1) return fail("m = %d outside 1..n(n+1)", m);
+    if (method_of(*cfg) == 0) return fail("unknown sampling method (code = %d)", cfg->method);
+    if (cfg->mhit < 0 || cfg->mhit > 65535) return fail("mhit = %d outside 0..65535", cfg->mhit);
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail("bad shard (rank %d of %d)", cfg->rank, cfg->world);
+    if (cfg->zbits < 0 || cfg->zbits > 52) return fail("zbits = %d outside 0..52", cfg->zbits);
+    if (l_local < 0 || l_local > 0x7fffffffL) return fail("l_local out of range");
+    if ((double)l_local * cfg->world > 4.0e9) return fail("global observation index exceeds 32 bits");
+    for (int i = 0; i < n1 * n1; i++) if (cfg->T[i] < 0 || cfg->T[i] > m) return fail("T[%d] = %d outside 0..m", i, cfg->T[i]);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device available (this library has no CPU path)"); }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d not present (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    pht_engine *e = new pht_engine();
+    e->cfg = *cfg;
+    e->T.assign(cfg->T, cfg->T + n1 * n1); e->C.assign(cfg->C, cfg->C + n1 * n1);
+    e->nu.assign(cfg->nu, cfg->nu + m); e->zeta.assign(cfg->zeta, cfg->zeta + m);
+    e->cfg.T = e->T.data(); e->cfg.C = e->C.data(); e->cfg.nu = e->nu.data(); e->cfg.zeta = e->zeta.data();
+    if (e->cfg.mhrs_cap <= 0) e->cfg.mhrs_cap = 256;
+    e->l_local = l_local;
+    e->L = ModelLayout::make(n, m);
+#define CUE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail("%s failed: %s", #call, cudaGetErrorString(e_)); pht_engine_destroy(e); return -1; } } while (0)
+    CUE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUE(cudaEventCreate(&e->ev0)); CUE(cudaEventCreate(&e->ev1));
+
+    /* observations: y as is, censoring flags repacked int32 -> uint8 (9 B per path in HBM) */
+    const size_t ln = (size_t)(l_local > 0 ? l_local : 1);
+    CUE(cudaMalloc(&e->d_y, ln * sizeof(double)));
+    CUE(cudaMalloc(&e->d_cens, ln));
+    if (l_local > 0) {
+        CUE(cudaMemcpyAsync(e->d_y, y_local, (size_t)l_local * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        uint8_t *hc = nullptr;
+        CUE(cudaMallocHost(&hc, (size_t)l_local));
+        for (long i = 0; i < l_local; i++) hc[i] = cens_local[i] != 0;
+        cudaError_t ce = cudaMemcpyAsync(e->d_cens, hc, (size_t)l_local, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        cudaFreeHost(hc);
+        CUE(ce);
+    }
+
+    /* parameter -> cells CSR in the reference's insertion order (row-major walk of T, src/PHT_MCMC_Aslett.c:210-228) */
+    std::vector<int> var_ptr(m + 1, 0), cell_i, cell_j;
+    for (int i = 0; i < n1; i++) for (int j = 0; j < n1; j++) { int v = e->T[i + j * n1]; if (v) var_ptr[v]++; }
+    for (int v = 0; v < m; v++) var_ptr[v + 1] += var_ptr[v];
+    cell_i.resize(var_ptr[m] > 0 ? var_ptr[m] : 1); cell_j.resize(cell_i.size());
+    { std::vector<int> fill(var_ptr.begin(), var_ptr.end() - 1);
+      for (int i = 0; i < n1; i++) for (int j = 0; j < n1; j++) { int v = e->T[i + j * n1]; if (v) { int c = fill[v - 1]++; cell_i[c] = i; cell_j[c] = j; } } }
+
+    CUE(cudaMalloc(&e->d_model, sizeof(double) * e->L.total)); CUE(cudaMemset(e->d_model, 0, sizeof(double) * e->L.total));
+    CUE(cudaMalloc(&e->d_stats, sizeof(long long) * stats_len(n))); CUE(cudaMemset(e->d_stats, 0, sizeof(long long) * stats_len(n)));
+    CUE(cudaMalloc(&e->d_state, sizeof(DevState))); CUE(cudaMemset(e->d_state, 0, sizeof(DevState)));
+    CUE(cudaMalloc(&e->d_T, sizeof(int) * n1 * n1)); CUE(cudaMemcpy(e->d_T, e->T.data(), sizeof(int) * n1 * n1, cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&e->d_C, sizeof(double) * n1 * n1)); CUE(cudaMemcpy(e->d_C, e->C.data(), sizeof(double) * n1 * n1, cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&e->d_nu, sizeof(double) * m)); CUE(cudaMemcpy(e->d_nu, e->nu.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&e->d_zeta, sizeof(double) * m)); CUE(cudaMemcpy(e->d_zeta, e->zeta.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&e->d_var_ptr, sizeof(int) * (m + 1))); CUE(cudaMemcpy(e->d_var_ptr, var_ptr.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&e->d_cell_i, sizeof(int) * cell_i.size())); CUE(cudaMemcpy(e->d_cell_i, cell_i.data(), sizeof(int) * cell_i.size(), cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&e->d_cell_j, sizeof(int) * cell_j.size())); CUE(cudaMemcpy(e->d_cell_j, cell_j.data(), sizeof(int) * cell_j.size(), cudaMemcpyHostToDevice));
+
+    if (method_of(e->cfg) == PHT_METHOD_MHRS) {
+        e->item_cap = (uint32_t)ln;
+        CUE(cudaMalloc(&e->d_items, sizeof(TailItem) * ln)); CUE(cudaMalloc(&e->d_pend0, sizeof(uint32_t) * ln));
+        CUE(cudaMalloc(&e->d_pend1, sizeof(uint32_t) * ln)); CUE(cudaMalloc(&e->d_done, sizeof(uint32_t) * ln));
+        CUE(cudaMalloc(&e->d_found, sizeof(unsigned long long) * ln));
+        e->grid_blocks = pht_mhrs_grid_blocks(cfg->device, n);
+        if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
+    }
+    /* sweep index 1, start-value assembly (src/PHT_MCMC_Aslett.c:268) */
+    DevState st; memset(&st, 0, sizeof(st)); st.iter = 1; st.first_assembly = 1;
+    CUE(cudaMemcpy(e->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+#undef CUE
+    *out = e;
+    return 0;
+}
+
+extern "C" int pht_comm_unique_id(void *id128) {
+    if (nccl_load()) return -1;
+    ncclUniqueId id; int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail("ncclGetUniqueId failed (%d)", rc);
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+extern "C" int pht_engine_comm_init(pht_engine *e, const void *id128) {
+    if (!e) return fail("null engine");
+    if (e->cfg.world == 1) return 0;
+    if (nccl_load()) return -1;
+    CU(cudaSetDevice(e->cfg.device));
+    ncclUniqueId id; memcpy(&id, id128, sizeof(id));
+    int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, id, e->cfg.rank);
+    if (rc != 0) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return 0;
+}
+
+extern "C" int pht_engine_set_theta(pht_engine *e, const double *theta, uint32_t next_iter) {
+    if (!e || !theta) return fail("null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(e->d_model + e->L.theta, theta, sizeof(double) * e->cfg.m, cudaMemcpyHostToDevice));
+    DevState st; CU(cudaMemcpy(&st, e->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    st.iter = next_iter; st.first_assembly = 1;
+    CU(cudaMemcpy(e->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int pht_engine_get_theta(pht_engine *e, double *theta) {
+    if (!e || !theta) return fail("null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(theta, e->d_model + e->L.theta, sizeof(double) * e->cfg.m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+static int ensure_res(pht_engine *e, int rows) {
+    if (rows <= e->res_rows) return 0;
+    if (e->d_res) { CU(cudaFree(e->d_res)); e->d_res = nullptr; }
+    CU(cudaMalloc(&e->d_res, sizeof(double) * (size_t)rows * e->cfg.m));
+    e->res_rows = rows;
+    return 0;
+}
+
+extern "C" int pht_engine_enqueue(pht_engine *e, int nsweeps) {
+    if (!e || nsweeps < 0) return fail("bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (ensure_res(e, nsweeps > 0 ? nsweeps : 1)) return -1;
+    CU(cudaMemsetAsync(&e->d_state->res_row, 0, sizeof(uint32_t), e->stream));
+    e->kev_used = 0;
+    const bool graph = e->cfg.use_graph != 0;
+    if (!graph) {
+        const int want = 2 * (nsweeps < 64 ? nsweeps : 64);
+        while ((int)e->kev.size() < want) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->kev.push_back(ev); }
+    }
+    if (graph && (e->graph_exec == nullptr || e->graph_res != e->d_res || e->graph_res_rows != e->res_rows)) {
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_sweep(e, e->d_res, e->res_rows, false);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        if (rc != 0) { if (g) cudaGraphDestroy(g); return -1; }
+        if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&e->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+        e->graph_res = e->d_res; e->graph_res_rows = e->res_rows;
+    }
+    CU(cudaEventRecord(e->ev0, e->stream));
+    for (int k = 0; k < nsweeps; k++) {
+        if (graph) { CU(cudaGraphLaunch(e->graph_exec, e->stream)); }
+        else if (enqueue_sweep(e, e->d_res, e->res_rows, k < 64)) return -1;
+    }
+    CU(cudaEventRecord(e->ev1, e->stream));
+    return 0;
+}
+
+static int check_state(pht_engine *e) {
+    DevState st; CU(cudaMemcpy(&st, e->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st.error) {
+        int err = st.error;
+        cudaMemset(&e->d_state->error, 0, sizeof(int));
+        return fail("device error word 0x%x (%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range; " : "",
+                    (err & 4) ? "MHRS tail list overflow; " : "",
+                    (err & 8) ? "an observation's survival probability is too small for rejection sampling; " : "");
+    }
+    return 0;
+}
+
+extern "C" int pht_engine_sync(pht_engine *e) {
+    if (!e) return fail("null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    return check_state(e);
+}
+
+extern "C" int pht_engine_last_ms(pht_engine *e, float *total_ms, float *path_kernel_ms) {
+    if (!e) return fail("null engine");
+    if (total_ms) CU(cudaEventElapsedTime(total_ms, e->ev0, e->ev1));
+    if (path_kernel_ms) {
+        float acc = 0.f; int pairs = e->kev_used / 2;
+        for (int i = 0; i < pairs; i++) { float ms; CU(cudaEventElapsedTime(&ms, e->kev[2 * i], e->kev[2 * i + 1])); acc += ms; }
+        *path_kernel_ms = pairs ? acc / pairs : -1.f;
+    }
+    return 0;
+}
+
+extern "C" int pht_engine_run(pht_engine *e, int nsweeps, double *out) {
+    if (pht_engine_enqueue(e, nsweeps)) return -1;
+    if (pht_engine_sync(e)) return -1;
+    if (out && nsweeps > 0) CU(cudaMemcpy(out, e->d_res, sizeof(double) * (size_t)nsweeps * e->cfg.m, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pht_engine_sweep_stats(pht_engine *e, long long *N, long long *B, long long *zfix) {
+    if (!e) return fail("null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n;
+    UpdateParams u = update_params(e, nullptr, 0);
+    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    SweepParams p = sweep_params(e);
+    if (enqueue_paths(e, p)) return -1;
+    if (pht_engine_sync(e)) return -1;
+    std::vector<long long> h(stats_len(n));
+    CU(cudaMemcpy(h.data(), e->d_stats, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    if (N) memcpy(N, h.data(), sizeof(long long) * n * n);
+    if (B) memcpy(B, h.data() + n * n, sizeof(long long) * n);
+    if (zfix) memcpy(zfix, h.data() + n * n + n, sizeof(long long) * n);
+    return 0;
+}
+
+extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, int *N, double *z) {
+    if (!e || !B || !N || !z) return fail("null argument");
+    if (first < 0 || count < 0 || first + count > e->l_local) return fail("range [%ld, %ld) outside the shard", first, first + count);
+    if (count == 0) return 0;
+    CU(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n;
+    int *dB = nullptr, *dN = nullptr; double *dz = nullptr;
+    CU(cudaMalloc(&dB, sizeof(int) * count)); CU(cudaMalloc(&dN, sizeof(int) * count * n * n)); CU(cudaMalloc(&dz, sizeof(double) * count * n));
+    CU(cudaMemsetAsync(dB, 0, sizeof(int) * count, e->stream)); CU(cudaMemsetAsync(dN, 0, sizeof(int) * count * n * n, e->stream));
+    CU(cudaMemsetAsync(dz, 0, sizeof(double) * count * n, e->stream));
+    UpdateParams u = update_params(e, nullptr, 0);
+    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    SweepParams p = sweep_params(e);
+    p.outB = dB; p.outN = dN; p.outz = dz; p.first = first; p.count = count;
+    int rc = enqueue_paths(e, p);
+    if (rc == 0) rc = pht_engine_sync(e);
+    if (rc == 0) {
+        CU(cudaMemcpy(B, dB, sizeof(int) * count, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(N, dN, sizeof(int) * count * n * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(z, dz, sizeof(double) * count * n, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dB); cudaFree(dN); cudaFree(dz);
+    return rc;
+}
+
+extern "C" int pht_engine_set_spectral(pht_engine *e, const double *evals, const double *Q, const double *Qinv) {
+    (void)evals; (void)Q; (void)Qinv;
+    if (!e) return fail("null engine");
+    return fail("spectral override is not available in this build");
+}
+
+extern "C" int pht_engine_get_model(pht_engine *e, double *S, double *s, double *P, double *Pfull,
+                                    double *evals, double *Q, double *Qinv) {
+    if (!e) return fail("null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    const int n = e->cfg.n;
+    std::vector<double> h(e->L.total);
+    CU(cudaMemcpy(h.data(), e->d_model, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+    if (S) memcpy(S, &h[e->L.S], sizeof(double) * n * n);
+    if (s) memcpy(s, &h[e->L.s], sizeof(double) * n);
+    if (P) memcpy(P, &h[e->L.P], sizeof(double) * n * n);
+    if (Pfull) memcpy(Pfull, &h[e->L.Pfull], sizeof(double) * n * (n + 1));
+    if (evals) memcpy(evals, &h[e->L.evals], sizeof(double) * n);
+    if (Q) memcpy(Q, &h[e->L.Q], sizeof(double) * n * n);
+    if (Qinv) memcpy(Qinv, &h[e->L.Qinv], sizeof(double) * n * n);
+    return 0;
+}
+
+extern "C" int pht_engine_counters(pht_engine *e, unsigned long long *out) {
+    if (!e || !out) return fail("null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    DevState st; CU(cudaMemcpy(&st, e->d_state, sizeof(st), cudaMemcpyDeviceToHost));
+    memcpy(out, st.counters, sizeof(st.counters));
+    out[PHT_CNT_LAUNCHES] = e->launches;
+    return 0;
+}

@@ -1,0 +1,403 @@
+/*
+ * k_mhrs.cu -- Bladt MHRS path sampler for sm_100a (method bit 1).
+ *
+ * What it computes (reference: per-observation independence Metropolis-Hastings over
+ * rejection-sampled paths, src/Simulate_AbsCTMC_eq_Bladt_MHRS.c:63-110 calling
+ * src/Simulate_AbsCTMC_gt_Bladt_MHRS.c:34-160): for every observation y, forward-simulate
+ * the unconditioned chain until an attempt survives past y, optionally MH-swap against
+ * `mhit` further draws, and add the accepted path's (B, N, z) to the sweep statistics.
+ *
+ * How it is organised on the GPU (nothing like the reference's loop nest):
+ *   - Every rejection attempt is its own Philox sub-stream (pht_philox.h), so attempts
+ *     are independent work items and "the first attempt that survives" is well defined
+ *     whatever order they run in.
+ *   - SEARCH / REPLAY split: while searching, a lane tracks only (t, state); the 26 of 27
+ *     attempts that fail never touch N or z.  The accepted attempt is replayed once from
+ *     its (attempt index, offset) with recording on.  No per-attempt zeroing of N2/z2.
+ *   - One jump-step is one Philox block: {state uniform of this jump, exponential uniform
+ *     of the next}; the attempt's first step uses the same code with the start
+ *     distribution as the scan row, so fresh and running lanes do not diverge.
+ *   - Lane phase: persistent warps, one observation per lane, refilled from a global
+ *     counter in warp-sized chunks as lanes finish (attempt counts are geometric with a
+ *     heavy tail).  A lane gives up after `cap` attempts and appends the
+ *     observation to the tail list.
+ *   - Tail phase (same cooperative launch, grid barriers between rounds): all lanes of the
+ *     GPU search each pending observation's attempts in parallel, 32-attempt runs handed
+ *     out from a global counter, chunk size doubling per round; atomicMin keeps the first
+ *     surviving attempt; one thread per observation then advances its MH state machine.
+ *   - Statistics: N, B in shared-memory integer atomics; z per path in a per-lane shared
+ *     slab (bit-identical to the reference's z2), then added as int64 fixed point, so the
+ *     sweep totals do not depend on scheduling or on the number of GPUs.
+ *
+ * Roofline: FP64/issue bound (one log + ~n compares per jump-step, 12 B of HBM per path).
+ */
+#include <cooperative_groups.h>
+#include "engine_internal.h"
+#include "pht_philox.h"
+
+namespace cg = cooperative_groups;
+
+#define MHRS_THREADS 256
+#define RUN_LEN 32u                 /* attempts per tail work unit */
+#define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
+#define TAIL_KMAX (1u << 24)
+#define OBS_CHUNK 64u               /* observations a warp takes from the global counter at once */
+#define FOUND_NONE 0xFFFFFFFFFFFFFFFFull
+
+enum { IDLE = 0, SEARCH = 1, REPLAY = 2 };
+
+struct Smem {
+    double *scale, *s, *cum, *z2;
+    long long *zacc; unsigned int *Nacc, *Bacc;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char *raw, int n) {
+    Smem sm; double *d = reinterpret_cast<double *>(raw);
+    sm.scale = d; d += n;
+    sm.s = d; d += n;
+    sm.cum = d; d += (n + 1) * (n + 1);
+    sm.z2 = d; d += n * MHRS_THREADS;
+    sm.zacc = reinterpret_cast<long long *>(d); d += n;
+    sm.Nacc = reinterpret_cast<unsigned int *>(d);
+    sm.Bacc = sm.Nacc + n * n;
+    return sm;
+}
+size_t pht_mhrs_smem_bytes(int n) {
+    return sizeof(double) * (size_t)(2 * n + (n + 1) * (n + 1) + n * MHRS_THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n);
+}
+
+struct Lane {
+    double y, t, lastt, spare;
+    uint32_t obs_local, obs_global;
+    uint32_t a, b;              /* attempt (= sub-stream) and next Philox block inside it */
+    uint32_t cur_a, tries;
+    int j, B;
+    int mode;
+    int cur_pre, kprop;
+    bool cens, odd, fresh, off, have_cur, cur_off;
+};
+
+/* position the lane on the first draw of attempt L.a; off = the MH accept uniform of the
+ * previous proposal occupies draw 0 of this sub-stream (src/Simulate_AbsCTMC_eq_Bladt_MHRS.c:79) */
+__device__ __forceinline__ void begin_attempt(Lane &L, const SweepParams &p, uint32_t iter) {
+    L.fresh = true; L.b = 0; L.odd = false;
+    if (L.off) {
+        pht_u32x4 r = pht_philox4x32_10(0u, L.a, L.obs_global, iter, p.k0, p.k1);
+        L.spare = pht_u01(r.v[2], r.v[3]); L.odd = true; L.b = 1;
+    }
+}
+
+/* one jump-step; returns true when the attempt ended on this step */
+template <bool RECORD>
+__device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter,
+                                          int n, int *Nout) {
+    pht_u32x4 r = pht_philox4x32_10(L.b, L.a, L.obs_global, iter, p.k0, p.k1);
+    L.b++;
+    const double f = pht_u01(r.v[0], r.v[1]), g = pht_u01(r.v[2], r.v[3]);
+    const double uA = L.odd ? L.spare : f;       /* start state / next state */
+    const double uB = L.odd ? f : g;             /* next exponential */
+    L.spare = g;
+    const int row = L.fresh ? n : L.j;
+    const int last = L.fresh ? n - 1 : n;
+    const double *c = sm.cum + row * (n + 1);
+    int k = 0;
+    while (k < last && c[k] < uA) k++;           /* reference scan: first k with running sum >= target */
+    if (L.fresh) {
+        L.fresh = false; L.j = k; L.B = k; L.t = 0.0; L.lastt = 0.0;
+    } else {
+        const bool cont = (k < n) && (L.t < L.y || L.cens);        /* gt_Bladt_MHRS.c:75,111 */
+        if (!cont) return true;
+        if (RECORD) {
+            sm.z2[L.j * MHRS_THREADS + threadIdx.x] += L.t - L.lastt;              /* :112 */
+            if (Nout) Nout[L.j + k * n]++; else atomicAdd(&sm.Nacc[L.j + k * n], 1u);   /* :113 */
+        }
+        L.lastt = L.t; L.j = k;
+    }
+    L.t = L.t + sm.scale[L.j] * (-pht_log(uB));                    /* :80, rexp(1/-S_jj) */
+    return false;
+}
+
+/* close a replayed path: gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110 */
+__device__ __forceinline__ void finish_replay(Lane &L, const SweepParams &p, const Smem &sm, int n, long out_idx) {
+    const int tid = threadIdx.x;
+    sm.z2[L.j * MHRS_THREADS + tid] += (L.cens ? L.t : L.y) - L.lastt;
+    if (p.outB != nullptr) {
+        p.outB[out_idx] = L.B;
+        p.outN[out_idx * n * n + L.j + L.j * n]++;
+        for (int i = 0; i < n; i++) p.outz[out_idx * n + i] = sm.z2[i * MHRS_THREADS + tid];
+    } else {
+        atomicAdd(&sm.Nacc[L.j + L.j * n], 1u);
+        atomicAdd(&sm.Bacc[L.B], 1u);
+        const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
+        for (int i = 0; i < n; i++) {
+            const double v = sm.z2[i * MHRS_THREADS + tid];
+            if (v != 0.0) {
+                if (!(v * zs < 4.0e18)) atomicOr(&p.state->error, 2);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&sm.zacc[i]), (unsigned long long)__double2ll_rn(v * zs));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void start_replay(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n) {
+    L.mode = REPLAY; L.a = L.cur_a; L.off = L.cur_off;
+    begin_attempt(L, p, iter);
+    for (int i = 0; i < n; i++) sm.z2[i * MHRS_THREADS + threadIdx.x] = 0.0;
+}
+
+__device__ __forceinline__ uint32_t pack_flags(const Lane &L) {
+    return (L.have_cur ? 1u : 0u) | (L.cur_off ? 2u : 0u) | (L.off ? 4u : 0u) |
+           ((uint32_t)(L.cur_pre & 0xff) << 8) | ((uint32_t)L.kprop << 16);
+}
+
+__global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31;
+    const unsigned FULL = 0xffffffffu;
+    const ModelLayout ML = ModelLayout::make(n, p.m);
+    Smem sm = carve(smem_raw, n);
+    const uint32_t iter = p.state->iter;
+
+    for (int i = tid; i < n; i += MHRS_THREADS) { sm.scale[i] = p.model[ML.scale + i]; sm.s[i] = p.model[ML.s + i]; sm.zacc[i] = 0; sm.Bacc[i] = 0u; }
+    for (int i = tid; i < (n + 1) * (n + 1); i += MHRS_THREADS) sm.cum[i] = p.model[ML.cum + i];
+    for (int i = tid; i < n * n; i += MHRS_THREADS) sm.Nacc[i] = 0u;
+    __syncthreads();
+
+    unsigned long long c_attempts = 0, c_jumps = 0, c_paths = 0, c_deferred = 0;
+    const bool per_obs = p.outB != nullptr;
+    const unsigned long long obs_begin = per_obs ? (unsigned long long)p.first : 0ull;
+    const unsigned long long obs_end = per_obs ? (unsigned long long)(p.first + p.count) : (unsigned long long)p.l_local;
+    const uint32_t cap = (uint32_t)p.mhrs_cap;
+
+    /* ---------------------------------------------------------------- lane phase */
+    {
+        Lane L; L.mode = IDLE; L.tries = 0;
+        unsigned long long chunk_next = 0, chunk_end = 0;      /* warp-uniform */
+        bool exhausted = false;
+        for (;;) {
+            unsigned idle = __ballot_sync(FULL, L.mode == IDLE);
+            if (idle && !exhausted) {
+                if (chunk_next == chunk_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = obs_begin + atomicAdd(&p.state->next_obs, (unsigned long long)OBS_CHUNK);
+                    base = __shfl_sync(FULL, base, 0);
+                    chunk_next = base < obs_end ? base : obs_end;
+                    chunk_end = base + OBS_CHUNK < obs_end ? base + OBS_CHUNK : obs_end;
+                    if (chunk_next == chunk_end) exhausted = true;
+                }
+                const unsigned avail = (unsigned)(chunk_end - chunk_next);
+                const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                if (L.mode == IDLE && rank < avail) {
+                    L.obs_local = (uint32_t)(chunk_next + rank);
+                    L.obs_global = p.obs_rank + L.obs_local * p.obs_world;
+                    L.y = p.y[L.obs_local]; L.cens = p.cens[L.obs_local] != 0;
+                    L.mode = SEARCH; L.a = 0; L.off = false; L.have_cur = false; L.kprop = 0; L.tries = 0;
+                    L.cur_a = 0; L.cur_off = false; L.cur_pre = 0;
+                    begin_attempt(L, p, iter);
+                }
+                const unsigned taken = __popc(idle) < avail ? __popc(idle) : avail;
+                chunk_next += taken;
+                idle = __ballot_sync(FULL, L.mode == IDLE);
+            }
+            if (idle == FULL) { if (exhausted) break; else continue; }
+            if (L.mode == IDLE) continue;
+
+            bool ended;
+            int *Nout = per_obs ? p.outN + (size_t)(L.obs_local - p.first) * n * n : nullptr;
+            if (L.mode == REPLAY) ended = jump_step<true>(L, p, sm, iter, n, Nout);
+            else ended = jump_step<false>(L, p, sm, iter, n, nullptr);
+            c_jumps++;
+            if (!ended) continue;
+
+            if (L.mode == REPLAY) {
+                finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
+                c_paths++; L.mode = IDLE;
+                continue;
+            }
+            /* SEARCH: an attempt just ended (gt_Bladt_MHRS.c:49 decides whether it survives) */
+            c_attempts++; L.tries++;
+            const bool ok = (L.t >= L.y) && (sm.s[L.j] != 0.0);            /* eq_Bladt_MHRS.c:66,74 */
+            if (!ok) {
+                L.a++; L.off = false;
+                if (cap != 0u && L.tries >= cap) {
+                    const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
+                    if (idx < p.item_cap) {
+                        TailItem it; it.obs_local = L.obs_local; it.a = L.a; it.cur_a = L.cur_a; it.flags = pack_flags(L);
+                        p.items[idx] = it; p.found[idx] = FOUND_NONE;
+                    } else atomicOr(&p.state->error, 4);
+                    c_deferred++; L.mode = IDLE;
+                } else begin_attempt(L, p, iter);
+                continue;
+            }
+            const int pre = L.j;
+            if (!L.have_cur) {
+                L.have_cur = true; L.cur_a = L.a; L.cur_off = L.off; L.cur_pre = pre;
+                if (L.cens || p.mhit == 0) { start_replay(L, p, sm, iter, n); continue; }      /* :70 */
+                L.a++; L.off = false; begin_attempt(L, p, iter);
+                continue;
+            }
+            /* a valid proposal: accept test with draw 0 of the next sub-stream (:79-82) */
+            pht_u32x4 r = pht_philox4x32_10(0u, L.a + 1u, L.obs_global, iter, p.k0, p.k1);
+            const double U = pht_u01(r.v[0], r.v[1]);
+            if (U < sm.s[pre] / sm.s[L.cur_pre]) { L.cur_a = L.a; L.cur_off = L.off; L.cur_pre = pre; }
+            L.kprop++;
+            if (L.kprop >= p.mhit) { start_replay(L, p, sm, iter, n); continue; }
+            L.a++; L.off = true; begin_attempt(L, p, iter);
+        }
+    }
+
+    /* ---------------------------------------------------------------- tail phase */
+    grid.sync();
+    const uint32_t n_items = p.state->n_items < p.item_cap ? p.state->n_items : p.item_cap;
+    if (n_items != 0u) {
+        const unsigned long long gtid = (unsigned long long)blockIdx.x * MHRS_THREADS + tid;
+        const unsigned long long gsize = (unsigned long long)gridDim.x * MHRS_THREADS;
+        for (unsigned long long i = gtid; i < n_items; i += gsize) p.pend0[i] = (uint32_t)i;
+        if (gtid == 0) { p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u; }
+        grid.sync();
+        uint32_t K = TAIL_K0; int cur = 0; unsigned rounds = 0;
+        for (;;) {
+            const uint32_t P = p.state->n_pend[cur];
+            if (P == 0u) break;
+            const uint32_t *pend = cur ? p.pend1 : p.pend0;
+            uint32_t *pend_next = cur ? p.pend0 : p.pend1;
+            const unsigned long long rpi = K / RUN_LEN, total_runs = (unsigned long long)P * rpi;
+            /* --- search: lanes take 32-attempt runs; the first surviving attempt wins */
+            {
+                Lane L; L.mode = IDLE;
+                uint32_t item = 0, a_end = 0; bool out_of_runs = false;
+                for (;;) {
+                    unsigned idle = __ballot_sync(FULL, L.mode == IDLE);
+                    if (idle && !out_of_runs) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(&p.state->unit_counter, (unsigned long long)__popc(idle));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (base >= total_runs) out_of_runs = true;
+                        const unsigned long long run = base + __popc(idle & ((1u << lane) - 1u));
+                        if (L.mode == IDLE && run < total_runs) {
+                            item = pend[run / rpi];
+                            const TailItem it = p.items[item];
+                            L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
+                            L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
+                            L.a = it.a + (uint32_t)(run % rpi) * RUN_LEN; a_end = L.a + RUN_LEN;
+                            L.off = (L.a == it.a) && (it.flags & 4u);
+                            if ((p.found[item] >> 8) >= (unsigned long long)L.a) { L.mode = SEARCH; begin_attempt(L, p, iter); }
+                        }
+                        idle = __ballot_sync(FULL, L.mode == IDLE);
+                    }
+                    if (idle == FULL) { if (out_of_runs) break; else continue; }
+                    if (L.mode == IDLE) continue;
+                    const bool ended = jump_step<false>(L, p, sm, iter, n, nullptr);
+                    c_jumps++;
+                    if (!ended) continue;
+                    c_attempts++;
+                    if ((L.t >= L.y) && (sm.s[L.j] != 0.0)) {
+                        atomicMin(&p.found[item], ((unsigned long long)L.a << 8) | (unsigned long long)L.j);
+                        L.mode = IDLE;
+                    } else {
+                        L.a++; L.off = false;
+                        if (L.a >= a_end || (p.found[item] >> 8) < (unsigned long long)L.a) L.mode = IDLE;
+                        else begin_attempt(L, p, iter);
+                    }
+                }
+            }
+            grid.sync();
+            /* --- advance each pending observation's MH state machine (eq_Bladt_MHRS.c:65-101) */
+            for (unsigned long long i = gtid; i < P; i += gsize) {
+                const uint32_t item = pend[i];
+                TailItem it = p.items[item];
+                const unsigned long long f = p.found[item];
+                bool done = false;
+                bool dropped = false;
+                if (f == FOUND_NONE) {
+                    if (it.a > 0xF0000000u - K) { atomicOr(&p.state->error, 8); dropped = true; }   /* survival probability ~ 0 */
+                    it.a += K; it.flags &= ~4u;
+                }
+                else {
+                    const uint32_t a = (uint32_t)(f >> 8); const int pre = (int)(f & 0xffull);
+                    const bool off = (a == it.a) && (it.flags & 4u);
+                    const bool cens = p.cens[it.obs_local] != 0;
+                    bool have_cur = it.flags & 1u; bool cur_off = it.flags & 2u;
+                    int cur_pre = (int)((it.flags >> 8) & 0xffu); uint32_t kprop = it.flags >> 16;
+                    bool next_off = false;
+                    if (!have_cur) {
+                        have_cur = true; it.cur_a = a; cur_off = off; cur_pre = pre;
+                        done = cens || p.mhit == 0;
+                    } else {
+                        const uint32_t og = p.obs_rank + it.obs_local * p.obs_world;
+                        pht_u32x4 r = pht_philox4x32_10(0u, a + 1u, og, iter, p.k0, p.k1);
+                        const double U = pht_u01(r.v[0], r.v[1]);
+                        if (U < sm.s[pre] / sm.s[cur_pre]) { it.cur_a = a; cur_off = off; cur_pre = pre; }
+                        kprop++; done = (int)kprop >= p.mhit; next_off = true;
+                    }
+                    it.a = a + 1u;
+                    it.flags = (have_cur ? 1u : 0u) | (cur_off ? 2u : 0u) | (next_off ? 4u : 0u) |
+                               ((uint32_t)(cur_pre & 0xff) << 8) | (kprop << 16);
+                    p.found[item] = FOUND_NONE;
+                }
+                p.items[item] = it;
+                if (dropped) continue;
+                if (done) p.done[atomicAdd(&p.state->n_done, 1u)] = item;
+                else pend_next[atomicAdd(&p.state->n_pend[cur ^ 1], 1u)] = item;
+            }
+            if (gtid == 0) { p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; }
+            grid.sync();
+            cur ^= 1; rounds++;
+            K = (K < TAIL_KMAX) ? K * 2u : K;
+        }
+        /* --- replay the accepted attempt of every tail observation */
+        {
+            const uint32_t n_done = p.state->n_done;
+            for (unsigned long long i = gtid; i < n_done; i += gsize) {
+                const TailItem it = p.items[p.done[i]];
+                Lane L;
+                L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
+                L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
+                L.cur_a = it.cur_a; L.cur_off = it.flags & 2u;
+                start_replay(L, p, sm, iter, n);
+                int *Nout = per_obs ? p.outN + (size_t)(L.obs_local - p.first) * n * n : nullptr;
+                while (!jump_step<true>(L, p, sm, iter, n, Nout)) c_jumps++;
+                c_jumps++;
+                finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
+                c_paths++;
+            }
+        }
+        if (gtid == 0) atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
+    }
+
+    /* ---------------------------------------------------------------- block -> global statistics */
+    __syncthreads();
+    if (!per_obs) {
+        unsigned long long *gN = reinterpret_cast<unsigned long long *>(p.stats);
+        for (int i = tid; i < n * n; i += MHRS_THREADS) if (sm.Nacc[i]) atomicAdd(&gN[i], (unsigned long long)sm.Nacc[i]);
+        for (int i = tid; i < n; i += MHRS_THREADS) {
+            if (sm.Bacc[i]) atomicAdd(&gN[n * n + i], (unsigned long long)sm.Bacc[i]);
+            if (sm.zacc[i]) atomicAdd(&gN[n * n + n + i], (unsigned long long)sm.zacc[i]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c_attempts += __shfl_down_sync(FULL, c_attempts, o); c_jumps += __shfl_down_sync(FULL, c_jumps, o);
+        c_paths += __shfl_down_sync(FULL, c_paths, o); c_deferred += __shfl_down_sync(FULL, c_deferred, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&p.state->counters[PHT_CNT_ATTEMPTS], c_attempts); atomicAdd(&p.state->counters[PHT_CNT_JUMPS], c_jumps);
+        atomicAdd(&p.state->counters[PHT_CNT_PATHS], c_paths); atomicAdd(&p.state->counters[PHT_CNT_DEFERRED], c_deferred);
+    }
+}
+
+int pht_mhrs_grid_blocks(int device, int n) {
+    int per_sm = 0, sms = 0;
+    const size_t smem = pht_mhrs_smem_bytes(n);
+    if (cudaFuncSetAttribute(k_mhrs_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mhrs_sweep, MHRS_THREADS, smem) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    return per_sm * sms;
+}
+
+cudaError_t pht_launch_mhrs(const SweepParams &p, int grid_blocks, cudaStream_t st) {
+    SweepParams q = p;
+    void *args[] = { &q };
+    return cudaLaunchCooperativeKernel((const void *)k_mhrs_sweep, dim3(grid_blocks), dim3(MHRS_THREADS), args,
+                                       pht_mhrs_smem_bytes(p.n), st);
+}

@@ -1,0 +1,116 @@
+/*
+ * k_model.cu -- the two single-block kernels that bracket every sweep so the
+ * whole Gibbs iteration stays on the device (no host round trip):
+ *
+ *   k_assemble  theta -> TT, S, s (reference src/PHT_MCMC_Aslett.c:209-246 for the
+ *               start values, :365-397 afterwards), embedded chain P / Pfull
+ *               (:280-297), rexp scales, running-sum tables for the categorical
+ *               scans, and zeroing of the statistics block;
+ *   k_update    gather Nsum / zsum per parameter (:340-355) and the conjugate
+ *               Gamma draw (:365-366) from the Philox parameter stream.
+ *
+ * Row i of every matrix is handled by thread i with the reference's own loop
+ * order, so each value is bit-identical to the host computation.
+ */
+#include "engine_internal.h"
+#include "pht_philox.h"
+
+__global__ void __launch_bounds__(64) k_assemble(UpdateParams p) {
+    const int n = p.n, n1 = n + 1, tid = threadIdx.x;
+    const ModelLayout L = ModelLayout::make(n, p.m);
+    double *M = p.model;
+    const double *theta = M + L.theta;
+    double *TT = M + L.TT, *S = M + L.S, *s = M + L.s;
+    const bool first = p.state->first_assembly != 0;
+
+    for (int i = tid; i < stats_len(n); i += blockDim.x) p.stats[i] = 0;
+    if (tid == 0) {
+        p.state->next_obs = 0ull; p.state->unit_counter = 0ull;
+        p.state->n_items = 0u; p.state->n_pend[0] = 0u; p.state->n_pend[1] = 0u; p.state->n_done = 0u;
+    }
+    if (tid <= n) {
+        const int i = tid;
+        for (int j = 0; j <= n; j++) {
+            const int v = p.T[i + j * n1];
+            if (j != i || v != 0) TT[i + j * n1] = v ? theta[v - 1] * p.C[i + j * n1] : 0.0;
+        }
+        /* diagonal = -(row sum): ascending columns when assembled from the start
+         * values (:215,229), descending afterwards (TTDiag is a prepend list, :226,389-393) */
+        double acc = 0.0;
+        if (first) { for (int j = 0; j <= n; j++) if (p.T[i + j * n1] != 0) acc -= TT[i + j * n1]; }
+        else       { for (int j = n; j >= 0; j--) if (p.T[i + j * n1] != 0) acc -= TT[i + j * n1]; }
+        if (i < n || first) TT[i + i * n1] = acc;
+    }
+    __syncthreads();
+    if (tid < n) {
+        const int i = tid;
+        for (int j = 0; j < n; j++) S[i + j * n] = TT[i + j * n1];
+        s[i] = TT[i + n * n1];
+        const double Sii = S[i + i * n];
+        M[L.scale + i] = 1.0 / -Sii;
+        /* embedded chain, src/PHT_MCMC_Aslett.c:280-297 */
+        double *P = M + L.P, *Pf = M + L.Pfull;
+        double rsumfull = 0.0;
+        for (int j = 0; j < n; j++) {
+            const double v = -S[i + j * n] / Sii;
+            P[i + j * n] = v; Pf[i + j * n] = v;
+            rsumfull += v;
+        }
+        const double rsum = rsumfull - P[i + i * n];
+        Pf[i + n * n] = -s[i] / Sii;
+        rsumfull += Pf[i + n * n];
+        rsumfull -= Pf[i + i * n];
+        Pf[i + i * n] = 0.0; P[i + i * n] = 0.0;
+        for (int j = 0; j < n; j++) {
+            P[i + j * n] = P[i + j * n] / rsum;
+            Pf[i + j * n] = Pf[i + j * n] / rsumfull;
+        }
+        Pf[i + n * n] = Pf[i + n * n] / rsumfull;
+        /* running sums in scan order: cum[i][k] = ((p0 + p1) + ...) + pk */
+        double *cum = M + L.cum + i * n1;
+        double sofar = 0.0;
+        for (int k = 0; k <= n; k++) { sofar += Pf[i + k * n]; cum[k] = sofar; }
+    }
+    if (tid == n) {
+        /* start distribution is fixed to e1 in the reference (src/PHT_MCMC_Aslett.c:190-193) */
+        double *pi = M + L.pi, *cum = M + L.cum + n * n1;
+        double sofar = 0.0;
+        for (int k = 0; k < n; k++) { pi[k] = (k == 0) ? 1.0 : 0.0; sofar += pi[k]; cum[k] = sofar; }
+        cum[n] = sofar;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_update(UpdateParams p) {
+    const int n = p.n, n1 = n + 1, m = p.m;
+    const ModelLayout L = ModelLayout::make(n, m);
+    const uint32_t iter = p.state->iter;
+    const uint32_t row = p.state->res_row;
+    const long long *Nacc = p.stats, *zfix = p.stats + n * n + n;
+    const double zscale = pht_u2d((uint64_t)(1023 - p.zbits) << 52);      /* 2^-zbits */
+    for (int v = threadIdx.x; v < m; v += blockDim.x) {
+        long long Nsum = 0; double zsum = 0.0;
+        /* the reference walks prepend lists, i.e. cells in reverse insertion order (:340-355) */
+        for (int c = p.var_ptr[v + 1] - 1; c >= p.var_ptr[v]; c--) {
+            const int i = p.cell_i[c], j = p.cell_j[c];
+            Nsum += (j == n) ? Nacc[i + i * n] : Nacc[i + j * n];
+            const double zi = (double)zfix[i] * zscale;
+            zsum += zi / p.C[i + j * n1];
+        }
+        pht_stream st; st.k0 = p.k0; st.k1 = p.k1;
+        pht_stream_seek(&st, iter, PHT_OBS_PARAM, (uint32_t)v, 0);
+        const double th = pht_rgamma(&st, p.nu[v] + (double)Nsum, 1.0 / (p.zeta[v] + zsum));   /* :366 */
+        p.model[L.theta + v] = th;
+        if (p.res != nullptr && row < (uint32_t)p.res_rows) p.res[(size_t)row * m + v] = th;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { p.state->iter = iter + 1; p.state->first_assembly = 0; p.state->res_row = row + 1; }
+}
+
+cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st) {
+    k_assemble<<<1, 64, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st) {
+    k_update<<<1, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}

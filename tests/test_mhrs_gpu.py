@@ -1,0 +1,82 @@
+"""Tier-1 parity of the CUDA MHRS path against the oracle (and, where the reference build is
+present, the unmodified reference C): per-observation B, N and z must be bit-identical."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine_paths(R, s, y, cens, mhit, seed, it, cap, world=1, rank=0):
+    import phasetype_b200 as pb
+    n = s.shape[0]
+    T, C, theta = util.general_model(R, s)
+    m = theta.shape[0]
+    idx = np.arange(rank, y.shape[0], world)
+    eng = pb.Engine(n, T, C, np.full(m, 2.0), np.full(m, 2.0), y[idx], cens[idx], method=1, mhit=mhit, seed=seed,
+                    rank=rank, world=world, mhrs_cap=cap, sum_y_global=float(y.sum()))
+    eng.set_theta(theta, next_iter=it)
+    B, N, z = eng.paths()
+    mdl = eng.model()
+    cnt = eng.counters()
+    eng.close()
+    return B, N, z, mdl, cnt, idx
+
+
+@pytest.mark.parametrize("n,mhit,cap,frac_cens", [(3, 1, 256, 0.0), (4, 2, 4, 0.2), (8, 1, 16, 0.2), (8, 0, 256, 0.5),
+                                                 (16, 1, 8, 0.2), (32, 3, 32, 0.1)])
+def test_paths_match_oracle(n, mhit, cap, frac_cens):
+    rng = np.random.default_rng(100 + n)
+    R, s = util.dense_rates(n, rng)
+    l = 3000
+    y = rng.exponential(1.2, l) + 0.01      # absorption-time scale ~ 1/mean(s), whatever n is
+    cens = (rng.uniform(size=l) < frac_cens).astype(np.int32)
+    B, N, z, mdl, cnt, _ = _engine_paths(R, s, y, cens, mhit, seed=0xABCDEF12345, it=7, cap=cap)
+    Bo, No, zo, co = po.mhrs_paths("oracle", 0xABCDEF12345, 7, y, cens, mdl["S"], mdl["s"], mhit=mhit)
+    assert np.array_equal(B, Bo)
+    assert np.array_equal(N, No)
+    assert np.array_equal(z, zo)            # bit-exact, not a tolerance
+    if po.have_ref():
+        Br, Nr, zr, _ = po.mhrs_paths("ref", 0xABCDEF12345, 7, y, cens, mdl["S"], mdl["s"], mhit=mhit)
+        assert np.array_equal(B, Br) and np.array_equal(N, Nr) and np.array_equal(z, zr)
+    if cap < 64:
+        assert cnt["deferred"] > 0          # the cooperative tail was exercised
+
+
+def test_coxian_heavy_tail_and_shards():
+    """4-phase Coxian (config 2 shape): a few observations need thousands of attempts; sharded engines
+    must reproduce the single-engine result observation by observation (Philox keys are global)."""
+    rng = np.random.default_rng(7)
+    R, s = util.coxian_rates(4)
+    y = util.simulate_pht(R, s, 4000, rng)
+    cens = np.zeros(4000, dtype=np.int32)
+    B, N, z, mdl, cnt, _ = _engine_paths(R, s, y, cens, 1, seed=99, it=3, cap=64)
+    Bo, No, zo, _ = po.mhrs_paths("oracle", 99, 3, y, cens, mdl["S"], mdl["s"], mhit=1)
+    assert np.array_equal(B, Bo) and np.array_equal(N, No) and np.array_equal(z, zo)
+    assert cnt["deferred"] > 0 and cnt["tail_rounds"] > 0
+    for rank in range(2):
+        Br, Nr, zr, _, _, idx = _engine_paths(R, s, y, cens, 1, seed=99, it=3, cap=64, world=2, rank=rank)
+        assert np.array_equal(Br, Bo[idx]) and np.array_equal(Nr, No[idx]) and np.array_equal(zr, zo[idx])
+
+
+def test_sweep_stats_equal_sum_of_paths():
+    rng = np.random.default_rng(11)
+    n = 8
+    R, s = util.dense_rates(n, rng)
+    T, C, theta = util.general_model(R, s)
+    l = 20000
+    y = rng.exponential(2.0, l) + 0.01
+    cens = (rng.uniform(size=l) < 0.2).astype(np.int32)
+    import phasetype_b200 as pb
+    eng = pb.Engine(n, T, C, np.full(theta.shape[0], 2.0), np.full(theta.shape[0], 2.0), y, cens, method=1, mhit=1,
+                    seed=5, mhrs_cap=32)
+    eng.set_theta(theta, next_iter=1)
+    Nacc, Bacc, zfix = eng.sweep_stats()
+    B, N, z = eng.paths()
+    assert np.array_equal(Nacc, N.astype(np.int64).sum(0))
+    assert np.array_equal(Bacc, np.bincount(B, minlength=n))
+    zf = np.rint(z * 2.0 ** eng.zbits).astype(np.int64).sum(0)
+    assert np.array_equal(zfix, zf)
+    eng.close()

@@ -1,0 +1,51 @@
+"""Shared helpers for the tests: synthetic phase-type models in LJMA_Gibbs argument form."""
+import numpy as np
+
+
+def dense_rates(n, rng, symmetric=False, lo=0.2, hi=1.2):
+    """Off-diagonal rates R (n x n, zero diagonal) and exit rates s."""
+    R = rng.uniform(lo, hi, (n, n))
+    if symmetric:
+        R = (R + R.T) / 2
+    np.fill_diagonal(R, 0.0)
+    s = rng.uniform(lo, hi, n)
+    return R, s
+
+
+def coxian_rates(n, early_exit=0.3, last_exit=1.5):
+    """forward rates 1.0 + 0.37 i, early-exit rate, last exit."""
+    R = np.zeros((n, n)); s = np.full(n, early_exit)
+    for i in range(n - 1):
+        R[i, i + 1] = 1.0 + 0.37 * i
+    s[n - 1] = last_exit
+    return R, s
+
+
+def general_model(R, s):
+    """Every non-zero rate is its own parameter.  Returns (T, C, theta): T, C column-major (n+1)^2
+    in the reference's encoding (R/phtMCMC2.R:58-63) with parameters numbered column-major."""
+    n = s.shape[0]
+    T = np.zeros((n + 1, n + 1), dtype=np.int32)
+    theta = []
+    for j in range(n + 1):
+        for i in range(n):
+            v = s[i] if j == n else R[i, j]
+            if v != 0.0 and i != j:
+                theta.append(v); T[i, j] = len(theta)
+    C = np.ones((n + 1, n + 1))
+    return T.ravel(order="F").copy(), C.ravel(order="F").copy(), np.array(theta)
+
+
+def simulate_pht(R, s, size, rng):
+    """Absorption times of the CTMC started in state 0 (plain numpy, test data only)."""
+    n = s.shape[0]
+    rate = R.sum(1) + s
+    P = np.concatenate([R, s[:, None]], axis=1) / rate[:, None]
+    out = np.zeros(size)
+    for k in range(size):
+        j = 0; t = 0.0
+        while j < n:
+            t += rng.exponential(1.0 / rate[j])
+            j = rng.choice(n + 1, p=P[j])
+        out[k] = t
+    return out
