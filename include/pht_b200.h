@@ -106,7 +106,9 @@ int pht_engine_get_model(pht_engine *e, double *S, double *s, double *P, double 
 /* event counters accumulated since creation (index meaning: PHT_CNT_*) */
 enum { PHT_CNT_PATHS = 0, PHT_CNT_ATTEMPTS, PHT_CNT_JUMPS, PHT_CNT_DENS_EVALS, PHT_CNT_ENV_UPDATES,
        PHT_CNT_BRENT_EVALS, PHT_CNT_ARMS_CALLS, PHT_CNT_METROP_REJECTS, PHT_CNT_NONFINITE,
-       PHT_CNT_DEFERRED, PHT_CNT_TAIL_ROUNDS, PHT_CNT_ERRORS, PHT_CNT_LAUNCHES, PHT_CNT_COUNT = 16 };
+       PHT_CNT_DEFERRED, PHT_CNT_TAIL_ROUNDS, PHT_CNT_ERRORS, PHT_CNT_LAUNCHES,
+       PHT_CNT_NS_LANE, PHT_CNT_NS_TAIL, PHT_CNT_NS_REPLAY,   /* device-timer ns spent in the MHRS kernel phases */
+       PHT_CNT_COUNT = 16 };
 int pht_engine_counters(pht_engine *e, unsigned long long *out);
 
 /* measurement helpers ------------------------------------------------------- */

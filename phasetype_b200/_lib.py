@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpht_b200.so")
+LIB_PATH = os.environ.get("PHT_B200_LIB") or os.path.join(HERE, "libpht_b200.so")
 
 # every symbol include/pht_b200.h declares (tests check the export list against the header)
 SYMBOLS = [
@@ -21,7 +21,7 @@ SYMBOLS = [
     "pht_engine_counters", "pht_fp64_fma_rate",
 ]
 CNT_NAMES = ["paths", "attempts", "jumps", "dens_evals", "env_updates", "brent_evals", "arms_calls",
-             "metrop_rejects", "nonfinite", "deferred", "tail_rounds", "errors", "launches"]
+             "metrop_rejects", "nonfinite", "deferred", "tail_rounds", "errors", "launches", "ns_lane", "ns_tail", "ns_replay"]
 N_CNT = 16
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

@@ -28,8 +28,12 @@ def _newer(src_list, target):
     return any(os.path.getmtime(s) > t for s in src_list)
 
 
-def build(force=False, verbose=False, ptxas_info=False):
+def build(force=False, verbose=False, ptxas_info=False, out=None, defines=()):
+    """defines/out: build an experimental variant (e.g. defines=("-DMHRS_MIN_BLOCKS=4",)) next to the default library."""
+    global OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if out is not None:
+        OUT = os.path.join(HERE, out); force = True
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pht_b200.h"), __file__]
     if not force and not _newer(deps, OUT):
         return OUT
@@ -38,7 +42,7 @@ def build(force=False, verbose=False, ptxas_info=False):
     objs = []
     for f in CU:
         o = os.path.join(objdir, f + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", os.path.join(CSRC, f), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", os.path.join(CSRC, f), "-o", o]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
@@ -58,4 +62,6 @@ def build(force=False, verbose=False, ptxas_info=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))
+    _defs = tuple(a for a in sys.argv[1:] if a.startswith("-D"))
+    _out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv, out=_out, defines=_defs))

@@ -38,6 +38,9 @@
 namespace cg = cooperative_groups;
 
 #define MHRS_THREADS 256
+#ifndef MHRS_MIN_BLOCKS
+#define MHRS_MIN_BLOCKS 3                /* 80 registers: 24 warps per SM */
+#endif
 #define RUN_LEN 32u                 /* attempts per tail work unit */
 #define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
 #define TAIL_KMAX (1u << 24)
@@ -50,6 +53,10 @@ struct Smem {
     double *scale, *s, *cum, *z2;
     long long *zacc; unsigned int *Nacc, *Bacc;
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
 
 __device__ __forceinline__ Smem carve(unsigned char *raw, int n) {
     Smem sm; double *d = reinterpret_cast<double *>(raw);
@@ -87,34 +94,44 @@ __device__ __forceinline__ void begin_attempt(Lane &L, const SweepParams &p, uin
     }
 }
 
-/* one jump-step; returns true when the attempt ended on this step */
-template <bool RECORD>
-__device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter,
-                                          int n, int *Nout) {
+/* one jump-step; returns true when the attempt ended on this step.  Written without control flow around
+ * the expensive parts (Philox, scan, log): fresh, running, ending, searching and replaying lanes all run the
+ * same instructions and differ only in selects, so a warp never serialises copies of this code. */
+__device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n, int top_step) {
     pht_u32x4 r = pht_philox4x32_10(L.b, L.a, L.obs_global, iter, p.k0, p.k1);
     L.b++;
     const double f = pht_u01(r.v[0], r.v[1]), g = pht_u01(r.v[2], r.v[3]);
     const double uA = L.odd ? L.spare : f;       /* start state / next state */
     const double uB = L.odd ? f : g;             /* next exponential */
     L.spare = g;
-    const int row = L.fresh ? n : L.j;
-    const int last = L.fresh ? n - 1 : n;
+    const bool fresh = L.fresh;
+    const int row = fresh ? n : L.j;
+    const int last = fresh ? n - 1 : n;
     const double *c = sm.cum + row * (n + 1);
+    /* reference scan `while (sofar < target) sofar += p[k++]` = number of running sums below the target among
+     * the first `last` (the sums are non-decreasing): branch-free lower bound, same trip count for every lane */
     int k = 0;
-    while (k < last && c[k] < uA) k++;           /* reference scan: first k with running sum >= target */
-    if (L.fresh) {
-        L.fresh = false; L.j = k; L.B = k; L.t = 0.0; L.lastt = 0.0;
-    } else {
-        const bool cont = (k < n) && (L.t < L.y || L.cens);        /* gt_Bladt_MHRS.c:75,111 */
-        if (!cont) return true;
-        if (RECORD) {
-            sm.z2[L.j * MHRS_THREADS + threadIdx.x] += L.t - L.lastt;              /* :112 */
-            if (Nout) Nout[L.j + k * n]++; else atomicAdd(&sm.Nacc[L.j + k * n], 1u);   /* :113 */
-        }
-        L.lastt = L.t; L.j = k;
+    for (int step = top_step; step > 0; step >>= 1) {
+        const int probe = k + step;
+        const double cv = c[(probe <= last ? probe : 1) - 1];
+        k = (probe <= last && cv < uA) ? probe : k;
     }
-    L.t = L.t + sm.scale[L.j] * (-pht_log(uB));                    /* :80, rexp(1/-S_jj) */
-    return false;
+    const bool cont = (k < n) && (L.t < L.y || L.cens);             /* gt_Bladt_MHRS.c:75,111 */
+    const bool ended = !fresh && !cont;
+    const bool advance = !fresh && cont;
+    if (advance && L.mode == REPLAY) {
+        sm.z2[L.j * MHRS_THREADS + threadIdx.x] += L.t - L.lastt;                  /* :112 */
+        if (p.outN != nullptr) p.outN[(size_t)(L.obs_local - p.first) * n * n + L.j + k * n]++;
+        else atomicAdd(&sm.Nacc[L.j + k * n], 1u);                                 /* :113 */
+    }
+    const double tb = fresh ? 0.0 : L.t;
+    L.lastt = fresh ? 0.0 : (advance ? L.t : L.lastt);
+    L.j = ended ? L.j : k;
+    L.B = fresh ? k : L.B;
+    L.fresh = false;
+    const double tn = tb + sm.scale[L.j] * (-pht_log(uB));          /* :80, rexp(1/-S_jj) */
+    L.t = ended ? L.t : tn;
+    return ended;
 }
 
 /* close a replayed path: gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110 */
@@ -150,7 +167,7 @@ __device__ __forceinline__ uint32_t pack_flags(const Lane &L) {
            ((uint32_t)(L.cur_pre & 0xff) << 8) | ((uint32_t)L.kprop << 16);
 }
 
-__global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
+__global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
     const int n = p.n, tid = threadIdx.x, lane = tid & 31;
@@ -165,10 +182,12 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
     __syncthreads();
 
     unsigned long long c_attempts = 0, c_jumps = 0, c_paths = 0, c_deferred = 0;
+    const unsigned long long t_start = gtimer();
     const bool per_obs = p.outB != nullptr;
     const unsigned long long obs_begin = per_obs ? (unsigned long long)p.first : 0ull;
     const unsigned long long obs_end = per_obs ? (unsigned long long)(p.first + p.count) : (unsigned long long)p.l_local;
     const uint32_t cap = (uint32_t)p.mhrs_cap;
+    int top_step = 1; while (top_step * 2 <= n) top_step *= 2;      /* largest power of two <= n */
 
     /* ---------------------------------------------------------------- lane phase */
     {
@@ -203,10 +222,7 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
             if (idle == FULL) { if (exhausted) break; else continue; }
             if (L.mode == IDLE) continue;
 
-            bool ended;
-            int *Nout = per_obs ? p.outN + (size_t)(L.obs_local - p.first) * n * n : nullptr;
-            if (L.mode == REPLAY) ended = jump_step<true>(L, p, sm, iter, n, Nout);
-            else ended = jump_step<false>(L, p, sm, iter, n, nullptr);
+            const bool ended = jump_step(L, p, sm, iter, n, top_step);
             c_jumps++;
             if (!ended) continue;
 
@@ -220,7 +236,9 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
             const bool ok = (L.t >= L.y) && (sm.s[L.j] != 0.0);            /* eq_Bladt_MHRS.c:66,74 */
             if (!ok) {
                 L.a++; L.off = false;
-                if (cap != 0u && L.tries >= cap) {
+                /* hand over to the cooperative tail after `cap` attempts, or as soon as the observation stream has
+                 * run dry (a lone lane grinding through attempts would hold the whole grid at the barrier) */
+                if (cap != 0u && (L.tries >= cap || exhausted)) {
                     const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
                     if (idx < p.item_cap) {
                         TailItem it; it.obs_local = L.obs_local; it.a = L.a; it.cur_a = L.cur_a; it.flags = pack_flags(L);
@@ -248,7 +266,10 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
     }
 
     /* ---------------------------------------------------------------- tail phase */
+    const bool timekeeper = (blockIdx.x == 0 && tid == 0);
     grid.sync();
+    unsigned long long t_mark = 0;
+    if (timekeeper) { t_mark = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_LANE], t_mark - t_start); }
     const uint32_t n_items = p.state->n_items < p.item_cap ? p.state->n_items : p.item_cap;
     if (n_items != 0u) {
         const unsigned long long gtid = (unsigned long long)blockIdx.x * MHRS_THREADS + tid;
@@ -262,7 +283,11 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
             if (P == 0u) break;
             const uint32_t *pend = cur ? p.pend1 : p.pend0;
             uint32_t *pend_next = cur ? p.pend0 : p.pend1;
-            const unsigned long long rpi = K / RUN_LEN, total_runs = (unsigned long long)P * rpi;
+            /* run length: 32 attempts per work unit while there is plenty of work, down to single attempts when
+             * only a few heavy observations remain (the round is then one attempt deep instead of 32) */
+            uint32_t rl = RUN_LEN;
+            while (rl > 1u && (unsigned long long)P * (K / rl) < 2ull * gsize) rl >>= 1;
+            const unsigned long long rpi = K / rl, total_runs = (unsigned long long)P * rpi;
             /* --- search: lanes take 32-attempt runs; the first surviving attempt wins */
             {
                 Lane L; L.mode = IDLE;
@@ -276,19 +301,21 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
                         if (base >= total_runs) out_of_runs = true;
                         const unsigned long long run = base + __popc(idle & ((1u << lane) - 1u));
                         if (L.mode == IDLE && run < total_runs) {
-                            item = pend[run / rpi];
+                            /* chunk-major order: the first chunk of every pending observation is handed out before
+                             * any second chunk, so later chunks are mostly skipped once an earlier one has survived */
+                            item = pend[run % P];
                             const TailItem it = p.items[item];
                             L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
                             L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
-                            L.a = it.a + (uint32_t)(run % rpi) * RUN_LEN; a_end = L.a + RUN_LEN;
+                            L.a = it.a + (uint32_t)(run / P) * rl; a_end = L.a + rl;
                             L.off = (L.a == it.a) && (it.flags & 4u);
-                            if ((p.found[item] >> 8) >= (unsigned long long)L.a) { L.mode = SEARCH; begin_attempt(L, p, iter); }
+                            if ((__ldcg(&p.found[item]) >> 8) >= (unsigned long long)L.a) { L.mode = SEARCH; begin_attempt(L, p, iter); }
                         }
                         idle = __ballot_sync(FULL, L.mode == IDLE);
                     }
                     if (idle == FULL) { if (out_of_runs) break; else continue; }
                     if (L.mode == IDLE) continue;
-                    const bool ended = jump_step<false>(L, p, sm, iter, n, nullptr);
+                    const bool ended = jump_step(L, p, sm, iter, n, top_step);
                     c_jumps++;
                     if (!ended) continue;
                     c_attempts++;
@@ -297,7 +324,7 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
                         L.mode = IDLE;
                     } else {
                         L.a++; L.off = false;
-                        if (L.a >= a_end || (p.found[item] >> 8) < (unsigned long long)L.a) L.mode = IDLE;
+                        if (L.a >= a_end || (__ldcg(&p.found[item]) >> 8) < (unsigned long long)L.a) L.mode = IDLE;
                         else begin_attempt(L, p, iter);
                     }
                 }
@@ -346,6 +373,7 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
             cur ^= 1; rounds++;
             K = (K < TAIL_KMAX) ? K * 2u : K;
         }
+        if (timekeeper) { const unsigned long long t = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_TAIL], t - t_mark); t_mark = t; }
         /* --- replay the accepted attempt of every tail observation */
         {
             const uint32_t n_done = p.state->n_done;
@@ -356,14 +384,14 @@ __global__ void __launch_bounds__(MHRS_THREADS) k_mhrs_sweep(SweepParams p) {
                 L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
                 L.cur_a = it.cur_a; L.cur_off = it.flags & 2u;
                 start_replay(L, p, sm, iter, n);
-                int *Nout = per_obs ? p.outN + (size_t)(L.obs_local - p.first) * n * n : nullptr;
-                while (!jump_step<true>(L, p, sm, iter, n, Nout)) c_jumps++;
+                while (!jump_step(L, p, sm, iter, n, top_step)) c_jumps++;
                 c_jumps++;
                 finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
                 c_paths++;
             }
         }
         if (gtid == 0) atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
+        if (timekeeper) atomicAdd(&p.state->counters[PHT_CNT_NS_REPLAY], gtimer() - t_mark);
     }
 
     /* ---------------------------------------------------------------- block -> global statistics */

@@ -61,8 +61,10 @@ PHT_HD pht_u32x4 pht_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32
 
 /* map 64 random bits to the open interval (0,1): 52 bits, centred */
 PHT_HD double pht_u01(uint32_t lo, uint32_t hi) {
-    uint64_t x = (((uint64_t)hi << 32) | lo) >> 12;
-    return ((double)x + 0.5) * 2.220446049250313e-16;     /* 2^-52 */
+    /* (x + 0.5) * 2^-52 with x the top 52 bits, built without an int->double conversion:
+     * 1.x (a double in [1,2)) minus 1 is x * 2^-52 exactly, and adding 2^-53 is exact too */
+    const uint64_t x = (((uint64_t)hi << 32) | lo) >> 12;
+    return (pht_u2d(0x3ff0000000000000ULL | x) - 1.0) + 1.1102230246251565e-16;   /* + 2^-53 */
 }
 
 /* A positioned stream: draws are numbered 0,1,2,... inside (iter, obs, sub). */
