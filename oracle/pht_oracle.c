@@ -158,3 +158,183 @@ int pho_mhrs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long co
     free(pi); free(za); free(zb); free(Na); free(Nb);
     return 0;
 }
+
+/* ------------------------------------------------------------------ a3 / a4 */
+extern void scipy_dgeevx_(const char *, const char *, const char *, const char *, const int *, double *, const int *,
+                          double *, double *, double *, const int *, double *, const int *, int *, int *, double *,
+                          double *, double *, double *, double *, const int *, int *, int *,
+                          size_t, size_t, size_t, size_t);
+extern void scipy_dgetrf_(const int *, const int *, double *, const int *, int *, int *);
+extern void scipy_dgetri_(const int *, double *, const int *, int *, double *, const int *, int *);
+
+/* src/utility.c:87-129: S = Q diag(evals) Q^-1 through LAPACK dgeevx('B','V','V','B') and an LU inverse.
+ * The algorithm lives in LAPACK (third-party; here the copy inside scipy's OpenBLAS 0.3.x wheel), so this is a
+ * call, not a restatement; the device solver is checked against it through invariants (tests/test_spectral*.py). */
+int pho_eigen(int n, const double *S, double *evals, double *evals_im, double *Q, double *Qinv) {
+    const char B = 'B', V = 'V';
+    int info = 0, ilo, ihi, lwork = -1; double abnrm, wq;
+    double *A = (double *)malloc(sizeof(double) * n * n), *Ql = (double *)malloc(sizeof(double) * n * n);
+    double *wi = (double *)malloc(sizeof(double) * n), *scale = (double *)malloc(sizeof(double) * n);
+    double *rce = (double *)malloc(sizeof(double) * n), *rcv = (double *)malloc(sizeof(double) * n);
+    int *iwork = (int *)malloc(sizeof(int) * (2 * n + 2)), *ipiv = (int *)malloc(sizeof(int) * n);
+    memcpy(A, S, sizeof(double) * n * n);
+    scipy_dgeevx_(&B, &V, &V, &B, &n, A, &n, evals, wi, Ql, &n, Q, &n, &ilo, &ihi, scale, &abnrm, rce, rcv, &wq, &lwork, iwork, &info, 1, 1, 1, 1);
+    lwork = (int)wq; if (lwork < 4 * n * n + 64) lwork = 4 * n * n + 64;
+    double *work = (double *)malloc(sizeof(double) * lwork);
+    scipy_dgeevx_(&B, &V, &V, &B, &n, A, &n, evals, wi, Ql, &n, Q, &n, &ilo, &ihi, scale, &abnrm, rce, rcv, work, &lwork, iwork, &info, 1, 1, 1, 1);
+    if (info == 0) {
+        if (evals_im) memcpy(evals_im, wi, sizeof(double) * n);
+        memcpy(Qinv, Q, sizeof(double) * n * n);
+        scipy_dgetrf_(&n, &n, Qinv, &n, ipiv, &info);
+        if (info == 0) scipy_dgetri_(&n, Qinv, &n, ipiv, work, &lwork, &info);
+    }
+    free(A); free(Ql); free(wi); free(scale); free(rce); free(rcv); free(iwork); free(ipiv); free(work);
+    return info;
+}
+
+/* ------------------------------------------------------------------ Brent root finder */
+/* src/utility.c:233-338 (R's zeroin with f(a), f(b) supplied; Tol = 0 asks for machine precision) */
+typedef double (*pho_fn)(double x, void *ctx);
+static double brent_root(double ax, double bx, double fa, double fb, pho_fn f, void *ctx, int maxit, int *status,
+                         unsigned long long *cnt) {
+    const double EPS = 2.220446049250313e-16;
+    double a = ax, b = bx, c = a, fc = fa;
+    *status = 0;
+    if (fa == 0.0) return a;
+    if (fb == 0.0) return b;
+    for (int left = maxit + 1; left > 0; left--) {
+        const double prev_step = b - a;
+        if (fabs(fc) < fabs(fb)) { a = b; b = c; c = a; fa = fb; fb = fc; fc = fa; }
+        const double tol_act = 2 * EPS * fabs(b) + 0.0 / 2;
+        double new_step = (c - b) / 2;
+        if (fabs(new_step) <= tol_act || fb == 0.0) return b;
+        if (fabs(prev_step) >= tol_act && fabs(fa) > fabs(fb)) {
+            double p, q; const double cb = c - b;
+            if (a == c) { const double t1 = fb / fa; p = cb * t1; q = 1.0 - t1; }
+            else {
+                q = fa / fc; const double t1 = fb / fc, t2 = fb / fa;
+                p = t2 * (cb * q * (q - t1) - (b - a) * (t1 - 1.0));
+                q = (q - 1.0) * (t1 - 1.0) * (t2 - 1.0);
+            }
+            if (p > 0.0) q = -q; else p = -p;
+            if (p < (0.75 * cb * q - fabs(tol_act * q) / 2) && p < fabs(prev_step * q / 2)) new_step = p / q;
+        }
+        if (fabs(new_step) < tol_act) new_step = (new_step > 0.0) ? tol_act : -tol_act;
+        a = b; fa = fb;
+        b += new_step; fb = f(b, ctx);
+        if (cnt) cnt[PHO_C_BRENT_EVALS]++;
+        if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) { c = a; fc = fa; }
+    }
+    *status = -1;
+    return b;
+}
+
+/* ------------------------------------------------------------------ a11 / a12: DCS */
+typedef struct {
+    int n, j;               /* j = destination state of the jump being timed */
+    double prob, Pab, T, u; /* T = y - t at the start of the jump */
+    double Sll, Slj;        /* S[lastj,lastj], S[lastj,j] */
+    const double *Q, *evals, *w; double *J;
+    unsigned long long *cnt;
+} hob_ctx;
+
+/* sojourn-time CDF minus u: src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:23-40 */
+static double hob_cdf(double x, void *vp) {
+    hob_ctx *h = (hob_ctx *)vp;
+    const int n = h->n;
+    for (int i = 0; i < n; i++) {
+        if (fabs((h->evals[i] - h->Sll) / h->Sll) < 1e-13) h->J[i] = x * pht_exp(h->evals[i] * h->T);
+        else h->J[i] = (pht_exp(h->evals[i] * h->T) - pht_exp((h->T - x) * h->evals[i] + h->Sll * x)) / (h->evals[i] - h->Sll);
+    }
+    double tmp = 0.0;
+    for (int i = 0; i < n; i++) tmp += h->Q[h->j + i * n] * h->J[i] * h->w[i];
+    return 1 / h->prob * h->Slj / h->Pab * tmp - h->u;
+}
+
+/* plain-loop y = A^T x in the association order of the reference BLAS (R's default libRblas dgemv 'T') */
+static void gemv_t(int n, const double *A, const double *x, double *y) {
+    for (int j = 0; j < n; j++) {
+        double t = 0.0;
+        for (int i = 0; i < n; i++) t += A[i + j * n] * x[i];
+        y[j] = 0.0 + 1.0 * t;
+    }
+}
+
+/* src/Simulate_AbsCTMC_eq_AslettHobolth_DCS.c:11-51: end state b with weight (pi e^{Sy})_i s_i */
+static int hob_end_state(pht_stream *st, double y, int n, const double *pi, const double *Q, const double *evals,
+                         const double *Qinv, const double *s, double *p, double *tmp) {
+    gemv_t(n, Q, pi, p);
+    for (int i = 0; i < n; i++) p[i] *= pht_exp(evals[i] * y);
+    gemv_t(n, Qinv, p, tmp);
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) { p[i] = tmp[i] * s[i]; sum += p[i]; }
+    for (int i = 0; i < n; i++) p[i] = p[i] / sum;
+    return cat_scan(p, 1, n - 1, runif01(st));
+}
+
+/* src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:74-226 with w = Q^-1 e_b (column b of Q^-1, :124-130 of the caller) */
+static int hob_path(pht_stream *st, double y, int b, int n, const double *pi, const double *S, const double *Q,
+                    const double *evals, const double *w, double *z, int *N, double *J, double *p,
+                    unsigned long long *cnt) {
+    for (int i = 0; i < n; i++) z[i] = 0.0;
+    memset(N, 0, sizeof(int) * (size_t)n * n);
+    const int B = cat_scan(pi, 1, n - 1, runif01(st));                               /* :88-95 */
+    double t = 0.0; int j = B;
+    while (t < y) {                                                                  /* :112 */
+        const int lastj = j;
+        const double T = y - t, Sjj = S[j + j * n];
+        double Pab = 0.0;
+        for (int i = 0; i < n; i++) Pab += Q[j + i * n] * pht_exp(evals[i] * T) * w[i];     /* :118-121 */
+        if (j == b) {                                                                /* :124 (b[j] > 0) */
+            if (runif01(st) < pht_exp(Sjj * T) / Pab) { z[j] += T; N[j + j * n] = 1; break; }
+        }
+        for (int i = 0; i < n; i++) {                                                /* :137-144 */
+            if (fabs((evals[i] - Sjj) / Sjj) < 1e-13) J[i] = T * pht_exp(evals[i] * T);
+            else J[i] = (pht_exp(evals[i] * T) - pht_exp(Sjj * T)) / (evals[i] - Sjj);
+        }
+        double p_sum = 0.0;
+        for (int i = 0; i < n; i++) {                                                /* :148-158 */
+            if (i == j) continue;
+            double tmp = 0.0;
+            for (int k = 0; k < n; k++) tmp += Q[i + k * n] * J[k] * w[k];
+            p[i] = S[j + i * n] / Pab * tmp;
+            p_sum += p[i];
+        }
+        p[j] = 0.0;
+        const double target = (p_sum == 0.0) ? 0.0 : 0.0 + (p_sum - 0.0) * pht_stream_unif(st);   /* runif(0, p_sum), :164 */
+        j = cat_scan(p, 1, n - 1, target);
+        hob_ctx h; h.n = n; h.j = j; h.prob = p[j]; h.Pab = Pab; h.T = T; h.Sll = Sjj; h.Slj = S[lastj + j * n];
+        h.Q = Q; h.evals = evals; h.w = w; h.J = J; h.cnt = cnt;
+        h.u = runif01(st);                                                           /* :184 */
+        int status;
+        double jtime = brent_root(0.0, T, -h.u, 1.0 - h.u, hob_cdf, &h, 1000, &status, cnt);   /* :189 */
+        if (status != 0 && cnt) cnt[PHO_C_NONFINITE]++;
+        while (t + jtime >= y) jtime = jtime / 2;                                    /* :204-206 */
+        N[lastj + j * n]++; z[lastj] += jtime; t += jtime;                           /* :209-213 */
+        if (cnt) cnt[PHO_C_JUMPS]++;
+    }
+    return B;
+}
+
+int pho_dcs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                  const double *y, int n, const double *S, const double *s,
+                  const double *evals, const double *Q, const double *Qinv,
+                  int *outB, int *outN, double *outz, unsigned long long *counters) {
+    double *pi = (double *)calloc(n, sizeof(double)), *wk = (double *)calloc(4 * (size_t)n, sizeof(double));
+    double *z = (double *)calloc(n, sizeof(double)); int *N = (int *)calloc((size_t)n * n, sizeof(int));
+    if (!pi || !wk || !z || !N) return -1;
+    pi[0] = 1.0;
+    for (long k = 0; k < count; k++) {
+        pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
+        const int b = hob_end_state(&st, y[k], n, pi, Q, evals, Qinv, s, wk, wk + n);
+        const int B = hob_path(&st, y[k], b, n, pi, S, Q, evals, Qinv + (size_t)b * n, z, N, wk + 2 * n, wk + 3 * n, counters);
+        if (counters) counters[PHO_C_PATHS]++;
+        if (outB) {
+            outB[k] = B;
+            memcpy(outN + (size_t)k * n * n, N, sizeof(int) * (size_t)n * n);
+            memcpy(outz + (size_t)k * n, z, sizeof(double) * (size_t)n);
+        }
+    }
+    free(pi); free(wk); free(z); free(N);
+    return 0;
+}

@@ -169,3 +169,60 @@ def mhrs_paths(impl, seed, it, y, cens, S, s, mhit=1, obs0=0, stride=1, want=Tru
     if B is None:
         return None, None, None, counters
     return B, N.reshape(count, n * n), z.reshape(count, n), counters
+
+
+def eigen(impl, S, n):
+    """(evals, Q, Qinv) of the column-major n x n matrix S, through LAPACK as the reference does (src/utility.c:87-129)."""
+    S = _f64(S)
+    ev = np.zeros(n); Q = np.zeros(n * n); Qi = np.zeros(n * n)
+    if impl == "oracle":
+        im = np.zeros(n)
+        rc = oracle().pho_eigen(n, S, ev, im, Q, Qi)
+        if rc != 0:
+            raise RuntimeError("pho_eigen failed rc=%d" % rc)
+        if (im != 0).any():
+            raise ValueError("complex spectrum: the reference's spectral samplers are not valid for this S")
+    else:
+        rc = ref().phtref_eigen(n, S.copy(), ev, Q, Qi)
+        if rc != 0:
+            raise RuntimeError("phtref_eigen failed rc=%d" % rc)
+    return ev, Q, Qi
+
+
+def spectral_paths(impl, method, seed, it, y, cens, S, s, obs0=0, stride=1, want=True, spectral=None):
+    """ECS / DCS per-observation statistics from `impl` in {"oracle","ref"}.  `spectral` = (evals, Q, Qinv)
+    overrides the LAPACK decomposition (both implementations then consume identical numbers)."""
+    y = _f64(y); cens = _i32(cens); S = _f64(S); s = _f64(s)
+    n = s.shape[0]; count = y.shape[0]
+    ev, Q, Qi = spectral if spectral is not None else eigen("oracle", S, n)
+    ev = _f64(ev); Q = _f64(Q); Qi = _f64(Qi)
+    P, Pfull = embedded(S, s)
+    cnt = np.zeros(N_COUNTERS, dtype=np.uint64)
+    B, N, z = _out(count, n, True if impl == "oracle" else want)
+    if method == "DCS":
+        if impl == "oracle":
+            rc = oracle().pho_dcs_paths(seed, it, obs0, stride, count, y, n, S, s, ev, Q, Qi, B, N, z, cnt)
+        else:
+            rc = ref().phtref_dcs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), ev.copy(), Q.copy(),
+                                        Qi.copy(), _ptr(B), _ptr(N), _ptr(z), cnt)
+    elif method == "ECS":
+        Qm = Qi.reshape(n, n, order="F")
+        # Q^-1 s and Q^-1 1 in the reference BLAS order (src/PHT_MCMC_Aslett.c:331-332: dgemv 'N')
+        Qinv_s = np.zeros(n); Qinv_1 = np.zeros(n)
+        for j in range(n):
+            Qinv_s += s[j] * Qm[:, j]
+            Qinv_1 += 1.0 * Qm[:, j]
+        if impl == "oracle":
+            rc = oracle().pho_ecs_paths(seed, it, obs0, stride, count, y, cens, n, S, s, P, Pfull, ev, Q, Qinv_s, Qinv_1,
+                                        B, N, z, cnt)
+        else:
+            rc = ref().phtref_ecs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), P.copy(), Pfull.copy(),
+                                        ev.copy(), Q.copy(), Qinv_s, Qinv_1, _ptr(B), _ptr(N), _ptr(z), cnt)
+    else:
+        raise ValueError(method)
+    if rc != 0:
+        raise RuntimeError("%s %s paths failed rc=%d" % (impl, method, rc))
+    counters = _counters(cnt) if impl == "oracle" else {"paths": count, "uniforms": int(cnt[0]), "jumps": int(cnt[4])}
+    if B is None:
+        return None, None, None, counters
+    return B, N.reshape(count, n * n), z.reshape(count, n), counters

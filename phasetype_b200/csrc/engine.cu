@@ -68,6 +68,7 @@ struct pht_engine {
     TailItem *d_items = nullptr; uint32_t *d_pend0 = nullptr, *d_pend1 = nullptr, *d_done = nullptr;
     unsigned long long *d_found = nullptr; uint32_t item_cap = 0;
     double *d_res = nullptr; int res_rows = 0;
+    double *d_inject = nullptr;        /* host-supplied evals | Q | Qinv (parity hook), else nullptr */
     ModelLayout L;
     int grid_blocks = 0;
     /* graph */
@@ -126,15 +127,26 @@ static int method_of(const pht_config &c) {       /* dispatch priority of src/PH
 static int enqueue_paths(pht_engine *e, const SweepParams &p) {
     switch (method_of(e->cfg)) {
     case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->stream)); break;
+    case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); break;
     default: return fail("sampling method %d has no kernel in this build", e->cfg.method);
     }
     e->launches++;
     return 0;
 }
 
+/* k_assemble (+ spectral data for ECS / DCS): everything the path kernels read from the model block */
+static int enqueue_model(pht_engine *e, const UpdateParams &u) {
+    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    if (method_of(e->cfg) != PHT_METHOD_MHRS) {
+        if (e->d_inject == nullptr) return fail("no device eigen-solver in this build: call pht_engine_set_spectral first");
+        CU(pht_launch_spectral(u, e->d_inject, e->stream)); e->launches++;
+    }
+    return 0;
+}
+
 static int enqueue_sweep(pht_engine *e, double *res, int res_rows, bool time_kernel) {
     UpdateParams u = update_params(e, res, res_rows);
-    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    if (enqueue_model(e, u)) return -1;
     SweepParams p = sweep_params(e);
     if (time_kernel && e->kev_used + 2 <= (int)e->kev.size()) CU(cudaEventRecord(e->kev[e->kev_used++], e->stream));
     if (enqueue_paths(e, p)) return -1;
@@ -157,7 +169,7 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     void *bufs[] = { e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res };
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res, e->d_inject };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -238,6 +250,10 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         CUE(cudaMalloc(&e->d_found, sizeof(unsigned long long) * ln));
         e->grid_blocks = pht_mhrs_grid_blocks(cfg->device, n);
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
+    }
+    if (method_of(e->cfg) == PHT_METHOD_DCS) {
+        e->grid_blocks = pht_dcs_grid_blocks(cfg->device, n);
+        if (e->grid_blocks <= 0) { fail("DCS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
     /* sweep index 1, start-value assembly (src/PHT_MCMC_Aslett.c:268) */
     DevState st; memset(&st, 0, sizeof(st)); st.iter = 1; st.first_assembly = 1;
@@ -366,7 +382,7 @@ extern "C" int pht_engine_sweep_stats(pht_engine *e, long long *N, long long *B,
     CU(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n;
     UpdateParams u = update_params(e, nullptr, 0);
-    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    if (enqueue_model(e, u)) return -1;
     SweepParams p = sweep_params(e);
     if (enqueue_paths(e, p)) return -1;
     if (pht_engine_sync(e)) return -1;
@@ -389,7 +405,7 @@ extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, i
     CU(cudaMemsetAsync(dB, 0, sizeof(int) * count, e->stream)); CU(cudaMemsetAsync(dN, 0, sizeof(int) * count * n * n, e->stream));
     CU(cudaMemsetAsync(dz, 0, sizeof(double) * count * n, e->stream));
     UpdateParams u = update_params(e, nullptr, 0);
-    CU(pht_launch_assemble(u, e->stream)); e->launches++;
+    if (enqueue_model(e, u)) { cudaFree(dB); cudaFree(dN); cudaFree(dz); return -1; }
     SweepParams p = sweep_params(e);
     p.outB = dB; p.outN = dN; p.outz = dz; p.first = first; p.count = count;
     int rc = enqueue_paths(e, p);
@@ -404,9 +420,20 @@ extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, i
 }
 
 extern "C" int pht_engine_set_spectral(pht_engine *e, const double *evals, const double *Q, const double *Qinv) {
-    (void)evals; (void)Q; (void)Qinv;
     if (!e) return fail("null engine");
-    return fail("spectral override is not available in this build");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    const int n = e->cfg.n;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }     /* the sweep changes shape */
+    if (!evals || !Q || !Qinv) {
+        if (e->d_inject) { CU(cudaFree(e->d_inject)); e->d_inject = nullptr; }
+        return 0;
+    }
+    if (!e->d_inject) CU(cudaMalloc(&e->d_inject, sizeof(double) * (n + 2 * n * n)));
+    CU(cudaMemcpy(e->d_inject, evals, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_inject + n, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_inject + n + n * n, Qinv, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    return 0;
 }
 
 extern "C" int pht_engine_get_model(pht_engine *e, double *S, double *s, double *P, double *Pfull,

@@ -95,6 +95,10 @@ struct UpdateParams {
 cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_mhrs(const SweepParams &p, int grid_blocks, cudaStream_t st);
+cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st);
+int pht_dcs_grid_blocks(int device, int n);
+/* spectral data of the sweep: inject != nullptr copies host-supplied (evals | Q | Qinv) instead of solving on the device */
+cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st);
 int pht_mhrs_grid_blocks(int device, int n);
 size_t pht_mhrs_smem_bytes(int n);
 

@@ -106,6 +106,35 @@ __global__ void __launch_bounds__(128) k_update(UpdateParams p) {
     if (threadIdx.x == 0) { p.state->iter = iter + 1; p.state->first_assembly = 0; p.state->res_row = row + 1; }
 }
 
+/* Spectral data for ECS / DCS (reference src/utility.c:87-129 via LJMA_eigen, then the GEMVs of
+ * src/PHT_MCMC_Aslett.c:328-332).  This variant takes (evals | Q | Q^-1) supplied by the host -- the parity
+ * hook pht_engine_set_spectral -- and derives Q^-1 s and Q^-1 1 in reference-BLAS order (dgemv 'N':
+ * y_i = sum_j x_j A_ij accumulated over j). */
+__global__ void __launch_bounds__(64) k_spectral_inject(UpdateParams p, const double *inject) {
+    const int n = p.n, tid = threadIdx.x;
+    const ModelLayout L = ModelLayout::make(n, p.m);
+    double *M = p.model;
+    for (int i = tid; i < n; i += blockDim.x) M[L.evals + i] = inject[i];
+    for (int i = tid; i < n * n; i += blockDim.x) { M[L.Q + i] = inject[n + i]; M[L.Qinv + i] = inject[n + n * n + i]; }
+    __syncthreads();
+    if (tid < n) {
+        const int i = tid;
+        double ys = 0.0, y1 = 0.0;
+        for (int j = 0; j < n; j++) {
+            const double a = M[L.Qinv + i + j * n];
+            ys += (1.0 * M[L.s + j]) * a;
+            y1 += (1.0 * 1.0) * a;
+        }
+        M[L.Qinv_s + i] = ys; M[L.Qinv_1 + i] = y1;
+    }
+}
+
+cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st) {
+    if (inject == nullptr) return cudaErrorNotSupported;
+    k_spectral_inject<<<1, 64, 0, st>>>(p, inject);
+    return cudaGetLastError();
+}
+
 cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st) {
     k_assemble<<<1, 64, 0, st>>>(p);
     return cudaGetLastError();

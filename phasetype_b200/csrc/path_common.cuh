@@ -1,0 +1,105 @@
+/*
+ * path_common.cuh -- pieces shared by the per-observation path kernels (k_dcs.cu, k_ecs.cu):
+ * warp-level observation dispenser, per-path uniform stream, per-lane shared-memory slabs and
+ * the reduction of a finished path into the sweep statistics.
+ */
+#ifndef PHT_PATH_COMMON_CUH
+#define PHT_PATH_COMMON_CUH
+
+#include "engine_internal.h"
+#include "pht_philox.h"
+
+#define PATH_CHUNK 32u          /* observations a warp takes from the global counter at once */
+
+/* warp-uniform dispenser of observation indices [obs_begin, obs_end) */
+struct Dispenser {
+    unsigned long long next, end, obs_begin, obs_end;
+    bool exhausted;
+    __device__ __forceinline__ void init(const SweepParams &p) {
+        const bool per_obs = p.outB != nullptr;
+        obs_begin = per_obs ? (unsigned long long)p.first : 0ull;
+        obs_end = per_obs ? (unsigned long long)(p.first + p.count) : (unsigned long long)p.l_local;
+        next = end = 0ull; exhausted = false;
+    }
+    /* every lane of the warp calls this with the same `idle` ballot; returns the observation index for this
+     * lane or ~0ull when it got none */
+    __device__ __forceinline__ unsigned long long take(const SweepParams &p, unsigned idle, bool me_idle) {
+        const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
+        if (next == end && !exhausted) {
+            unsigned long long base = 0;
+            if (lane == 0) base = obs_begin + atomicAdd(&p.state->next_obs, (unsigned long long)PATH_CHUNK);
+            base = __shfl_sync(FULL, base, 0);
+            next = base < obs_end ? base : obs_end;
+            end = base + PATH_CHUNK < obs_end ? base + PATH_CHUNK : obs_end;
+            if (next == end) exhausted = true;
+        }
+        const unsigned avail = (unsigned)(end - next);
+        const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+        const unsigned long long mine = (me_idle && rank < avail) ? next + rank : ~0ull;
+        const unsigned cnt = __popc(idle);
+        next += cnt < avail ? cnt : avail;
+        return mine;
+    }
+};
+
+/* sequential uniforms of one path: sub-stream 0 of (iter, observation) */
+struct PathRng {
+    uint32_t obs, b; double spare; bool odd;
+    __device__ __forceinline__ void seek(uint32_t obs_global) { obs = obs_global; b = 0; odd = false; spare = 0.0; }
+    __device__ __forceinline__ double next(const SweepParams &p, uint32_t iter) {
+        if (odd) { odd = false; return spare; }
+        pht_u32x4 r = pht_philox4x32_10(b++, 0u, obs, iter, p.k0, p.k1);
+        spare = pht_u01(r.v[2], r.v[3]); odd = true;
+        return pht_u01(r.v[0], r.v[1]);
+    }
+};
+
+/* reference scan `while (sofar < target) sofar += p[k++]; k--` over a per-lane slab, bounded at n-1 */
+template <int THREADS>
+__device__ __forceinline__ int slab_scan(const double *slab, int n, double target) {
+    double sofar = 0.0; int k = 0;
+    while (sofar < target && k <= n - 1) { sofar += slab[k * THREADS + threadIdx.x]; k++; }
+    k--;
+    return k < 0 ? 0 : k;
+}
+
+/* add one finished path to the statistics (production) or write it out (parity mode) */
+template <int THREADS>
+__device__ __forceinline__ void path_flush(const SweepParams &p, int n, const double *zslab, long long *zacc,
+                                           unsigned int *Bacc, int B, long out_idx) {
+    const int tid = threadIdx.x;
+    if (p.outB != nullptr) {
+        p.outB[out_idx] = B;
+        for (int i = 0; i < n; i++) p.outz[out_idx * n + i] = zslab[i * THREADS + tid];
+    } else {
+        atomicAdd(&Bacc[B], 1u);
+        const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
+        for (int i = 0; i < n; i++) {
+            const double v = zslab[i * THREADS + tid];
+            if (v != 0.0) {
+                if (!(v * zs < 4.0e18) || !(v * zs > -4.0e18)) atomicOr(&p.state->error, 2);
+                atomicAdd(reinterpret_cast<unsigned long long *>(&zacc[i]), (unsigned long long)__double2ll_rn(v * zs));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void count_transition(const SweepParams &p, int n, unsigned int *Nacc, long out_idx, int from, int to) {
+    if (p.outN != nullptr) p.outN[(size_t)out_idx * n * n + from + to * n]++;
+    else atomicAdd(&Nacc[from + to * n], 1u);
+}
+
+/* block accumulators -> global statistics block */
+template <int THREADS>
+__device__ __forceinline__ void block_flush(const SweepParams &p, int n, const unsigned int *Nacc, const unsigned int *Bacc,
+                                            const long long *zacc) {
+    if (p.outB != nullptr) return;
+    unsigned long long *g = reinterpret_cast<unsigned long long *>(p.stats);
+    for (int i = threadIdx.x; i < n * n; i += THREADS) if (Nacc[i]) atomicAdd(&g[i], (unsigned long long)Nacc[i]);
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        if (Bacc[i]) atomicAdd(&g[n * n + i], (unsigned long long)Bacc[i]);
+        if (zacc[i]) atomicAdd(&g[n * n + n + i], (unsigned long long)zacc[i]);
+    }
+}
+
+#endif

@@ -49,3 +49,26 @@ def simulate_pht(R, s, size, rng):
             j = rng.choice(n + 1, p=P[j])
         out[k] = t
     return out
+
+
+def assemble(T, C, theta, n, first=True):
+    """S (column-major flat) and s from the parameter vector exactly as the engine's k_assemble / the reference
+    do it: cell = theta * C, diagonal = -(row sum) accumulated over ascending columns for the start values
+    (src/PHT_MCMC_Aslett.c:215,229) and over descending columns afterwards (:389-393)."""
+    n1 = n + 1
+    T = np.asarray(T).reshape(n1, n1, order="F"); C = np.asarray(C, dtype=np.float64).reshape(n1, n1, order="F")
+    TT = np.zeros((n1, n1))
+    for i in range(n1):
+        for j in range(n1):
+            if T[i, j] != 0:
+                TT[i, j] = theta[T[i, j] - 1] * C[i, j]
+    for i in range(n):
+        acc = 0.0
+        cols = range(n1) if first else range(n, -1, -1)
+        for j in cols:
+            if T[i, j] != 0:
+                acc -= TT[i, j]
+        TT[i, i] = acc
+    S = TT[:n, :n].ravel(order="F").copy()
+    s = TT[:n, n].copy()
+    return S, s
