@@ -338,3 +338,345 @@ int pho_dcs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     free(pi); free(wk); free(z); free(N);
     return 0;
 }
+
+/* ------------------------------------------------------------------ a9: ARMS (Gilks) */
+/* src/arms.c restated with index links instead of pointers.  Point 0 is always the left bound and point
+ * 2*ninit the right bound (new points are only ever inserted between them), which replaces the reference's
+ * walks to the list ends.  Constants: src/arms.c:46-49. */
+#define A_XEPS 0.00001
+#define A_YEPS 0.1
+#define A_EYEPS 0.001
+#define A_YCEIL 50.
+#define A_NPOINT 100
+#define A_NIL (-1)
+
+typedef struct { double x, y, ey, cum; int f, pl, pr; } arms_pt;
+typedef struct {
+    arms_pt p[A_NPOINT];
+    int cpoint, right;
+    double ymax, convex, xprev, yprev;
+    pho_fn f; void *ctx;
+    pht_stream *st; unsigned long long *cnt;
+} arms_env;
+
+static double a_expshift(double y, double y0) { return (y - y0 > -2.0 * A_YCEIL) ? pht_exp(y - y0 + A_YCEIL) : 0.0; }   /* :794-803 */
+static double a_logshift(double y, double y0) { return pht_log(y) + y0 - A_YCEIL; }                                      /* :807-812 */
+static double a_perfunc(arms_env *e, double x) {                                                                          /* :816-834 */
+    double y = e->f(x, e->ctx);
+    if (e->cnt) { e->cnt[PHO_C_DENS_EVALS]++; if (!isfinite(y)) e->cnt[PHO_C_NONFINITE]++; }
+    return y;
+}
+
+/* intersection of the chords either side of q: src/arms.c:659-764 (Metropolis is always on here) */
+static void a_meet(arms_env *e, int q) {
+    arms_pt *p = e->p;
+    double gl = 0.0, gr = 0.0, grl = 0.0, dl = 0.0, dr = 0.0;
+    const int pl = p[q].pl, pr = p[q].pr;
+    int il = 0, ir = 0, irl = 0;
+    if (pl != A_NIL && p[p[pl].pl].pl != A_NIL) {
+        const int a = p[p[pl].pl].pl;
+        gl = (p[pl].y - p[a].y) / (p[pl].x - p[a].x); il = 1;
+    }
+    if (pr != A_NIL && p[p[pr].pr].pr != A_NIL) {
+        const int a = p[p[pr].pr].pr;
+        gr = (p[pr].y - p[a].y) / (p[pr].x - p[a].x); ir = 1;
+    }
+    if (pl != A_NIL && pr != A_NIL) { grl = (p[pr].y - p[pl].y) / (p[pr].x - p[pl].x); irl = 1; }
+    if (irl && il && (gl < grl)) gl = gl + (1.0 + e->convex) * (grl - gl);
+    if (irl && ir && (gr > grl)) gr = gr + (1.0 + e->convex) * (grl - gr);
+    if (il && irl) { dr = (gl - grl) * (p[pr].x - p[pl].x); if (dr < A_YEPS) dr = A_YEPS; }
+    if (ir && irl) { dl = (grl - gr) * (p[pr].x - p[pl].x); if (dl < A_YEPS) dl = A_YEPS; }
+    if (il && ir && irl) {
+        p[q].x = (dl * p[pr].x + dr * p[pl].x) / (dl + dr);
+        p[q].y = (dl * p[pr].y + dr * p[pl].y + dl * dr) / (dl + dr);
+    } else if (il && irl) { p[q].x = p[pr].x; p[q].y = p[pr].y + dr; }
+    else if (ir && irl) { p[q].x = p[pl].x; p[q].y = p[pl].y + dl; }
+    else if (il) p[q].y = p[pl].y + gl * (p[q].x - p[pl].x);
+    else if (ir) p[q].y = p[pr].y - gr * (p[pr].x - p[q].x);
+}
+
+/* exponentiate and integrate the envelope: src/arms.c:625-655, area :768-790 */
+static void a_cumulate(arms_env *e) {
+    arms_pt *p = e->p;
+    e->ymax = p[0].y;
+    for (int q = p[0].pr; q != A_NIL; q = p[q].pr) if (p[q].y > e->ymax) e->ymax = p[q].y;
+    for (int q = 0; q != A_NIL; q = p[q].pr) p[q].ey = a_expshift(p[q].y, e->ymax);
+    p[0].cum = 0.;
+    for (int q = p[0].pr; q != A_NIL; q = p[q].pr) {
+        const int l = p[q].pl; double a;
+        if (p[l].x == p[q].x) a = 0.;
+        else if (fabs(p[q].y - p[l].y) < A_YEPS) a = 0.5 * (p[q].ey + p[l].ey) * (p[q].x - p[l].x);
+        else a = ((p[q].ey - p[l].ey) / (p[q].y - p[l].y)) * (p[q].x - p[l].x);
+        p[q].cum = p[l].cum + a;
+    }
+}
+
+/* x with cumulative envelope probability prob: src/arms.c:356-420 */
+static void a_invert(arms_env *e, double prob, arms_pt *w) {
+    arms_pt *p = e->p;
+    int q = e->right;
+    const double u = prob * p[q].cum;
+    while (p[q].pl != A_NIL && p[p[q].pl].cum > u) q = p[q].pl;
+    const int l = p[q].pl;
+    w->pl = l; w->pr = q; w->f = 0; w->cum = u;
+    const double prop = (u - p[l].cum) / (p[q].cum - p[l].cum);
+    if (p[l].x == p[q].x) { w->x = p[q].x; w->y = p[q].y; w->ey = p[q].ey; return; }
+    const double xl = p[l].x, xr = p[q].x, yl = p[l].y, yr = p[q].y, eyl = p[l].ey, eyr = p[q].ey;
+    if (fabs(yr - yl) < A_YEPS) {
+        if (fabs(eyr - eyl) > A_EYEPS * fabs(eyr + eyl))
+            w->x = xl + ((xr - xl) / (eyr - eyl)) * (-eyl + sqrt((1. - prop) * eyl * eyl + prop * eyr * eyr));
+        else w->x = xl + (xr - xl) * prop;
+        w->ey = ((w->x - xl) / (xr - xl)) * (eyr - eyl) + eyl;
+        w->y = a_logshift(w->ey, e->ymax);
+    } else {
+        w->x = xl + ((xr - xl) / (yr - yl)) * (-yl + a_logshift(((1. - prop) * eyl + prop * eyr), e->ymax));
+        w->y = ((w->x - xl) / (xr - xl)) * (yr - yl) + yl;
+        w->ey = a_expshift(w->y, e->ymax);
+    }
+}
+
+/* insert the evaluated point w: src/arms.c:525-621 */
+static void a_update(arms_env *e, arms_pt *w) {
+    arms_pt *p = e->p;
+    if (!w->f || e->cpoint > A_NPOINT - 2) return;
+    const int q = e->cpoint++, m = e->cpoint++;
+    p[q].x = w->x; p[q].y = w->y; p[q].f = 1;
+    p[m].f = 0;
+    if (p[w->pl].f && !p[w->pr].f) {
+        p[m].pl = w->pl; p[m].pr = q; p[q].pl = m; p[q].pr = w->pr;
+        p[p[m].pl].pr = m; p[p[q].pr].pl = q;
+    } else if (!p[w->pl].f && p[w->pr].f) {
+        p[m].pr = w->pr; p[m].pl = q; p[q].pr = m; p[q].pl = w->pl;
+        p[p[m].pr].pl = m; p[p[q].pl].pr = q;
+    } else { e->cpoint -= 2; return; }      /* "impossible" in the reference (it prints and carries on with dangling links) */
+    const int ql = (p[p[q].pl].pl != A_NIL) ? p[p[q].pl].pl : p[q].pl;
+    const int qr = (p[p[q].pr].pr != A_NIL) ? p[p[q].pr].pr : p[q].pr;
+    if (p[q].x < (1. - A_XEPS) * p[ql].x + A_XEPS * p[qr].x) {
+        p[q].x = (1. - A_XEPS) * p[ql].x + A_XEPS * p[qr].x; p[q].y = a_perfunc(e, p[q].x);
+    } else if (p[q].x > A_XEPS * p[ql].x + (1. - A_XEPS) * p[qr].x) {
+        p[q].x = A_XEPS * p[ql].x + (1. - A_XEPS) * p[qr].x; p[q].y = a_perfunc(e, p[q].x);
+    }
+    a_meet(e, p[q].pl); a_meet(e, p[q].pr);
+    if (p[p[q].pl].pl != A_NIL) a_meet(e, p[p[p[q].pl].pl].pl);
+    if (p[p[q].pr].pr != A_NIL) a_meet(e, p[p[p[q].pr].pr].pr);
+    a_cumulate(e);
+    if (e->cnt) e->cnt[PHO_C_ENV_UPDATES]++;
+}
+
+/* rejection + Metropolis tests: src/arms.c:424-521 with metrop->on; 1 = accepted (w->x is the draw) */
+static int a_test(arms_env *e, arms_pt *w) {
+    arms_pt *p = e->p;
+    const double u = pht_stream_unif(e->st) * w->ey;
+    const double y = a_logshift(u, e->ymax);
+    const double ynew = a_perfunc(e, w->x);
+    if (y >= ynew) {
+        w->y = ynew; w->ey = a_expshift(w->y, e->ymax); w->f = 1;
+        a_update(e, w);
+        return 0;
+    }
+    const double yold = e->yprev;
+    int ql = 0;
+    while (p[p[ql].pr].x < e->xprev) ql = p[ql].pr;
+    const int qr = p[ql].pr;
+    double wgt = (e->xprev - p[ql].x) / (p[qr].x - p[ql].x);
+    double zold = p[ql].y + wgt * (p[qr].y - p[ql].y);
+    double znew = w->y;
+    if (yold < zold) zold = yold;
+    if (ynew < znew) znew = ynew;
+    wgt = ynew - znew - yold + zold;
+    if (wgt > 0.0) wgt = 0.0;
+    wgt = (wgt > -A_YCEIL) ? pht_exp(wgt) : 0.0;
+    const double u2 = pht_stream_unif(e->st);
+    if (u2 > wgt) {
+        w->x = e->xprev; w->y = e->yprev; w->ey = a_expshift(w->y, e->ymax); w->f = 1; w->pl = ql; w->pr = qr;
+        if (e->cnt) e->cnt[PHO_C_METROP_REJECTS]++;
+    } else { e->xprev = w->x; e->yprev = ynew; }
+    return 1;
+}
+
+/* one ARMS draw with the settings both callers use (ninit = 4, npoint = 100, convex = 1, Metropolis on,
+ * xprev = 0): src/arms.c:115-222 + initial :226-333 */
+static double arms_draw(pht_stream *st, const double xinit[4], double xl, double xr, pho_fn f, void *ctx,
+                        unsigned long long *cnt) {
+    arms_env e; arms_pt w;
+    e.f = f; e.ctx = ctx; e.st = st; e.cnt = cnt; e.convex = 1.0;
+    if (cnt) cnt[PHO_C_ARMS_CALLS]++;
+    const int mpoint = 9;
+    /* the reference returns error 1003/1004 (and its callers carry on with xsamp = 0) when the abscissae are not
+     * strictly inside (xl, xr) and increasing */
+    if (xinit[0] <= xl || xinit[3] >= xr) return 0.0;
+    for (int i = 1; i < 4; i++) if (xinit[i] <= xinit[i - 1]) return 0.0;
+    for (int j = 0; j < mpoint; j++) { e.p[j].pl = j - 1; e.p[j].pr = (j == mpoint - 1) ? A_NIL : j + 1; e.p[j].f = j & 1; e.p[j].y = 0.0; }
+    e.p[0].x = xl; e.p[mpoint - 1].x = xr;
+    for (int j = 1, k = 0; j < mpoint - 1; j += 2) { e.p[j].x = xinit[k++]; e.p[j].y = a_perfunc(&e, e.p[j].x); }
+    e.right = mpoint - 1; e.cpoint = mpoint;
+    for (int j = 0; j < mpoint; j += 2) a_meet(&e, j);
+    a_cumulate(&e);
+    e.xprev = 0.0;
+    if (e.xprev < xl || e.xprev > xr) return 0.0;                    /* error 1007 */
+    e.yprev = a_perfunc(&e, e.xprev);
+    for (;;) {
+        a_invert(&e, pht_stream_unif(st), &w);
+        if (a_test(&e, &w)) return w.x;
+    }
+}
+
+/* ------------------------------------------------------------------ a8: ECS, exact observation */
+typedef struct { int n; double y_t, Sjj; const double *pq, *evals, *Qinv_s; } ecs_ctx;
+
+/* log density of the sojourn up to a constant: src/Simulate_AbsCTMC_eq_Aslett_ECS.c:150-171; pq = p_j^T Q is the
+ * same for every evaluation of one ARMS call, so it is formed once by the caller */
+static double ecs_dens(double d, void *vp) {
+    const ecs_ctx *c = (const ecs_ctx *)vp;
+    double term1 = 0.0;
+    for (int i = 0; i < c->n; i++) term1 += (c->pq[i] * pht_exp(c->evals[i] * (c->y_t - d))) * c->Qinv_s[i];
+    return pht_log(term1) + c->Sjj * d;
+}
+
+/* src/Simulate_AbsCTMC_eq_Aslett_ECS.c:205-373 */
+static int ecs_exact_path(pht_stream *st, double y, int n, const double *pi, const double *S, const double *s,
+                          const double *Q, const double *evals, const double *Qinv_s, const double *P,
+                          double *z, int *N, double *wk, unsigned long long *cnt) {
+    double *p = wk, *pq = wk + n, *tmp = wk + 2 * n;
+    for (int i = 0; i < n; i++) z[i] = 0.0;
+    memset(N, 0, sizeof(int) * (size_t)n * n);
+    const int B = cat_scan(pi, 1, n - 1, runif01(st));                               /* :231-238 */
+    double t = 0.0; int j = B;
+    for (;;) {
+        const double y_t = y - t, Sjj = S[j + j * n];
+        if (s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
+            const double num = (Sjj * y_t) + pht_log(s[j]);
+            double den = 0.0;
+            for (int i = 0; i < n; i++) den += Q[j + i * n] * pht_exp(evals[i] * y_t) * Qinv_s[i];
+            if (runif01(st) < pht_exp(num - pht_log(den))) break;
+        }
+        const int lastj = j;
+        for (int i = 0; i < n; i++) p[i] = S[j + i * n] / (-Sjj);                    /* :292-295 */
+        p[j] = 0.0;
+        gemv_t(n, Q, p, pq);                                                         /* :160 */
+        ecs_ctx c; c.n = n; c.y_t = y_t; c.Sjj = Sjj; c.pq = pq; c.evals = evals; c.Qinv_s = Qinv_s;
+        double xinit[4];
+        xinit[0] = y_t / 1e6; xinit[1] = y_t / 3.0; xinit[2] = xinit[1] * 2.0; xinit[3] = y_t - xinit[0];   /* :315-318 */
+        const double d = arms_draw(st, xinit, 0.0, y_t, ecs_dens, &c, cnt);          /* :338 */
+        t += d;
+        /* next state, moveMass :21-41: weights P[j,i] * (Q e^{L (y_t-d)} Q^-1 s)_i */
+        const double rem = y_t - d;
+        for (int i = 0; i < n; i++) tmp[i] = pht_exp(evals[i] * rem) * Qinv_s[i];
+        for (int r = 0; r < n; r++) p[r] = 0.0;
+        for (int c2 = 0; c2 < n; c2++) { const double tv = 1.0 * tmp[c2]; for (int r = 0; r < n; r++) p[r] += tv * Q[r + c2 * n]; }
+        double sum = 0.0;
+        for (int i = 0; i < n; i++) { p[i] = p[i] * P[j + i * n]; sum += p[i]; }
+        for (int i = 0; i < n; i++) p[i] = p[i] / sum;
+        j = cat_scan(p, 1, n - 1, runif01(st));                                      /* :352-358 */
+        z[lastj] += d; N[lastj + j * n]++;                                           /* :362-363 */
+        if (cnt) cnt[PHO_C_JUMPS]++;
+    }
+    N[j + j * n]++; z[j] += y - t;                                                   /* :368-369 */
+    return B;
+}
+
+/* ------------------------------------------------------------------ a10: Aslett-DCS gt sampler (censored observations under ECS) */
+typedef struct { int n; double rem, scale; const double *pq1, *evals, *Qinv_1; } gt_ctx;
+
+/* upper tail sum_c piQ_c exp(x evals_c) (Q^-1 1)_c: src/Simulate_AbsCTMC_gt_Aslett_DCS.c:26-43 */
+static double pht_tail(int n, double x, const double *piQ, const double *evals, const double *Qinv_1) {
+    if (!(x > 0)) return 1.0;
+    double r = 0.0;
+    for (int i = 0; i < n; i++) r += piQ[i] * pht_exp(x * evals[i]) * Qinv_1[i];
+    return r;
+}
+/* log conditional jump density up to a constant: :111-132 (pq1 = P[j,.]^T Q hoisted) */
+static double gt_dens(double d, void *vp) {
+    const gt_ctx *c = (const gt_ctx *)vp;
+    const double x1 = c->rem - d;
+    const double r1 = (x1 > 0) ? pht_tail(c->n, x1, c->pq1, c->evals, c->Qinv_1) : 1.0;
+    double dens;                                                                     /* dexp(d, scale, log = TRUE) */
+    if (c->scale <= 0.0) dens = NAN; else if (d < 0.0) dens = -INFINITY; else dens = (-d / c->scale) - pht_log(c->scale);
+    return pht_log(r1) + dens;
+}
+
+/* src/Simulate_AbsCTMC_gt_Aslett_DCS.c:299-418 (reverse = 0) with condjump_r_ars :184-260 */
+static int gt_path(pht_stream *st, double y, int censored, int n, const double *pi, const double *S, const double *Q,
+                   const double *evals, const double *Qinv_1, const double *P, const double *Pfull,
+                   double *z, int *N, double *wk, unsigned long long *cnt) {
+    double *pv = wk, *pq = wk + n, *ex = wk + 2 * n;
+    for (int i = 0; i < n; i++) z[i] = 0.0;
+    memset(N, 0, sizeof(int) * (size_t)n * n);
+    const int B = cat_scan(pi, 1, n - 1, runif01(st));                               /* :313-320 */
+    double t = 0.0, lastt = 0.0; int j = B, lastj = 0;
+    while (t < y || censored) {                                                      /* :339 */
+        lastt = t; lastj = j;
+        const double Sjj = S[j + j * n];
+        double d;
+        if (t >= y) d = rexp_scale(st, 1.0 / -Sjj);                                  /* :187-191 */
+        else {
+            const double x = y - t;
+            for (int i = 0; i < n; i++) pv[i] = 0.0;
+            pv[j] = 1.0;
+            gemv_t(n, Q, pv, pq);                                                    /* :75 via :198 */
+            const double denom = pht_tail(n, x, pq, evals, Qinv_1);
+            if (runif01(st) < pht_exp(Sjj * (y - t)) / denom) d = y - t + rexp_scale(st, 1.0 / -Sjj);   /* :200-204 */
+            else {
+                for (int i = 0; i < n; i++) pv[i] = P[j + i * n];
+                gemv_t(n, Q, pv, pq);
+                gt_ctx c; c.n = n; c.rem = y - t; c.scale = -1.0 / Sjj; c.pq1 = pq; c.evals = evals; c.Qinv_1 = Qinv_1;
+                double xinit[4];
+                xinit[0] = (y - t) / 1e6; xinit[1] = (y - t) / 3.0; xinit[2] = xinit[1] * 2.0; xinit[3] = y - t - xinit[0];   /* :227-230 */
+                d = arms_draw(st, xinit, 0.0, y - t, gt_dens, &c, cnt);              /* :250 */
+            }
+        }
+        if (cnt) cnt[PHO_C_JUMPS]++;
+        t += d;
+        const double target = runif01(st);                                           /* :350 */
+        double sofar = 0.0; j = 0;
+        if (t < y) {                                                                 /* :353-369 */
+            const double x1 = y - t;
+            for (int i = 0; i < n; i++) pv[i] = P[lastj + i * n];
+            gemv_t(n, Q, pv, pq);
+            const double r2 = pht_tail(n, x1, pq, evals, Qinv_1);
+            for (int i = 0; i < n; i++) ex[i] = pht_exp(x1 * evals[i]);
+            while (sofar < target && j <= n - 1) {
+                if (P[lastj + j * n] == 0.0) { j++; continue; }
+                for (int i = 0; i < n; i++) pv[i] = 0.0;
+                pv[j] = 1.0;
+                gemv_t(n, Q, pv, pq);
+                double r1 = 0.0;
+                for (int i = 0; i < n; i++) r1 += pq[i] * ex[i] * Qinv_1[i];
+                sofar += r1 * P[lastj + j * n] / r2; j++;
+            }
+            j--;
+            if (j < 0) j = 0;
+        } else j = cat_scan(Pfull + lastj, n, n, target);                            /* :370-375 */
+        if (j == n) break;                                                           /* :379 */
+        if (t < y || censored) { z[lastj] += t - lastt; N[lastj + j * n]++; }        /* :381-383 */
+    }
+    if (!censored) z[lastj] += y - lastt; else z[lastj] += t - lastt;                /* :390-391 */
+    N[lastj + lastj * n]++;                                                          /* :392 */
+    return B;
+}
+
+/* a7: src/Simulate_AbsCTMC_eq_Aslett_ECS.c:461-479 */
+int pho_ecs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                  const double *y, const int *cens, int n, const double *S, const double *s,
+                  const double *P, const double *Pfull,
+                  const double *evals, const double *Q, const double *Qinv_s, const double *Qinv_1,
+                  int *outB, int *outN, double *outz, unsigned long long *counters) {
+    double *pi = (double *)calloc(n, sizeof(double)), *wk = (double *)calloc(4 * (size_t)n, sizeof(double));
+    double *z = (double *)calloc(n, sizeof(double)); int *N = (int *)calloc((size_t)n * n, sizeof(int));
+    if (!pi || !wk || !z || !N) return -1;
+    pi[0] = 1.0;
+    for (long k = 0; k < count; k++) {
+        pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
+        int B;
+        if (cens[k]) B = gt_path(&st, y[k], 1, n, pi, S, Q, evals, Qinv_1, P, Pfull, z, N, wk, counters);
+        else B = ecs_exact_path(&st, y[k], n, pi, S, s, Q, evals, Qinv_s, P, z, N, wk, counters);
+        if (counters) counters[PHO_C_PATHS]++;
+        if (outB) {
+            outB[k] = B;
+            memcpy(outN + (size_t)k * n * n, N, sizeof(int) * (size_t)n * n);
+            memcpy(outz + (size_t)k * n, z, sizeof(double) * (size_t)n);
+        }
+    }
+    free(pi); free(wk); free(z); free(N);
+    return 0;
+}
