@@ -68,6 +68,8 @@ struct pht_engine {
     TailItem *d_items = nullptr; uint32_t *d_pend0 = nullptr, *d_pend1 = nullptr, *d_done = nullptr;
     unsigned long long *d_found = nullptr; uint32_t item_cap = 0;
     double *d_res = nullptr; int res_rows = 0;
+    uint32_t *d_idx_exact = nullptr, *d_idx_cens = nullptr; unsigned long long n_exact = 0, n_cens = 0;   /* ECS launch lists */
+    std::vector<uint8_t> h_cens;       /* host copy of the flags (ECS parity ranges) */
     double *d_inject = nullptr;        /* host-supplied evals | Q | Qinv (parity hook), else nullptr */
     ModelLayout L;
     int grid_blocks = 0;
@@ -124,8 +126,14 @@ static int method_of(const pht_config &c) {       /* dispatch priority of src/PH
 }
 
 /* enqueue the path kernel of the configured method */
-static int enqueue_paths(pht_engine *e, const SweepParams &p) {
+static int enqueue_paths(pht_engine *e, const SweepParams &p, const uint32_t *idx_exact = nullptr, unsigned long long n_exact = 0,
+                         const uint32_t *idx_cens = nullptr, unsigned long long n_cens = 0, bool lists_given = false) {
     switch (method_of(e->cfg)) {
+    case PHT_METHOD_ECS:
+        if (lists_given) CU(pht_launch_ecs(p, e->grid_blocks, idx_exact, n_exact, idx_cens, n_cens, e->stream));
+        else CU(pht_launch_ecs(p, e->grid_blocks, e->d_idx_exact, e->n_exact, e->d_idx_cens, e->n_cens, e->stream));
+        e->launches += (lists_given ? (n_exact != 0) + (n_cens != 0) : (e->n_exact != 0) + (e->n_cens != 0)) - 1;
+        break;
     case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->stream)); break;
     case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); break;
     default: return fail("sampling method %d has no kernel in this build", e->cfg.method);
@@ -169,7 +177,7 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     void *bufs[] = { e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res, e->d_inject };
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -218,6 +226,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         uint8_t *hc = nullptr;
         CUE(cudaMallocHost(&hc, (size_t)l_local));
         for (long i = 0; i < l_local; i++) hc[i] = cens_local[i] != 0;
+        if (method_of(e->cfg) == PHT_METHOD_ECS) e->h_cens.assign(hc, hc + l_local);
         cudaError_t ce = cudaMemcpyAsync(e->d_cens, hc, (size_t)l_local, cudaMemcpyHostToDevice, e->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
         cudaFreeHost(hc);
@@ -250,6 +259,16 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         CUE(cudaMalloc(&e->d_found, sizeof(unsigned long long) * ln));
         e->grid_blocks = pht_mhrs_grid_blocks(cfg->device, n);
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
+    }
+    if (method_of(e->cfg) == PHT_METHOD_ECS) {
+        std::vector<uint32_t> ie, ic;
+        for (long i = 0; i < l_local; i++) (e->h_cens[i] ? ic : ie).push_back((uint32_t)i);
+        e->n_exact = ie.size(); e->n_cens = ic.size();
+        CUE(cudaMalloc(&e->d_idx_exact, sizeof(uint32_t) * (ie.size() + 1))); CUE(cudaMalloc(&e->d_idx_cens, sizeof(uint32_t) * (ic.size() + 1)));
+        if (!ie.empty()) CUE(cudaMemcpy(e->d_idx_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice));
+        if (!ic.empty()) CUE(cudaMemcpy(e->d_idx_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
+        e->grid_blocks = pht_ecs_grid_blocks(cfg->device, n);
+        if (e->grid_blocks <= 0) { fail("ECS kernels do not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
     if (method_of(e->cfg) == PHT_METHOD_DCS) {
         e->grid_blocks = pht_dcs_grid_blocks(cfg->device, n);
@@ -408,7 +427,16 @@ extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, i
     if (enqueue_model(e, u)) { cudaFree(dB); cudaFree(dN); cudaFree(dz); return -1; }
     SweepParams p = sweep_params(e);
     p.outB = dB; p.outN = dN; p.outz = dz; p.first = first; p.count = count;
-    int rc = enqueue_paths(e, p);
+    int rc;
+    uint32_t *t_exact = nullptr, *t_cens = nullptr;
+    if (method_of(e->cfg) == PHT_METHOD_ECS) {
+        std::vector<uint32_t> ie, ic;
+        for (long i = first; i < first + count; i++) (e->h_cens[i] ? ic : ie).push_back((uint32_t)i);
+        CU(cudaMalloc(&t_exact, sizeof(uint32_t) * (ie.size() + 1))); CU(cudaMalloc(&t_cens, sizeof(uint32_t) * (ic.size() + 1)));
+        if (!ie.empty()) CU(cudaMemcpy(t_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice));
+        if (!ic.empty()) CU(cudaMemcpy(t_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
+        rc = enqueue_paths(e, p, t_exact, ie.size(), t_cens, ic.size(), true);
+    } else rc = enqueue_paths(e, p);
     if (rc == 0) rc = pht_engine_sync(e);
     if (rc == 0) {
         CU(cudaMemcpy(B, dB, sizeof(int) * count, cudaMemcpyDeviceToHost));
@@ -416,6 +444,8 @@ extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, i
         CU(cudaMemcpy(z, dz, sizeof(double) * count * n, cudaMemcpyDeviceToHost));
     }
     cudaFree(dB); cudaFree(dN); cudaFree(dz);
+    if (t_exact) cudaFree(t_exact);
+    if (t_cens) cudaFree(t_cens);
     return rc;
 }
 

@@ -97,6 +97,10 @@ cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_mhrs(const SweepParams &p, int grid_blocks, cudaStream_t st);
 cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st);
 int pht_dcs_grid_blocks(int device, int n);
+/* ECS: exact and right-censored observations are separate launches over index lists (nullptr = identity) */
+cudaError_t pht_launch_ecs(const SweepParams &p, int grid_blocks, const uint32_t *idx_exact, unsigned long long n_exact,
+                           const uint32_t *idx_cens, unsigned long long n_cens, cudaStream_t st);
+int pht_ecs_grid_blocks(int device, int n);
 /* spectral data of the sweep: inject != nullptr copies host-supplied (evals | Q | Qinv) instead of solving on the device */
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st);
 int pht_mhrs_grid_blocks(int device, int n);

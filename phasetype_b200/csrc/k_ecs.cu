@@ -1,0 +1,488 @@
+/*
+ * k_ecs.cu -- Aslett-Wilson exact conditional sampling (method bit 2) for sm_100a, two kernels:
+ *
+ *   k_ecs_exact  observations absorbed AT y (reference src/Simulate_AbsCTMC_eq_Aslett_ECS.c:205-373): at each
+ *                step decide "absorb now" with probability exp(S_jj T) s_j / (e_j e^{ST} s), else draw the sojourn
+ *                d in (0,T) by ARMS from log(p_j^T e^{S(T-d)} s) + S_jj d and the next state with weight
+ *                P_ji (e^{S(T-d)} s)_i;
+ *   k_ecs_gt     right-censored observations, absorbed AFTER y (the reference delegates them to the Aslett-DCS
+ *                gt sampler, src/Simulate_AbsCTMC_gt_Aslett_DCS.c:299-418 with :184-260): before y the sojourn
+ *                is either "jump beyond y" or an ARMS draw conditioned on survival, after y plain forward
+ *                simulation to absorption.
+ *
+ * Both use a per-lane ARMS (Gilks' adaptive rejection Metropolis sampling, src/arms.c) with the reference's
+ * settings (4 starting abscissae, up to 100 envelope points, convex = 1, Metropolis on, xprev = 0).  The
+ * envelope is an index-linked array in the lane's local memory (typically 9-13 live points, L1 resident);
+ * log-density evaluations read the lane's hoisted row vector p^T Q from a shared-memory slab and the spectrum
+ * from shared memory.  Exact and censored observations are separate launches over index lists built at upload,
+ * so a warp never serialises the two samplers.  All sums run in the reference's order inside one thread:
+ * results are bit-identical to the host for the same spectral data.
+ *
+ * Roofline: FP64 issue bound (~6 density evaluations of n exp each per sojourn); 12 B of HBM per path.
+ */
+#include "path_common.cuh"
+
+#define ECS_THREADS 128
+#define A_XEPS 0.00001
+#define A_YEPS 0.1
+#define A_EYEPS 0.001
+#define A_YCEIL 50.
+#define A_NPOINT 100
+#define A_NIL (-1)
+
+struct EcsSmem {
+    double *S, *Q, *P, *Pfull, *evals, *s, *Qinv_s, *Qinv_1, *pi;
+    double *PQ, *W, *Z;                 /* per-lane slabs: hoisted p^T Q, scratch weights, sojourn totals */
+    long long *zacc; unsigned int *Nacc, *Bacc;
+    __device__ __forceinline__ void carve(unsigned char *raw, int n) {
+        double *d = reinterpret_cast<double *>(raw);
+        S = d; d += n * n; Q = d; d += n * n; P = d; d += n * n; Pfull = d; d += n * (n + 1);
+        evals = d; d += n; s = d; d += n; Qinv_s = d; d += n; Qinv_1 = d; d += n; pi = d; d += n;
+        PQ = d; d += n * ECS_THREADS; W = d; d += n * ECS_THREADS; Z = d; d += n * ECS_THREADS;
+        zacc = reinterpret_cast<long long *>(d); d += n;
+        Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n;
+    }
+    static size_t bytes(int n) {
+        return sizeof(double) * (size_t)(3 * n * n + n * (n + 1) + 5 * n + 3 * n * ECS_THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n);
+    }
+};
+
+struct ArmsPt { double x, y, ey, cum; int f, pl, pr; };
+
+struct EcsCounters { unsigned long long jumps, evals, updates, calls, rejects, nonfinite, paths; };
+
+/* log-density closures (state kept in registers; the row vector lives in the PQ slab) */
+struct DensExact {      /* eq_Aslett_ECS.c:150-171 */
+    double y_t, Sjj;
+    __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
+        double term1 = 0.0;
+        for (int i = 0; i < n; i++)
+            term1 += (sm.PQ[i * ECS_THREADS + threadIdx.x] * pht_exp(sm.evals[i] * (y_t - d))) * sm.Qinv_s[i];
+        return pht_log(term1) + Sjj * d;
+    }
+};
+struct DensGt {         /* gt_Aslett_DCS.c:111-132 */
+    double rem, scale;
+    __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
+        const double x1 = rem - d;
+        double r1 = 1.0;
+        if (x1 > 0) {
+            r1 = 0.0;
+            for (int i = 0; i < n; i++)
+                r1 += sm.PQ[i * ECS_THREADS + threadIdx.x] * pht_exp(x1 * sm.evals[i]) * sm.Qinv_1[i];
+        }
+        double dens;                                     /* dexp(d, scale, log = TRUE) */
+        if (scale <= 0.0) dens = pht_u2d(0x7ff8000000000000ULL);
+        else if (d < 0.0) dens = -pht_u2d(0x7ff0000000000000ULL);
+        else dens = (-d / scale) - pht_log(scale);
+        return pht_log(r1) + dens;
+    }
+};
+
+__device__ __forceinline__ double a_expshift(double y, double y0) { return (y - y0 > -2.0 * A_YCEIL) ? pht_exp(y - y0 + A_YCEIL) : 0.0; }
+__device__ __forceinline__ double a_logshift(double y, double y0) { return pht_log(y) + y0 - A_YCEIL; }
+
+/* chord intersection at envelope point q (arms.c:659-764, Metropolis on) */
+__device__ __noinline__ void a_meet(ArmsPt *p, int q, double convex) {
+    double gl = 0.0, gr = 0.0, grl = 0.0, dl = 0.0, dr = 0.0;
+    const int pl = p[q].pl, pr = p[q].pr;
+    bool il = false, ir = false, irl = false;
+    if (pl != A_NIL && p[p[pl].pl].pl != A_NIL) { const int a = p[p[pl].pl].pl; gl = (p[pl].y - p[a].y) / (p[pl].x - p[a].x); il = true; }
+    if (pr != A_NIL && p[p[pr].pr].pr != A_NIL) { const int a = p[p[pr].pr].pr; gr = (p[pr].y - p[a].y) / (p[pr].x - p[a].x); ir = true; }
+    if (pl != A_NIL && pr != A_NIL) { grl = (p[pr].y - p[pl].y) / (p[pr].x - p[pl].x); irl = true; }
+    if (irl && il && (gl < grl)) gl = gl + (1.0 + convex) * (grl - gl);
+    if (irl && ir && (gr > grl)) gr = gr + (1.0 + convex) * (grl - gr);
+    if (il && irl) { dr = (gl - grl) * (p[pr].x - p[pl].x); if (dr < A_YEPS) dr = A_YEPS; }
+    if (ir && irl) { dl = (grl - gr) * (p[pr].x - p[pl].x); if (dl < A_YEPS) dl = A_YEPS; }
+    if (il && ir && irl) {
+        p[q].x = (dl * p[pr].x + dr * p[pl].x) / (dl + dr);
+        p[q].y = (dl * p[pr].y + dr * p[pl].y + dl * dr) / (dl + dr);
+    } else if (il && irl) { p[q].x = p[pr].x; p[q].y = p[pr].y + dr; }
+    else if (ir && irl) { p[q].x = p[pl].x; p[q].y = p[pl].y + dl; }
+    else if (il) p[q].y = p[pl].y + gl * (p[q].x - p[pl].x);
+    else if (ir) p[q].y = p[pr].y - gr * (p[pr].x - p[q].x);
+}
+
+/* exponentiate and integrate the envelope (arms.c:625-655, :768-790); returns ymax */
+__device__ __noinline__ double a_cumulate(ArmsPt *p) {
+    double ymax = p[0].y;
+    for (int q = p[0].pr; q != A_NIL; q = p[q].pr) if (p[q].y > ymax) ymax = p[q].y;
+    for (int q = 0; q != A_NIL; q = p[q].pr) p[q].ey = a_expshift(p[q].y, ymax);
+    p[0].cum = 0.;
+    for (int q = p[0].pr; q != A_NIL; q = p[q].pr) {
+        const int l = p[q].pl; double a;
+        if (p[l].x == p[q].x) a = 0.;
+        else if (fabs(p[q].y - p[l].y) < A_YEPS) a = 0.5 * (p[q].ey + p[l].ey) * (p[q].x - p[l].x);
+        else a = ((p[q].ey - p[l].ey) / (p[q].y - p[l].y)) * (p[q].x - p[l].x);
+        p[q].cum = p[l].cum + a;
+    }
+    return ymax;
+}
+
+/* One ARMS draw on (0, xr) with the four reference abscissae xr*{1e-6, 1/3, 2/3, 1-1e-6}: arms.c:115-222 */
+template <class Dens>
+__device__ double arms_draw(const SweepParams &p, uint32_t iter, PathRng &rng, const EcsSmem &sm, int n, const Dens &f,
+                            const double xinit[4], double xr, EcsCounters &c) {
+    ArmsPt e[A_NPOINT];
+    const double xl = 0.0, convex = 1.0;
+    const int mpoint = 9, right = mpoint - 1;
+    c.calls++;
+    if (xinit[0] <= xl || xinit[3] >= xr) return 0.0;                /* reference error 1003: caller uses xsamp = 0 */
+    for (int i = 1; i < 4; i++) if (xinit[i] <= xinit[i - 1]) return 0.0;       /* error 1004 */
+    for (int j = 0; j < mpoint; j++) { e[j].pl = j - 1; e[j].pr = (j == mpoint - 1) ? A_NIL : j + 1; e[j].f = j & 1; e[j].y = 0.0; }
+    e[0].x = xl; e[right].x = xr;
+    for (int j = 1, k = 0; j < mpoint - 1; j += 2) {
+        e[j].x = xinit[k++]; e[j].y = f(sm, n, e[j].x); c.evals++;
+        if (!isfinite(e[j].y)) c.nonfinite++;
+    }
+    int cpoint = mpoint;
+    for (int j = 0; j < mpoint; j += 2) a_meet(e, j, convex);
+    double ymax = a_cumulate(e);
+    double xprev = 0.0, yprev = f(sm, n, xprev); c.evals++;
+    if (!isfinite(yprev)) c.nonfinite++;
+    for (;;) {
+        /* ---- sample from the envelope (invert, arms.c:356-420) */
+        ArmsPt w;
+        {
+            int q = right;
+            const double u = rng.next(p, iter) * e[q].cum;
+            while (e[q].pl != A_NIL && e[e[q].pl].cum > u) q = e[q].pl;
+            const int l = e[q].pl;
+            w.pl = l; w.pr = q; w.f = 0; w.cum = u;
+            const double prop = (u - e[l].cum) / (e[q].cum - e[l].cum);
+            if (e[l].x == e[q].x) { w.x = e[q].x; w.y = e[q].y; w.ey = e[q].ey; }
+            else {
+                const double xa = e[l].x, xb = e[q].x, yl = e[l].y, yr = e[q].y, eyl = e[l].ey, eyr = e[q].ey;
+                if (fabs(yr - yl) < A_YEPS) {
+                    if (fabs(eyr - eyl) > A_EYEPS * fabs(eyr + eyl))
+                        w.x = xa + ((xb - xa) / (eyr - eyl)) * (-eyl + PHT_SQRT((1. - prop) * eyl * eyl + prop * eyr * eyr));
+                    else w.x = xa + (xb - xa) * prop;
+                    w.ey = ((w.x - xa) / (xb - xa)) * (eyr - eyl) + eyl;
+                    w.y = a_logshift(w.ey, ymax);
+                } else {
+                    w.x = xa + ((xb - xa) / (yr - yl)) * (-yl + a_logshift(((1. - prop) * eyl + prop * eyr), ymax));
+                    w.y = ((w.x - xa) / (xb - xa)) * (yr - yl) + yl;
+                    w.ey = a_expshift(w.y, ymax);
+                }
+            }
+        }
+        /* ---- rejection / Metropolis tests (arms.c:424-521) */
+        const double ystar = a_logshift(rng.next(p, iter) * w.ey, ymax);
+        const double ynew = f(sm, n, w.x); c.evals++;
+        if (!isfinite(ynew)) c.nonfinite++;
+        if (ystar >= ynew) {
+            /* reject; add the point to the envelope (update, arms.c:525-621) */
+            w.y = ynew; w.f = 1;
+            if (cpoint <= A_NPOINT - 2) {
+                const int q = cpoint, m = cpoint + 1;
+                bool linked = true;
+                e[q].x = w.x; e[q].y = w.y; e[q].f = 1; e[m].f = 0;
+                if (e[w.pl].f && !e[w.pr].f) {
+                    e[m].pl = w.pl; e[m].pr = q; e[q].pl = m; e[q].pr = w.pr;
+                    e[e[m].pl].pr = m; e[e[q].pr].pl = q;
+                } else if (!e[w.pl].f && e[w.pr].f) {
+                    e[m].pr = w.pr; e[m].pl = q; e[q].pr = m; e[q].pl = w.pl;
+                    e[e[m].pr].pl = m; e[e[q].pl].pr = q;
+                } else linked = false;
+                if (linked) {
+                    cpoint += 2;
+                    const int ql = (e[e[q].pl].pl != A_NIL) ? e[e[q].pl].pl : e[q].pl;
+                    const int qr = (e[e[q].pr].pr != A_NIL) ? e[e[q].pr].pr : e[q].pr;
+                    if (e[q].x < (1. - A_XEPS) * e[ql].x + A_XEPS * e[qr].x) {
+                        e[q].x = (1. - A_XEPS) * e[ql].x + A_XEPS * e[qr].x; e[q].y = f(sm, n, e[q].x); c.evals++;
+                    } else if (e[q].x > A_XEPS * e[ql].x + (1. - A_XEPS) * e[qr].x) {
+                        e[q].x = A_XEPS * e[ql].x + (1. - A_XEPS) * e[qr].x; e[q].y = f(sm, n, e[q].x); c.evals++;
+                    }
+                    a_meet(e, e[q].pl, convex); a_meet(e, e[q].pr, convex);
+                    if (e[e[q].pl].pl != A_NIL) a_meet(e, e[e[e[q].pl].pl].pl, convex);
+                    if (e[e[q].pr].pr != A_NIL) a_meet(e, e[e[e[q].pr].pr].pr, convex);
+                    ymax = a_cumulate(e);
+                    c.updates++;
+                }
+            }
+            continue;
+        }
+        /* Metropolis step against the previous iterate xprev (always 0 here) */
+        int ql = 0;
+        while (e[e[ql].pr].x < xprev) ql = e[ql].pr;
+        const int qr = e[ql].pr;
+        double wgt = (xprev - e[ql].x) / (e[qr].x - e[ql].x);
+        double zold = e[ql].y + wgt * (e[qr].y - e[ql].y);
+        double znew = w.y;
+        if (yprev < zold) zold = yprev;
+        if (ynew < znew) znew = ynew;
+        wgt = ynew - znew - yprev + zold;
+        if (wgt > 0.0) wgt = 0.0;
+        wgt = (wgt > -A_YCEIL) ? pht_exp(wgt) : 0.0;
+        if (rng.next(p, iter) > wgt) { c.rejects++; return xprev; }
+        return w.x;
+    }
+}
+
+__device__ __forceinline__ void ecs_load_model(const SweepParams &p, EcsSmem &sm, int n) {
+    const ModelLayout ML = ModelLayout::make(n, p.m);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n * n; i += ECS_THREADS) {
+        sm.S[i] = p.model[ML.S + i]; sm.Q[i] = p.model[ML.Q + i]; sm.P[i] = p.model[ML.P + i]; sm.Nacc[i] = 0u;
+    }
+    for (int i = tid; i < n * (n + 1); i += ECS_THREADS) sm.Pfull[i] = p.model[ML.Pfull + i];
+    for (int i = tid; i < n; i += ECS_THREADS) {
+        sm.evals[i] = p.model[ML.evals + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
+        sm.Qinv_s[i] = p.model[ML.Qinv_s + i]; sm.Qinv_1[i] = p.model[ML.Qinv_1 + i];
+        sm.zacc[i] = 0; sm.Bacc[i] = 0u;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void ecs_finish(const SweepParams &p, int n, EcsSmem &sm, EcsCounters &c) {
+    const unsigned FULL = 0xffffffffu;
+    __syncthreads();
+    block_flush<ECS_THREADS>(p, n, sm.Nacc, sm.Bacc, sm.zacc);
+    for (int o = 16; o > 0; o >>= 1) {
+        c.jumps += __shfl_down_sync(FULL, c.jumps, o); c.evals += __shfl_down_sync(FULL, c.evals, o);
+        c.updates += __shfl_down_sync(FULL, c.updates, o); c.calls += __shfl_down_sync(FULL, c.calls, o);
+        c.rejects += __shfl_down_sync(FULL, c.rejects, o); c.nonfinite += __shfl_down_sync(FULL, c.nonfinite, o);
+        c.paths += __shfl_down_sync(FULL, c.paths, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&p.state->counters[PHT_CNT_JUMPS], c.jumps); atomicAdd(&p.state->counters[PHT_CNT_DENS_EVALS], c.evals);
+        atomicAdd(&p.state->counters[PHT_CNT_ENV_UPDATES], c.updates); atomicAdd(&p.state->counters[PHT_CNT_ARMS_CALLS], c.calls);
+        atomicAdd(&p.state->counters[PHT_CNT_METROP_REJECTS], c.rejects); atomicAdd(&p.state->counters[PHT_CNT_NONFINITE], c.nonfinite);
+        atomicAdd(&p.state->counters[PHT_CNT_PATHS], c.paths);
+    }
+}
+
+/* start state from pi: `while (sofar < target) sofar += pi[k++]` bounded at n-1 */
+__device__ __forceinline__ int start_state(const EcsSmem &sm, int n, double target) {
+    double sofar = 0.0; int k = 0;
+    while (sofar < target && k <= n - 1) { sofar += sm.pi[k]; k++; }
+    return k - 1 < 0 ? 0 : k - 1;
+}
+
+/* index list entry k -> local observation; list == nullptr means the identity */
+struct ObsList { const uint32_t *idx; unsigned long long count; };
+
+/* warp dispenser over a list */
+struct ListDispenser {
+    unsigned long long next, end, total; bool exhausted; unsigned long long *counter;
+    __device__ __forceinline__ void init(unsigned long long total_, unsigned long long *counter_) {
+        next = end = 0ull; total = total_; exhausted = (total_ == 0ull); counter = counter_;
+    }
+    __device__ __forceinline__ unsigned long long take(unsigned idle, bool me_idle) {
+        const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
+        if (next == end && !exhausted) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)PATH_CHUNK);
+            base = __shfl_sync(FULL, base, 0);
+            next = base < total ? base : total;
+            end = base + PATH_CHUNK < total ? base + PATH_CHUNK : total;
+            if (next == end) exhausted = true;
+        }
+        const unsigned avail = (unsigned)(end - next);
+        const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+        const unsigned long long mine = (me_idle && rank < avail) ? next + rank : ~0ull;
+        const unsigned cnt = __popc(idle);
+        next += cnt < avail ? cnt : avail;
+        return mine;
+    }
+};
+
+/* ------------------------------------------------------------------ exact observations */
+__global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsList list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, tid = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    EcsSmem sm; sm.carve(smem_raw, n);
+    const uint32_t iter = p.state->iter;
+    ecs_load_model(p, sm, n);
+    EcsCounters c = {0, 0, 0, 0, 0, 0, 0};
+    ListDispenser disp; disp.init(list.count, &p.state->next_obs);
+    PathRng rng; rng.seek(0);
+    bool active = false;
+    double y = 0.0, t = 0.0; int j = 0, B = 0; long out_idx = 0;
+
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !disp.exhausted) {
+            const unsigned long long k = disp.take(idle, !active);
+            if (k != ~0ull) {
+                const uint32_t o = list.idx ? list.idx[k] : (uint32_t)k;
+                active = true; y = p.y[o]; out_idx = (long)o - p.first; t = 0.0;
+                rng.seek(p.obs_rank + o * p.obs_world);
+                B = start_state(sm, n, rng.next(p, iter));                              /* eq_Aslett_ECS.c:231-238 */
+                j = B;
+                for (int i = 0; i < n; i++) sm.Z[i * ECS_THREADS + tid] = 0.0;
+            }
+            idle = __ballot_sync(FULL, !active);
+        }
+        if (idle == FULL) { if (disp.exhausted) break; else continue; }
+        if (!active) continue;
+
+        /* ---- one step of the path (eq_Aslett_ECS.c:247-364) */
+        const double y_t = y - t, Sjj = sm.S[j + j * n];
+        bool absorb = false;
+        if (sm.s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
+            const double num = (Sjj * y_t) + pht_log(sm.s[j]);
+            double den = 0.0;
+            for (int i = 0; i < n; i++) den += sm.Q[j + i * n] * pht_exp(sm.evals[i] * y_t) * sm.Qinv_s[i];
+            absorb = rng.next(p, iter) < pht_exp(num - pht_log(den));
+        }
+        if (absorb) {
+            count_transition(p, n, sm.Nacc, out_idx, j, j);                             /* :368 */
+            sm.Z[j * ECS_THREADS + tid] += y - t;                                       /* :369 */
+            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
+            c.paths++; active = false;
+            continue;
+        }
+        /* p_j = S[j,.]/(-S_jj) with p_jj = 0 (:292-295); PQ = p_j^T Q in reference-BLAS order (:160) */
+        for (int i = 0; i < n; i++) sm.W[i * ECS_THREADS + tid] = (i == j) ? 0.0 : sm.S[j + i * n] / (-Sjj);
+        for (int col = 0; col < n; col++) {
+            double acc = 0.0;
+            for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.W[i * ECS_THREADS + tid];
+            sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
+        }
+        DensExact f; f.y_t = y_t; f.Sjj = Sjj;
+        double xinit[4];
+        xinit[0] = y_t / 1e6; xinit[1] = y_t / 3.0; xinit[2] = xinit[1] * 2.0; xinit[3] = y_t - xinit[0];   /* :315-318 */
+        const double d = arms_draw(p, iter, rng, sm, n, f, xinit, y_t, c);              /* :338 */
+        t += d;
+        /* next state (moveMass :21-41): W_r = sum_c Q[r,c] exp(evals_c rem) (Q^-1 s)_c, accumulated over c */
+        const double rem = y_t - d;
+        for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] = 0.0;
+        for (int col = 0; col < n; col++) {
+            const double tv = 1.0 * (pht_exp(sm.evals[col] * rem) * sm.Qinv_s[col]);
+            for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] += tv * sm.Q[r + col * n];
+        }
+        double sum = 0.0;
+        for (int i = 0; i < n; i++) { const double v = sm.W[i * ECS_THREADS + tid] * sm.P[j + i * n]; sm.W[i * ECS_THREADS + tid] = v; sum += v; }
+        for (int i = 0; i < n; i++) sm.W[i * ECS_THREADS + tid] = sm.W[i * ECS_THREADS + tid] / sum;
+        const int k = slab_scan<ECS_THREADS>(sm.W, n, rng.next(p, iter));               /* :352-358 */
+        sm.Z[j * ECS_THREADS + tid] += d;                                               /* :362 */
+        count_transition(p, n, sm.Nacc, out_idx, j, k);                                 /* :363 */
+        j = k; c.jumps++;
+    }
+    ecs_finish(p, n, sm, c);
+}
+
+/* ------------------------------------------------------------------ censored observations */
+__global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, tid = threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    EcsSmem sm; sm.carve(smem_raw, n);
+    const uint32_t iter = p.state->iter;
+    ecs_load_model(p, sm, n);
+    EcsCounters c = {0, 0, 0, 0, 0, 0, 0};
+    ListDispenser disp; disp.init(list.count, &p.state->unit_counter);
+    PathRng rng; rng.seek(0);
+    bool active = false;
+    double y = 0.0, t = 0.0; int j = 0, B = 0; long out_idx = 0;
+
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && !disp.exhausted) {
+            const unsigned long long k = disp.take(idle, !active);
+            if (k != ~0ull) {
+                const uint32_t o = list.idx ? list.idx[k] : (uint32_t)k;
+                active = true; y = p.y[o]; out_idx = (long)o - p.first; t = 0.0;
+                rng.seek(p.obs_rank + o * p.obs_world);
+                B = start_state(sm, n, rng.next(p, iter));                              /* gt_Aslett_DCS.c:313-320 */
+                j = B;
+                for (int i = 0; i < n; i++) sm.Z[i * ECS_THREADS + tid] = 0.0;
+            }
+            idle = __ballot_sync(FULL, !active);
+        }
+        if (idle == FULL) { if (disp.exhausted) break; else continue; }
+        if (!active) continue;
+
+        /* ---- one step (gt_Aslett_DCS.c:339-384 with censored = 1) */
+        const double lastt = t; const int lastj = j;
+        const double Sjj = sm.S[j + j * n];
+        double d;
+        if (t >= y) d = (1.0 / -Sjj) * (-pht_log(rng.next(p, iter)));                   /* :187-191 */
+        else {
+            const double x = y - t;
+            /* e_j^T Q is row j of Q (the reference forms it with a dgemv over a unit vector) */
+            double denom = 1.0;
+            if (x > 0) { denom = 0.0; for (int i = 0; i < n; i++) denom += sm.Q[j + i * n] * pht_exp(x * sm.evals[i]) * sm.Qinv_1[i]; }
+            if (rng.next(p, iter) < pht_exp(Sjj * (y - t)) / denom)                     /* :200-204 */
+                d = y - t + (1.0 / -Sjj) * (-pht_log(rng.next(p, iter)));
+            else {
+                for (int col = 0; col < n; col++) {                                     /* P[j,.]^T Q */
+                    double acc = 0.0;
+                    for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.P[j + i * n];
+                    sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
+                }
+                DensGt f; f.rem = y - t; f.scale = -1.0 / Sjj;
+                double xinit[4];
+                xinit[0] = (y - t) / 1e6; xinit[1] = (y - t) / 3.0; xinit[2] = xinit[1] * 2.0; xinit[3] = y - t - xinit[0];   /* :227-230 */
+                d = arms_draw(p, iter, rng, sm, n, f, xinit, y - t, c);                 /* :250 */
+            }
+        }
+        c.jumps++;
+        t += d;
+        const double target = rng.next(p, iter);                                        /* :350 */
+        int k;
+        if (t < y) {                                                                    /* :353-369 */
+            const double x1 = y - t;
+            for (int col = 0; col < n; col++) {
+                double acc = 0.0;
+                for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.P[lastj + i * n];
+                sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
+            }
+            double r2 = 0.0;
+            for (int i = 0; i < n; i++) {
+                const double ex = pht_exp(x1 * sm.evals[i]);
+                sm.W[i * ECS_THREADS + tid] = ex;
+                r2 += sm.PQ[i * ECS_THREADS + tid] * ex * sm.Qinv_1[i];
+            }
+            double sofar = 0.0; k = 0;
+            while (sofar < target && k <= n - 1) {
+                const double Plk = sm.P[lastj + k * n];
+                if (Plk == 0.0) { k++; continue; }
+                double r1 = 0.0;
+                for (int i = 0; i < n; i++) r1 += sm.Q[k + i * n] * sm.W[i * ECS_THREADS + tid] * sm.Qinv_1[i];
+                sofar += r1 * Plk / r2; k++;
+            }
+            k--; if (k < 0) k = 0;
+        } else {                                                                        /* :370-375 */
+            double sofar = 0.0; k = 0;
+            while (sofar < target && k <= n) { sofar += sm.Pfull[lastj + k * n]; k++; }
+            k--; if (k < 0) k = 0;
+        }
+        if (k == n) {                                                                   /* :379, :390-392 */
+            sm.Z[lastj * ECS_THREADS + tid] += t - lastt;
+            count_transition(p, n, sm.Nacc, out_idx, lastj, lastj);
+            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
+            c.paths++; active = false;
+            continue;
+        }
+        sm.Z[lastj * ECS_THREADS + tid] += t - lastt;                                   /* :382 */
+        count_transition(p, n, sm.Nacc, out_idx, lastj, k);                             /* :383 */
+        j = k;
+    }
+    ecs_finish(p, n, sm, c);
+}
+
+int pht_ecs_grid_blocks(int device, int n) {
+    int a = 0, b = 0, sms = 0;
+    const size_t smem = EcsSmem::bytes(n);
+    if (cudaFuncSetAttribute(k_ecs_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_ecs_gt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_ecs_exact, ECS_THREADS, smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_ecs_gt, ECS_THREADS, smem) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    return (a < b ? a : b) * sms;
+}
+
+cudaError_t pht_launch_ecs(const SweepParams &p, int grid_blocks, const uint32_t *idx_exact, unsigned long long n_exact,
+                           const uint32_t *idx_cens, unsigned long long n_cens, cudaStream_t st) {
+    const size_t smem = EcsSmem::bytes(p.n);
+    ObsList le; le.idx = idx_exact; le.count = n_exact;
+    ObsList lc; lc.idx = idx_cens; lc.count = n_cens;
+    if (n_exact) k_ecs_exact<<<grid_blocks, ECS_THREADS, smem, st>>>(p, le);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (n_cens) k_ecs_gt<<<grid_blocks, ECS_THREADS, smem, st>>>(p, lc);
+    return cudaGetLastError();
+}
