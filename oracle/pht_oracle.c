@@ -680,3 +680,143 @@ int pho_ecs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     free(pi); free(wk); free(z); free(N);
     return 0;
 }
+
+/* ------------------------------------------------------------------ the engine's own spectral solver, on the host */
+#include "../phasetype_b200/csrc/pht_eigen.h"
+/* same code the device runs (pht_eigen.h); used by the chain-level oracle and checked against LAPACK through
+ * invariants in tests/test_spectral.py */
+int pho_eigen_native(int n, const double *S, double *evals, double *Q, double *Qinv) {
+    double *w = (double *)malloc(sizeof(double) * (2 * (size_t)n * n + 3 * (size_t)n));
+    if (!w) return -1;
+    int rc = pht_eigen_real(n, S, evals, Q, Qinv, w, w + n * n, w + 2 * n * n, w + 2 * n * n + n, w + 2 * n * n + 2 * n);
+    free(w);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ a1 / a13 / a14: the Gibbs driver */
+int pho_choose_zbits(double sum_y) {
+    if (!(sum_y > 0.0) || !isfinite(sum_y)) return 30;
+    int b = 62 - (int)ceil(log2(16.0 * sum_y + 1.0));
+    if (b > 52) b = 52;
+    if (b < 0) b = 0;
+    return b;
+}
+
+/* theta -> TT, S, s: src/PHT_MCMC_Aslett.c:209-246 (first) and :365-397 (afterwards) */
+static void assemble(int n, const int *T, const double *C, const double *theta, int first, double *TT, double *S, double *s) {
+    const int n1 = n + 1;
+    for (int i = 0; i < n1; i++) {
+        for (int j = 0; j < n1; j++) {
+            const int v = T[i + j * n1];
+            if (j != i || v != 0) TT[i + j * n1] = v ? theta[v - 1] * C[i + j * n1] : 0.0;
+        }
+        double acc = 0.0;
+        if (first) { for (int j = 0; j < n1; j++) if (T[i + j * n1] != 0) acc -= TT[i + j * n1]; }
+        else       { for (int j = n; j >= 0; j--) if (T[i + j * n1] != 0) acc -= TT[i + j * n1]; }
+        if (i < n || first) TT[i + i * n1] = acc;
+    }
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) S[i + j * n] = TT[i + j * n1];
+        s[i] = TT[i + n * n1];
+    }
+}
+
+static int method_pick(int method) {        /* dispatch priority of src/PHT_MCMC_Aslett.c:325-337 */
+    if (method & PHO_MHRS) return PHO_MHRS;
+    if (method & PHO_DCS) return PHO_DCS;
+    if (method & PHO_ECS) return PHO_ECS;
+    return 0;
+}
+
+int pho_sweep_stats(uint64_t seed, uint32_t iter, int first, int mhit, int method, int n, int m, const int *T, const double *C,
+                    const double *theta, const double *y, long l, const int *censored, int rank, int world,
+                    int zbits, long long *Nacc, long long *Bacc, long long *zfix, unsigned long long *counters) {
+    (void)m;
+    const int n1 = n + 1, which = method_pick(method);
+    if (!which) return -2;
+    long cnt = 0;
+    for (long i = rank; i < l; i += world) cnt++;
+    double *TT = (double *)calloc((size_t)n1 * n1, sizeof(double)), *S = (double *)calloc((size_t)n * n, sizeof(double));
+    double *s = (double *)calloc(n, sizeof(double)), *P = (double *)calloc((size_t)n * n, sizeof(double));
+    double *Pfull = (double *)calloc((size_t)n * n1, sizeof(double));
+    double *yl = (double *)malloc(sizeof(double) * (size_t)(cnt + 1)); int *cl = (int *)malloc(sizeof(int) * (size_t)(cnt + 1));
+    int *B = (int *)malloc(sizeof(int) * (size_t)(cnt + 1)), *N = (int *)malloc(sizeof(int) * (size_t)(cnt + 1) * n * n);
+    double *z = (double *)malloc(sizeof(double) * (size_t)(cnt + 1) * n);
+    double *ev = (double *)calloc(n, sizeof(double)), *Q = (double *)calloc((size_t)n * n, sizeof(double)), *Qi = (double *)calloc((size_t)n * n, sizeof(double));
+    double *Qs = (double *)calloc(n, sizeof(double)), *Q1 = (double *)calloc(n, sizeof(double));
+    int rc = 0;
+    long k = 0;
+    for (long i = rank; i < l; i += world, k++) { yl[k] = y[i]; cl[k] = censored[i]; }
+    assemble(n, T, C, theta, first, TT, S, s);
+    pho_embedded(n, S, s, P, Pfull);
+    if (which != PHO_MHRS) {
+        rc = pho_eigen_native(n, S, ev, Q, Qi);
+        for (int i = 0; i < n; i++) {             /* Q^-1 s, Q^-1 1 in reference-BLAS order (src/PHT_MCMC_Aslett.c:331-332) */
+            double a = 0.0, b = 0.0;
+            for (int j = 0; j < n; j++) { a += (1.0 * s[j]) * Qi[i + j * n]; b += (1.0 * 1.0) * Qi[i + j * n]; }
+            Qs[i] = a; Q1[i] = b;
+        }
+    }
+    if (rc == 0) {
+        if (which == PHO_MHRS) rc = pho_mhrs_paths(seed, iter, rank, world, cnt, yl, cl, n, S, s, Pfull, mhit, B, N, z, counters);
+        else if (which == PHO_DCS) rc = pho_dcs_paths(seed, iter, rank, world, cnt, yl, n, S, s, ev, Q, Qi, B, N, z, counters);
+        else rc = pho_ecs_paths(seed, iter, rank, world, cnt, yl, cl, n, S, s, P, Pfull, ev, Q, Qs, Q1, B, N, z, counters);
+    }
+    if (rc == 0) {
+        const double zs = ldexp(1.0, zbits);
+        memset(Nacc, 0, sizeof(long long) * (size_t)n * n); memset(Bacc, 0, sizeof(long long) * n); memset(zfix, 0, sizeof(long long) * n);
+        for (k = 0; k < cnt; k++) {
+            Bacc[B[k]]++;
+            for (int c = 0; c < n * n; c++) Nacc[c] += N[(size_t)k * n * n + c];
+            for (int i = 0; i < n; i++) { const double v = z[(size_t)k * n + i]; if (v != 0.0) zfix[i] += llrint(v * zs); }
+        }
+    }
+    free(TT); free(S); free(s); free(P); free(Pfull); free(yl); free(cl); free(B); free(N); free(z);
+    free(ev); free(Q); free(Qi); free(Qs); free(Q1);
+    return rc;
+}
+
+/* gather + conjugate Gamma draw: src/PHT_MCMC_Aslett.c:340-366 (prepend lists = reverse insertion order) */
+int pho_update(uint64_t seed, uint32_t iter, int n, int m, const double *nu, const double *zeta, const int *T,
+               const double *C, int zbits, const long long *Nacc, const long long *zfix, double *theta_new) {
+    const int n1 = n + 1;
+    const double zscale = ldexp(1.0, -zbits);
+    for (int v = 0; v < m; v++) {
+        long long Nsum = 0; double zsum = 0.0;
+        for (int i = n; i >= 0; i--)
+            for (int j = n; j >= 0; j--) {
+                if (T[i + j * n1] != v + 1) continue;
+                Nsum += (j == n) ? Nacc[i + i * n] : Nacc[i + j * n];
+                const double zi = (double)zfix[i] * zscale;
+                zsum += zi / C[i + j * n1];
+            }
+        theta_new[v] = pho_rgamma_at(seed, iter, (uint32_t)v, nu[v] + (double)Nsum, 1.0 / (zeta[v] + zsum));
+    }
+    return 0;
+}
+
+int pho_gibbs(uint64_t seed, int it, int mhit, int method, int n, int m, const double *nu, const double *zeta,
+              const int *T, const double *C, const double *y, long l, const int *censored,
+              const double *start, double *res, unsigned long long *counters) {
+    double *theta = (double *)malloc(sizeof(double) * m), *next = (double *)malloc(sizeof(double) * m);
+    long long *Nacc = (long long *)malloc(sizeof(long long) * (size_t)n * n), *Bacc = (long long *)malloc(sizeof(long long) * n);
+    long long *zfix = (long long *)malloc(sizeof(long long) * n);
+    if (start[0] < 0) {                                        /* src/PHT_MCMC_Aslett.c:195-207 */
+        uint32_t k = 0;
+        for (int i = 0; i < m; i++) theta[i] = (nu[i] > 1) ? (nu[i] - 1.0) / zeta[i] : pho_rgamma_at(seed, 0, k++, nu[i], 1.0 / zeta[i]);
+    } else for (int i = 0; i < m; i++) theta[i] = start[i];
+    for (int i = 0; i < m; i++) res[0 + (size_t)i * it] = theta[i];
+    double sum_y = 0.0;
+    for (long i = 0; i < l; i++) sum_y += y[i];
+    const int zbits = pho_choose_zbits(sum_y);
+    int rc = 0;
+    for (int iter = 1; iter < it && rc == 0; iter++) {         /* :268 */
+        rc = pho_sweep_stats(seed, (uint32_t)iter, iter == 1, mhit, method, n, m, T, C, theta, y, l, censored, 0, 1, zbits,
+                             Nacc, Bacc, zfix, counters);
+        if (rc) break;
+        pho_update(seed, (uint32_t)iter, n, m, nu, zeta, T, C, zbits, Nacc, zfix, next);
+        for (int i = 0; i < m; i++) { theta[i] = next[i]; res[iter + (size_t)i * it] = next[i]; }
+    }
+    free(theta); free(next); free(Nacc); free(Bacc); free(zfix);
+    return rc;
+}

@@ -84,9 +84,12 @@ int pho_gibbs(uint64_t seed, int it, int mhit, int method, int n, int m, const d
 /* one sweep's sufficient statistics for the shard {obs : obs % world == rank}:
  * Nacc[n*n] and Bacc[n] as int64, zfix[n] as int64 fixed point with zbits
  * fractional bits; theta is the current parameter vector (length m). */
-int pho_sweep_stats(uint64_t seed, uint32_t iter, int mhit, int method, int n, int m, const int *T, const double *C,
+int pho_sweep_stats(uint64_t seed, uint32_t iter, int first, int mhit, int method, int n, int m, const int *T, const double *C,
                     const double *theta, const double *y, long l, const int *censored, int rank, int world,
                     int zbits, long long *Nacc, long long *Bacc, long long *zfix, unsigned long long *counters);
+/* `first` != 0: the generator is assembled from start values (diagonal summed over ascending columns,
+ * src/PHT_MCMC_Aslett.c:215,229); 0: after an update (descending, :389-393) */
+int pho_eigen_native(int n, const double *S, double *evals, double *Q, double *Qinv);
 
 /* conjugate update from (allreduced) statistics: writes theta_new (length m) */
 int pho_update(uint64_t seed, uint32_t iter, int n, int m, const double *nu, const double *zeta, const int *T,

@@ -89,6 +89,8 @@ def oracle():
                 continue
         if hasattr(L, "pho_eigen"):
             L.pho_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp]
+        if hasattr(L, "pho_eigen_native"):
+            L.pho_eigen_native.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
         if hasattr(L, "pho_dcs_paths"):
             L.pho_dcs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, C.c_int,
                                         _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _up]
@@ -101,7 +103,7 @@ def oracle():
             L.pho_gibbs.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp,
                                     _dp, C.c_long, _ip, _dp, _dp, _up]
         if hasattr(L, "pho_sweep_stats"):
-            L.pho_sweep_stats.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp,
+            L.pho_sweep_stats.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp,
                                           _dp, _dp, C.c_long, _ip, C.c_int, C.c_int, C.c_int, _lp, _lp, _lp, _up]
         if hasattr(L, "pho_update"):
             L.pho_update.argtypes = [C.c_uint64, C.c_uint32, C.c_int, C.c_int, _dp, _dp, _ip, _dp, C.c_int,
@@ -175,7 +177,11 @@ def eigen(impl, S, n):
     """(evals, Q, Qinv) of the column-major n x n matrix S, through LAPACK as the reference does (src/utility.c:87-129)."""
     S = _f64(S)
     ev = np.zeros(n); Q = np.zeros(n * n); Qi = np.zeros(n * n)
-    if impl == "oracle":
+    if impl == "native":
+        rc = oracle().pho_eigen_native(n, S, ev, Q, Qi)
+        if rc != 0:
+            raise ValueError("pht_eigen_real status %d (1 = no convergence, 2 = complex pair, 4 = singular Q)" % rc)
+    elif impl == "oracle":
         im = np.zeros(n)
         rc = oracle().pho_eigen(n, S, ev, im, Q, Qi)
         if rc != 0:
@@ -226,3 +232,57 @@ def spectral_paths(impl, method, seed, it, y, cens, S, s, obs0=0, stride=1, want
     if B is None:
         return None, None, None, counters
     return B, N.reshape(count, n * n), z.reshape(count, n), counters
+
+
+def choose_zbits(sum_y):
+    return int(oracle().pho_choose_zbits(float(sum_y)))
+
+
+def sweep_stats(seed, it, first, mhit, method, n, T, Cm, theta, y, cens, rank=0, world=1, zbits=None):
+    """Packed sufficient statistics (N int64 n*n, B int64 n, z int64 fixed point) of one sweep for the shard
+    {i : i % world == rank}, computed by the CPU restatement with the engine's own spectral solver."""
+    y = _f64(y); cens = _i32(cens); theta = _f64(theta); T = _i32(np.asarray(T).ravel()); Cm = _f64(np.asarray(Cm).ravel())
+    if zbits is None:
+        zbits = choose_zbits(y.sum())
+    N = np.zeros(n * n, dtype=np.int64); B = np.zeros(n, dtype=np.int64); z = np.zeros(n, dtype=np.int64)
+    cnt = np.zeros(N_COUNTERS, dtype=np.uint64)
+    rc = oracle().pho_sweep_stats(seed, it, 1 if first else 0, mhit, method, n, theta.shape[0], T, Cm, theta, y, y.shape[0], cens,
+                                  rank, world, zbits, N, B, z, cnt)
+    if rc != 0:
+        raise RuntimeError("pho_sweep_stats failed rc=%d" % rc)
+    return N, B, z, _counters(cnt)
+
+
+def update(seed, it, n, nu, zeta, T, Cm, zbits, N, zfix):
+    nu = _f64(nu); zeta = _f64(zeta); T = _i32(np.asarray(T).ravel()); Cm = _f64(np.asarray(Cm).ravel())
+    out = np.zeros(nu.shape[0])
+    oracle().pho_update(seed, it, n, nu.shape[0], nu, zeta, T, Cm, zbits, np.ascontiguousarray(N, dtype=np.int64),
+                        np.ascontiguousarray(zfix, dtype=np.int64), out)
+    return out
+
+
+def gibbs(seed, it, mhit, method, n, nu, zeta, T, Cm, y, cens, start):
+    """The whole chain from the CPU restatement: (it, m) array like LJMA_Gibbs's res."""
+    nu = _f64(nu); zeta = _f64(zeta); T = _i32(np.asarray(T).ravel()); Cm = _f64(np.asarray(Cm).ravel())
+    y = _f64(y); cens = _i32(cens); m = nu.shape[0]
+    start = _f64(np.atleast_1d(start))
+    if start.shape[0] < m:
+        start = np.concatenate([start, np.zeros(m - start.shape[0])])
+    res = np.zeros(it * m); cnt = np.zeros(N_COUNTERS, dtype=np.uint64)
+    rc = oracle().pho_gibbs(seed, it, mhit, method, n, m, nu, zeta, T, Cm, y, y.shape[0], cens, start, res, cnt)
+    if rc != 0:
+        raise RuntimeError("pho_gibbs failed rc=%d" % rc)
+    return res.reshape(m, it).T.copy(), _counters(cnt)
+
+
+def ref_gibbs(seed, keyed, it, mhit, method, n, nu, zeta, T, Cm, y, cens, start):
+    """The reference's own LJMA_Gibbs (unmodified C + R stand-in).  keyed=True (ECS/DCS) maps path p of sweep i
+    to Philox stream (i, p); otherwise one sequential stream."""
+    nu = _f64(nu).copy(); zeta = _f64(zeta).copy(); T = _i32(np.asarray(T).ravel()).copy(); Cm = _f64(np.asarray(Cm).ravel()).copy()
+    y = _f64(y).copy(); cens = _i32(cens).copy(); m = nu.shape[0]
+    start = _f64(np.atleast_1d(start))
+    if start.shape[0] < m:
+        start = np.concatenate([start, np.zeros(m - start.shape[0])])
+    res = np.zeros(it * m)
+    ref().phtref_gibbs(seed, 1 if keyed else 0, it, mhit, method, n, m, nu, zeta, T, Cm, y, y.shape[0], cens, start.copy(), res)
+    return res.reshape(m, it).T.copy()

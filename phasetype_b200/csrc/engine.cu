@@ -146,7 +146,6 @@ static int enqueue_paths(pht_engine *e, const SweepParams &p, const uint32_t *id
 static int enqueue_model(pht_engine *e, const UpdateParams &u) {
     CU(pht_launch_assemble(u, e->stream)); e->launches++;
     if (method_of(e->cfg) != PHT_METHOD_MHRS) {
-        if (e->d_inject == nullptr) return fail("no device eigen-solver in this build: call pht_engine_set_spectral first");
         CU(pht_launch_spectral(u, e->d_inject, e->stream)); e->launches++;
     }
     return 0;
@@ -364,9 +363,11 @@ static int check_state(pht_engine *e) {
     if (st.error) {
         int err = st.error;
         cudaMemset(&e->d_state->error, 0, sizeof(int));
-        return fail("device error word 0x%x (%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range; " : "",
+        return fail("device error word 0x%x (%s%s%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range; " : "",
                     (err & 4) ? "MHRS tail list overflow; " : "",
-                    (err & 8) ? "an observation's survival probability is too small for rejection sampling; " : "");
+                    (err & 8) ? "an observation's survival probability is too small for rejection sampling; " : "",
+                    (err & 16) ? "S has complex eigenvalues: the spectral samplers (ECS/DCS) are not valid for it; " : "",
+                    (err & 32) ? "spectral decomposition failed; " : "");
     }
     return 0;
 }

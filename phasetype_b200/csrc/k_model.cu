@@ -14,6 +14,7 @@
  */
 #include "engine_internal.h"
 #include "pht_philox.h"
+#include "pht_eigen.h"
 
 __global__ void __launch_bounds__(64) k_assemble(UpdateParams p) {
     const int n = p.n, n1 = n + 1, tid = threadIdx.x;
@@ -129,9 +130,37 @@ __global__ void __launch_bounds__(64) k_spectral_inject(UpdateParams p, const do
     }
 }
 
+/* The engine's own solver (pht_eigen.h: Hessenberg + shifted QR + Gauss-Jordan), one thread working in shared
+ * memory: O(10 n^3) dependent flops once per sweep, microseconds at n = 8 and about a millisecond at n = 32,
+ * against sweeps of tens of milliseconds to seconds.  The other threads then form Q^-1 s and Q^-1 1. */
+__global__ void __launch_bounds__(64) k_spectral_solve(UpdateParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, tid = threadIdx.x;
+    const ModelLayout L = ModelLayout::make(n, p.m);
+    double *M = p.model;
+    double *w = reinterpret_cast<double *>(smem_raw);
+    if (tid == 0) {
+        const int st = pht_eigen_real(n, M + L.S, M + L.evals, M + L.Q, M + L.Qinv, w, w + n * n, w + 2 * n * n,
+                                      w + 2 * n * n + n, w + 2 * n * n + 2 * n);
+        if (st & 2) atomicOr(&p.state->error, 16);
+        if (st & 5) atomicOr(&p.state->error, 32);
+    }
+    __syncthreads();
+    if (tid < n) {
+        const int i = tid;
+        double ys = 0.0, y1 = 0.0;
+        for (int j = 0; j < n; j++) {
+            const double a = M[L.Qinv + i + j * n];
+            ys += (1.0 * M[L.s + j]) * a;
+            y1 += (1.0 * 1.0) * a;
+        }
+        M[L.Qinv_s + i] = ys; M[L.Qinv_1 + i] = y1;
+    }
+}
+
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st) {
-    if (inject == nullptr) return cudaErrorNotSupported;
-    k_spectral_inject<<<1, 64, 0, st>>>(p, inject);
+    if (inject != nullptr) k_spectral_inject<<<1, 64, 0, st>>>(p, inject);
+    else k_spectral_solve<<<1, 64, sizeof(double) * (2 * p.n * p.n + 3 * p.n), st>>>(p);
     return cudaGetLastError();
 }
 
