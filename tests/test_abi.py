@@ -1,0 +1,96 @@
+"""Drop-in boundary checks that need no GPU: the shared library loads, exports every symbol include/pht_b200.h
+declares, refuses to run without a CUDA device (no CPU fallback), and the Python mirrors of the R wrappers
+validate their arguments like the R code does."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import phasetype_b200 as pb
+from phasetype_b200 import _lib, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "pht_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(LJMA_Gibbs|pht_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from phasetype_b200 import build
+    build.build()
+    names = header_functions()
+    assert "LJMA_Gibbs" in names and len(names) >= 18
+    assert sorted(_lib.SYMBOLS) == names
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    for nm in names:
+        assert nm in exported, nm
+    L = pb.lib()
+    for nm in names:
+        assert hasattr(L, nm)
+
+
+def test_ljma_gibbs_signature_is_the_registered_one():
+    """15 pointer arguments in the order of reference src/PHT_MCMC_Aslett.h:1-3 / src/Registrations.c:6-12."""
+    src = open(os.path.join(ROOT, "include", "pht_b200.h")).read()
+    m = re.search(r"void LJMA_Gibbs\((.*?)\);", src, flags=re.S)
+    args = [a.strip() for a in m.group(1).replace("\n", " ").split(",")]
+    assert [a.split("*")[-1].strip() for a in args] == ["it", "mhit", "method", "n", "m", "nu", "zeta", "T", "C", "y", "l",
+                                                        "censored", "start", "silent", "res"]
+    assert [a.split("*")[0].strip() for a in args] == ["int"] * 5 + ["double"] * 2 + ["int"] + ["double"] * 2 + ["int"] * 2 + \
+        ["double", "int", "double"]
+
+
+@pytest.mark.skipif(pb.lib().pht_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback():
+    with pytest.raises(pb.EngineError, match="no CUDA device"):
+        pb.Engine(3, np.zeros(16, dtype=np.int32), np.ones(16), [1.0], [1.0], [1.0], [0], method=1)
+    os.environ["PHT_B200_QUIET"] = "1"
+    res = pb.ljma_gibbs(5, 1, 1, 3, 2, [24, 180], [16, 16], [0, 2, 2, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0], np.ones(16),
+                        [1.0, 2.0], [0, 0], [-1.0])
+    assert np.allclose(res[0], [23 / 16, 179 / 16])       # start row = prior mode (src/PHT_MCMC_Aslett.c:197-198)
+    assert (res[1:] == 0).all()                            # nothing was computed on the CPU
+    with pytest.raises(pb.EngineError):
+        pb.fp64_fma_rate()
+
+
+def test_zbits_rule():
+    L = pb.lib()
+    assert L.pht_choose_zbits(1.0) == 52 and L.pht_choose_zbits(1e7) == 34 and L.pht_choose_zbits(1e9) == 28    # capped at 52 bits
+    from oracle import pyoracle as po
+    for v in (1e-3, 1.0, 123.4, 1e7, 3e9):
+        assert L.pht_choose_zbits(v) == po.choose_zbits(v)
+
+
+def test_wrapper_argument_checks_follow_the_r_code():
+    x = [1.0, 2.0]
+    TT = np.array([["0", "F", "F", "0"], ["R", "0", "0", "F"], ["R", "0", "0", "F"], ["0", "0", "0", "0"]], dtype=object)
+    nu = {"R": 180, "F": 24}; zeta = {"R": 16, "F": 16}
+    with pytest.raises(ValueError, match="invalid number of MCMC iterations"):
+        api.phtMCMC2(x, TT, [1, 0, 0], nu, zeta, 0)
+    with pytest.raises(ValueError, match="must be square"):
+        api.phtMCMC2(x, TT[:3], [1, 0, 0], nu, zeta, 5)
+    bad = TT.copy(); bad[1, 1] = "R"
+    with pytest.raises(ValueError, match="diagonal"):
+        api.phtMCMC2(x, bad, [1, 0, 0], nu, zeta, 5)
+    bad = TT.copy(); bad[3, 0] = "R"
+    with pytest.raises(ValueError, match="last row"):
+        api.phtMCMC2(x, bad, [1, 0, 0], nu, zeta, 5)
+    with pytest.raises(ValueError, match="beta should be a vector of length 3"):
+        api.phtMCMC2(x, TT, [1, 0], nu, zeta, 5)
+    with pytest.raises(ValueError, match="don't match those in prior nu"):
+        api.phtMCMC2(x, TT, [1, 0, 0], {"R": 1}, zeta, 5)
+    with pytest.raises(ValueError, match="unknown sampling methods"):
+        api.phtMCMC2(x, TT, [1, 0, 0], nu, zeta, 5, method="HMC")
+    names, TN = api._encode(TT, nu, zeta)
+    assert names == ["F", "R"]
+    assert TN.ravel(order="F").tolist() == [0, 2, 2, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0]      # SURVEY Appendix C, fixture 2
+    with pytest.raises(ValueError, match="nu must specify"):
+        api.phtMCMC(x, 3, [1, 0, 0], [1.0] * 8, [1.0] * 3, 5)
+    with pytest.raises(ValueError):                      # 11 states: "S111" names collide, as upstream (R/phtMCMC.R:17)
+        api.phtMCMC(x, 11, np.ones(11), np.ones(121), np.ones(11), 5)
