@@ -5,7 +5,7 @@ A "step" is one Gibbs sweep (reference src/PHT_MCMC_Aslett.c:268-405) over all o
 one conditioned latent-path draw per observation + the conjugate parameter update.
 Metric: path draws per second (= l x sweeps / time); Gibbs iterations/s is reported beside it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--method MHRS|ECS|DCS] [--config 3] [--l L]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--method MHRS|ECS|DCS] [--config 3] [--obs L]
   python bench.py --impl reference ...      # the reference's own C on the host cores
 
 Contract details are in the task statement; the JSON line carries `roofline`, `cpu_baseline`,
@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="MHRS", choices=["MHRS", "ECS", "DCS"])
     ap.add_argument("--config", type=int, default=3)
-    ap.add_argument("--l", type=int, default=None, help="override the number of observations")
+    ap.add_argument("--obs", dest="l", type=int, default=None, help="override the number of observations")
     ap.add_argument("--mhit", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")

@@ -170,8 +170,9 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    /* the graph holds captured NCCL work: it must go before the communicator it refers to */
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -296,6 +297,11 @@ extern "C" int pht_engine_comm_init(pht_engine *e, const void *id128) {
     ncclUniqueId id; memcpy(&id, id128, sizeof(id));
     int rc = g_nccl.CommInitRank(&e->comm, e->cfg.world, id, e->cfg.rank);
     if (rc != 0) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    /* one collective outside any graph capture: NCCL connects its transports lazily on first use */
+    CU(cudaMemsetAsync(e->d_stats, 0, sizeof(long long) * stats_len(e->cfg.n), e->stream));
+    rc = g_nccl.AllReduce(e->d_stats, e->d_stats, (size_t)stats_len(e->cfg.n), NCCL_INT64, NCCL_SUM, e->comm, e->stream);
+    if (rc != 0) return fail("ncclAllReduce (warm-up) failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
 

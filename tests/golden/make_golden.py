@@ -44,10 +44,8 @@ def main():
     for name, method, kind, n, fc, mhit in cases:
         rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
         R, s = model(kind, n, rng)
-        S = R.copy()
-        for i in range(n):
-            S[i, i] = -(R[i].sum() + s[i])
-        S = S.ravel(order="F").copy()
+        T, Cm, theta = util.general_model(R, s)
+        S, s = util.assemble(T, Cm, theta, n)        # diagonal = sequential row sum, as the reference assembles it
         y = np.array(Y20) if name.endswith("y20") else rng.exponential(1.2, 150) + 0.01
         cens = (rng.uniform(size=y.shape[0]) < fc).astype(np.int32)
         seed, it = 20260000 + n, 3
