@@ -9,7 +9,7 @@
  * so this restatement is pinned against the reference ITSELF: oracle/_ref/
  * (the unmodified reference C built by oracle/Makefile with the R stand-in in
  * oracle/shim/) must agree bit for bit on per-observation (B, N, z); see
- * tests/test_oracle_vs_ref.py and the committed vectors in tests/golden/.
+ * tests/test_oracle.py and the committed vectors in tests/golden/.
  *
  * Conventions: column-major matrices X[i + j*n] as in the reference; `seed`,
  * `iter`, global observation index and sub-stream address the Philox contract

@@ -16,7 +16,14 @@
  *     its (attempt index, offset) with recording on.  No per-attempt zeroing of N2/z2.
  *   - One jump-step is one Philox block: {state uniform of this jump, exponential uniform
  *     of the next}; the attempt's first step uses the same code with the start
- *     distribution as the scan row, so fresh and running lanes do not diverge.
+ *     distribution as the scan row, and a FAILED attempt restarts the lane on the next
+ *     sub-stream inside the same branch-free step, so fresh, running, failing, searching
+ *     and replaying lanes execute one instruction stream.  Only the rare events (a
+ *     surviving attempt, the end of a replay, a hand-over to the tail) leave it.
+ *   - The categorical scan `while (sofar < target) sofar += p[k++]` is answered from
+ *     precomputed running sums: a 64-bucket guide table indexed by the top 6 random bits
+ *     gives a lower bound of the answer, one or two comparisons finish it (same result as
+ *     the sequential scan because the running sums are non-decreasing).
  *   - Lane phase: persistent warps, one observation per lane, refilled from a global
  *     counter in warp-sized chunks as lanes finish (attempt counts are geometric with a
  *     heavy tail).  A lane gives up after `cap` attempts and appends the
@@ -41,7 +48,8 @@ namespace cg = cooperative_groups;
 #ifndef MHRS_MIN_BLOCKS
 #define MHRS_MIN_BLOCKS 3                /* 80 registers: 24 warps per SM */
 #endif
-#define RUN_LEN 32u                 /* attempts per tail work unit */
+#define RUN_LEN 4u                  /* attempts per tail work unit (short: a round ends when its slowest run does) */
+#define GUIDE 64                    /* buckets of the scan guide table */
 #define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
 #define TAIL_KMAX (1u << 24)
 #define OBS_CHUNK 64u               /* observations a warp takes from the global counter at once */
@@ -52,6 +60,7 @@ enum { IDLE = 0, SEARCH = 1, REPLAY = 2 };
 struct Smem {
     double *scale, *s, *cum, *z2;
     long long *zacc; unsigned int *Nacc, *Bacc;
+    unsigned char *guide;            /* (n+1) x GUIDE lower bounds of the scan result */
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -67,16 +76,19 @@ __device__ __forceinline__ Smem carve(unsigned char *raw, int n) {
     sm.zacc = reinterpret_cast<long long *>(d); d += n;
     sm.Nacc = reinterpret_cast<unsigned int *>(d);
     sm.Bacc = sm.Nacc + n * n;
+    sm.guide = reinterpret_cast<unsigned char *>(sm.Bacc + n);
     return sm;
 }
 size_t pht_mhrs_smem_bytes(int n) {
-    return sizeof(double) * (size_t)(2 * n + (n + 1) * (n + 1) + n * MHRS_THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n);
+    return sizeof(double) * (size_t)(2 * n + (n + 1) * (n + 1) + n * MHRS_THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n) + (size_t)(n + 1) * GUIDE;
 }
 
 struct Lane {
     double y, t, lastt, spare;
+    uint32_t spare_hi;          /* high random word behind `spare` (guide-table bucket) */
     uint32_t obs_local, obs_global;
     uint32_t a, b;              /* attempt (= sub-stream) and next Philox block inside it */
+    uint32_t a_end;             /* tail phase: first attempt index beyond this lane's run */
     uint32_t cur_a, tries;
     int j, B;
     int mode;
@@ -90,32 +102,56 @@ __device__ __forceinline__ void begin_attempt(Lane &L, const SweepParams &p, uin
     L.fresh = true; L.b = 0; L.odd = false;
     if (L.off) {
         pht_u32x4 r = pht_philox4x32_10(0u, L.a, L.obs_global, iter, p.k0, p.k1);
-        L.spare = pht_u01(r.v[2], r.v[3]); L.odd = true; L.b = 1;
+        L.spare = pht_u01(r.v[2], r.v[3]); L.spare_hi = r.v[3]; L.odd = true; L.b = 1;
     }
 }
 
-/* one jump-step; returns true when the attempt ended on this step.  Written without control flow around
- * the expensive parts (Philox, scan, log): fresh, running, ending, searching and replaying lanes all run the
- * same instructions and differ only in selects, so a warp never serialises copies of this code. */
-__device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n, int top_step) {
+/* log of a uniform in (0,1): the normal, positive branch of pht_log (bit-identical on that domain) */
+__device__ __forceinline__ double log_unit(double x) {
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01, L3 = 2.857142874366239149e-01,
+                 L4 = 2.222219843214978396e-01, L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
+                 L7 = 1.479819860511658591e-01;
+    const uint64_t ux = pht_d2u(x);
+    uint32_t hx = (uint32_t)(ux >> 32);
+    hx += 0x3ff00000u - 0x3fe6a09eu;
+    const int e = (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+    const double m = pht_u2d(((uint64_t)hx << 32) | (ux & 0xffffffffULL));
+    const double f = m - 1.0;
+    const double hfsq = 0.5 * f * f;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * PHT_FMA(w, PHT_FMA(w, L6, L4), L2);
+    const double t2 = z * PHT_FMA(w, PHT_FMA(w, PHT_FMA(w, L7, L5), L3), L1);
+    const double R = t2 + t1;
+    const double dk = (double)e;
+    return dk * LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LN2_LO)) - f);
+}
+
+/* One jump-step.  Returns true when the lane needs the (divergent) event handler: a searching attempt that
+ * survived, a replay that finished, or a failed attempt that must not simply restart (`stop_on_fail`, or the
+ * lane's run of attempts [a, a_end) is used up).  A failed attempt otherwise restarts on sub-stream a+1 right
+ * here.  No control flow around the expensive parts (Philox, scan, log): every lane of the warp runs the same
+ * instructions and differs only in selects. */
+__device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n, bool stop_on_fail,
+                                          unsigned long long &c_attempts) {
     pht_u32x4 r = pht_philox4x32_10(L.b, L.a, L.obs_global, iter, p.k0, p.k1);
     L.b++;
     const double f = pht_u01(r.v[0], r.v[1]), g = pht_u01(r.v[2], r.v[3]);
-    const double uA = L.odd ? L.spare : f;       /* start state / next state */
-    const double uB = L.odd ? f : g;             /* next exponential */
-    L.spare = g;
+    const double uA = L.odd ? L.spare : f;               /* start state / next state */
+    const uint32_t hiA = L.odd ? L.spare_hi : r.v[1];
+    const double uB = L.odd ? f : g;                     /* next exponential */
+    L.spare = g; L.spare_hi = r.v[3];
     const bool fresh = L.fresh;
     const int row = fresh ? n : L.j;
     const int last = fresh ? n - 1 : n;
     const double *c = sm.cum + row * (n + 1);
-    /* reference scan `while (sofar < target) sofar += p[k++]` = number of running sums below the target among
-     * the first `last` (the sums are non-decreasing): branch-free lower bound, same trip count for every lane */
-    int k = 0;
-    for (int step = top_step; step > 0; step >>= 1) {
-        const int probe = k + step;
-        const double cv = c[(probe <= last ? probe : 1) - 1];
-        k = (probe <= last && cv < uA) ? probe : k;
-    }
+    /* reference scan `while (sofar < target) sofar += p[k++]` = number of running sums below the target among the
+     * first `last` (the sums are non-decreasing).  The guide entry counts the sums <= bucket floor < uA. */
+    int k = sm.guide[row * GUIDE + (hiA >> 26)];
+    while (k < last && c[k] < uA) k++;
     const bool cont = (k < n) && (L.t < L.y || L.cens);             /* gt_Bladt_MHRS.c:75,111 */
     const bool ended = !fresh && !cont;
     const bool advance = !fresh && cont;
@@ -128,10 +164,22 @@ __device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const S
     L.lastt = fresh ? 0.0 : (advance ? L.t : L.lastt);
     L.j = ended ? L.j : k;
     L.B = fresh ? k : L.B;
-    L.fresh = false;
-    const double tn = tb + sm.scale[L.j] * (-pht_log(uB));          /* :80, rexp(1/-S_jj) */
+    const double tn = tb + sm.scale[L.j] * (-log_unit(uB));         /* :80, rexp(1/-S_jj) */
     L.t = ended ? L.t : tn;
-    return ended;
+    /* an ended searching attempt survives when it reached y in a state that can exit (eq_Bladt_MHRS.c:66,74) */
+    const bool searching = L.mode == SEARCH;
+    const bool ok = (L.t >= L.y) && (sm.s[L.j] != 0.0);
+    const bool failed = ended && searching && !ok;
+    c_attempts += (ended && searching) ? 1ull : 0ull;
+    L.tries += failed ? 1u : 0u;
+    const bool restart = failed && !stop_on_fail && (L.a + 1u < L.a_end);
+    /* restart on the next sub-stream (begin_attempt with off = false) */
+    L.a += failed ? 1u : 0u;
+    L.off = failed ? false : L.off;
+    L.fresh = restart;
+    L.b = restart ? 0u : L.b;
+    L.odd = restart ? false : L.odd;
+    return ended && !restart;
 }
 
 /* close a replayed path: gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110 */
@@ -157,7 +205,7 @@ __device__ __forceinline__ void finish_replay(Lane &L, const SweepParams &p, con
 }
 
 __device__ __forceinline__ void start_replay(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n) {
-    L.mode = REPLAY; L.a = L.cur_a; L.off = L.cur_off;
+    L.mode = REPLAY; L.a = L.cur_a; L.off = L.cur_off; L.a_end = 0xFFFFFFFFu;
     begin_attempt(L, p, iter);
     for (int i = 0; i < n; i++) sm.z2[i * MHRS_THREADS + threadIdx.x] = 0.0;
 }
@@ -180,6 +228,15 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
     for (int i = tid; i < (n + 1) * (n + 1); i += MHRS_THREADS) sm.cum[i] = p.model[ML.cum + i];
     for (int i = tid; i < n * n; i += MHRS_THREADS) sm.Nacc[i] = 0u;
     __syncthreads();
+    /* guide[row][b] = #{ i < last(row) : cum[row][i] <= b / GUIDE }: every uniform of bucket b is > b / GUIDE */
+    for (int e = tid; e < (n + 1) * GUIDE; e += MHRS_THREADS) {
+        const int row = e / GUIDE, b = e % GUIDE, last = (row == n) ? n - 1 : n;
+        const double floor_u = (double)b * (1.0 / GUIDE);
+        int k = 0;
+        while (k < last && sm.cum[row * (n + 1) + k] <= floor_u) k++;
+        sm.guide[e] = (unsigned char)k;
+    }
+    __syncthreads();
 
     unsigned long long c_attempts = 0, c_jumps = 0, c_paths = 0, c_deferred = 0;
     const unsigned long long t_start = gtimer();
@@ -187,11 +244,10 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
     const unsigned long long obs_begin = per_obs ? (unsigned long long)p.first : 0ull;
     const unsigned long long obs_end = per_obs ? (unsigned long long)(p.first + p.count) : (unsigned long long)p.l_local;
     const uint32_t cap = (uint32_t)p.mhrs_cap;
-    int top_step = 1; while (top_step * 2 <= n) top_step *= 2;      /* largest power of two <= n */
 
     /* ---------------------------------------------------------------- lane phase */
     {
-        Lane L; L.mode = IDLE; L.tries = 0;
+        Lane L; L.mode = IDLE; L.tries = 0; L.a_end = 0xFFFFFFFFu;
         unsigned long long chunk_next = 0, chunk_end = 0;      /* warp-uniform */
         bool exhausted = false;
         for (;;) {
@@ -212,7 +268,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                     L.obs_global = p.obs_rank + L.obs_local * p.obs_world;
                     L.y = p.y[L.obs_local]; L.cens = p.cens[L.obs_local] != 0;
                     L.mode = SEARCH; L.a = 0; L.off = false; L.have_cur = false; L.kprop = 0; L.tries = 0;
-                    L.cur_a = 0; L.cur_off = false; L.cur_pre = 0;
+                    L.cur_a = 0; L.cur_off = false; L.cur_pre = 0; L.a_end = 0xFFFFFFFFu;
                     begin_attempt(L, p, iter);
                 }
                 const unsigned taken = __popc(idle) < avail ? __popc(idle) : avail;
@@ -222,9 +278,13 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (idle == FULL) { if (exhausted) break; else continue; }
             if (L.mode == IDLE) continue;
 
-            const bool ended = jump_step(L, p, sm, iter, n, top_step);
+            /* a failed attempt restarts inside the step unless the lane is due to hand the observation over: after
+             * `cap` attempts, or as soon as the observation stream has run dry (a lone lane grinding through
+             * attempts would hold the whole grid at the barrier) */
+            const bool stop_on_fail = cap != 0u && (L.tries + 1u >= cap || exhausted);
+            const bool event = jump_step(L, p, sm, iter, n, stop_on_fail, c_attempts);
             c_jumps++;
-            if (!ended) continue;
+            if (!event) continue;
 
             if (L.mode == REPLAY) {
                 finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
@@ -232,13 +292,10 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                 continue;
             }
             /* SEARCH: an attempt just ended (gt_Bladt_MHRS.c:49 decides whether it survives) */
-            c_attempts++; L.tries++;
             const bool ok = (L.t >= L.y) && (sm.s[L.j] != 0.0);            /* eq_Bladt_MHRS.c:66,74 */
             if (!ok) {
-                L.a++; L.off = false;
-                /* hand over to the cooperative tail after `cap` attempts, or as soon as the observation stream has
-                 * run dry (a lone lane grinding through attempts would hold the whole grid at the barrier) */
-                if (cap != 0u && (L.tries >= cap || exhausted)) {
+                /* (the step already moved the lane to attempt a+1, off = false) */
+                if (stop_on_fail) {
                     const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
                     if (idx < p.item_cap) {
                         TailItem it; it.obs_local = L.obs_local; it.a = L.a; it.cur_a = L.cur_a; it.flags = pack_flags(L);
@@ -261,7 +318,9 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (U < sm.s[pre] / sm.s[L.cur_pre]) { L.cur_a = L.a; L.cur_off = L.off; L.cur_pre = pre; }
             L.kprop++;
             if (L.kprop >= p.mhit) { start_replay(L, p, sm, iter, n); continue; }
-            L.a++; L.off = true; begin_attempt(L, p, iter);
+            /* next proposal: sub-stream a+1 from draw 1 (the spare half of the block just computed) */
+            L.a++; L.off = true;
+            L.fresh = true; L.b = 1; L.odd = true; L.spare = pht_u01(r.v[2], r.v[3]); L.spare_hi = r.v[3];
         }
     }
 
@@ -283,15 +342,15 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (P == 0u) break;
             const uint32_t *pend = cur ? p.pend1 : p.pend0;
             uint32_t *pend_next = cur ? p.pend0 : p.pend1;
-            /* run length: 32 attempts per work unit while there is plenty of work, down to single attempts when
-             * only a few heavy observations remain (the round is then one attempt deep instead of 32) */
+            /* run length: RUN_LEN attempts per work unit while there is plenty of work, down to single attempts when
+             * only a few heavy observations remain */
             uint32_t rl = RUN_LEN;
             while (rl > 1u && (unsigned long long)P * (K / rl) < 2ull * gsize) rl >>= 1;
             const unsigned long long rpi = K / rl, total_runs = (unsigned long long)P * rpi;
-            /* --- search: lanes take 32-attempt runs; the first surviving attempt wins */
+            /* --- search: lanes take runs of attempts; the first surviving attempt wins */
             {
-                Lane L; L.mode = IDLE;
-                uint32_t item = 0, a_end = 0; bool out_of_runs = false;
+                Lane L; L.mode = IDLE; L.tries = 0;
+                uint32_t item = 0; bool out_of_runs = false;
                 for (;;) {
                     unsigned idle = __ballot_sync(FULL, L.mode == IDLE);
                     if (idle && !out_of_runs) {
@@ -307,26 +366,22 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                             const TailItem it = p.items[item];
                             L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
                             L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
-                            L.a = it.a + (uint32_t)(run / P) * rl; a_end = L.a + rl;
+                            L.a = it.a + (uint32_t)(run / P) * rl; L.a_end = L.a + rl;
                             L.off = (L.a == it.a) && (it.flags & 4u);
+                            /* skip the run when an earlier attempt has already survived (checked once per run) */
                             if ((__ldcg(&p.found[item]) >> 8) >= (unsigned long long)L.a) { L.mode = SEARCH; begin_attempt(L, p, iter); }
                         }
                         idle = __ballot_sync(FULL, L.mode == IDLE);
                     }
                     if (idle == FULL) { if (out_of_runs) break; else continue; }
                     if (L.mode == IDLE) continue;
-                    const bool ended = jump_step(L, p, sm, iter, n, top_step);
+                    const bool event = jump_step(L, p, sm, iter, n, false, c_attempts);
                     c_jumps++;
-                    if (!ended) continue;
-                    c_attempts++;
-                    if ((L.t >= L.y) && (sm.s[L.j] != 0.0)) {
+                    if (!event) continue;
+                    /* the run's last attempt failed, or an attempt survived */
+                    if ((L.t >= L.y) && (sm.s[L.j] != 0.0))
                         atomicMin(&p.found[item], ((unsigned long long)L.a << 8) | (unsigned long long)L.j);
-                        L.mode = IDLE;
-                    } else {
-                        L.a++; L.off = false;
-                        if (L.a >= a_end || (__ldcg(&p.found[item]) >> 8) < (unsigned long long)L.a) L.mode = IDLE;
-                        else begin_attempt(L, p, iter);
-                    }
+                    L.mode = IDLE;
                 }
             }
             grid.sync();
@@ -379,12 +434,13 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             const uint32_t n_done = p.state->n_done;
             for (unsigned long long i = gtid; i < n_done; i += gsize) {
                 const TailItem it = p.items[p.done[i]];
-                Lane L;
+                Lane L; L.tries = 0;
                 L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
                 L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
                 L.cur_a = it.cur_a; L.cur_off = it.flags & 2u;
                 start_replay(L, p, sm, iter, n);
-                while (!jump_step(L, p, sm, iter, n, top_step)) c_jumps++;
+                unsigned long long dummy = 0;
+                while (!jump_step(L, p, sm, iter, n, false, dummy)) c_jumps++;
                 c_jumps++;
                 finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
                 c_paths++;
