@@ -104,6 +104,7 @@ static SweepParams sweep_params(pht_engine *e) {
     p.model = e->d_model; p.stats = e->d_stats; p.state = e->d_state;
     p.n = e->cfg.n; p.m = e->cfg.m; p.mhit = e->cfg.mhit; p.zbits = e->cfg.zbits;
     p.k0 = (uint32_t)e->cfg.seed; p.k1 = (uint32_t)(e->cfg.seed >> 32);
+    pht_roundkeys_init(&p.rk, p.k0, p.k1);
     p.items = e->d_items; p.pend0 = e->d_pend0; p.pend1 = e->d_pend1; p.done = e->d_done; p.found = e->d_found;
     p.item_cap = e->item_cap; p.mhrs_cap = e->cfg.mhrs_cap;
     return p;

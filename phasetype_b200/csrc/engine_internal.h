@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "../../include/pht_b200.h"
+#include "pht_philox.h"
 
 #define PHT_NMAX PHT_MAX_PHASES
 
@@ -77,6 +78,7 @@ struct SweepParams {
     double *model; long long *stats; DevState *state;
     int n, m, mhit, zbits;
     uint32_t k0, k1;           /* Philox key */
+    pht_roundkeys rk;          /* its ten round keys (constant-bank operands of the path kernels) */
     /* MHRS tail lists */
     TailItem *items; uint32_t *pend0, *pend1, *done; unsigned long long *found; uint32_t item_cap;
     int mhrs_cap;

@@ -11,32 +11,38 @@
  *   - Every rejection attempt is its own Philox sub-stream (pht_philox.h), so attempts
  *     are independent work items and "the first attempt that survives" is well defined
  *     whatever order they run in.
- *   - SEARCH / REPLAY split: while searching, a lane tracks only (t, state); the 26 of 27
+ *   - SEARCH / REPLAY split: while searching, a lane tracks only (t, state); the 21 of 22
  *     attempts that fail never touch N or z.  The accepted attempt is replayed once from
  *     its (attempt index, offset) with recording on.  No per-attempt zeroing of N2/z2.
- *   - One jump-step is one Philox block: {state uniform of this jump, exponential uniform
- *     of the next}; the attempt's first step uses the same code with the start
- *     distribution as the scan row, and a FAILED attempt restarts the lane on the next
- *     sub-stream inside the same branch-free step, so fresh, running, failing, searching
- *     and replaying lanes execute one instruction stream.  Only the rare events (a
- *     surviving attempt, the end of a replay, a hand-over to the tail) leave it.
+ *   - One jump-step (walk_step) is one Philox block: {state uniform of this jump,
+ *     exponential uniform of the next}; the attempt's first step uses the same code with
+ *     the start distribution as the scan row, and a failed attempt restarts the lane on
+ *     the next sub-stream with a handful of selects, so fresh, running and failing lanes
+ *     execute one instruction stream.  Only the rare events (a surviving attempt, a
+ *     hand-over to the tail) leave it.
  *   - The categorical scan `while (sofar < target) sofar += p[k++]` is answered from
  *     precomputed running sums: a 64-bucket guide table indexed by the top 6 random bits
  *     gives a lower bound of the answer, one or two comparisons finish it (same result as
  *     the sequential scan because the running sums are non-decreasing).
  *   - Lane phase: persistent warps, one observation per lane, refilled from a global
- *     counter in warp-sized chunks as lanes finish (attempt counts are geometric with a
- *     heavy tail).  A lane gives up after `cap` attempts and appends the
- *     observation to the tail list.
- *   - Tail phase (same cooperative launch, grid barriers between rounds): all lanes of the
- *     GPU search each pending observation's attempts in parallel, 32-attempt runs handed
- *     out from a global counter, chunk size doubling per round; atomicMin keeps the first
- *     surviving attempt; one thread per observation then advances its MH state machine.
+ *     counter in warp-sized chunks (prefetched into shared memory) as lanes finish.
+ *     Accepted attempts go to a per-warp ring in shared memory; when the ring holds two
+ *     warps' worth, the whole warp replays them together, so the recording code runs
+ *     converged instead of on one or two lanes at a time.  A lane gives up after `cap`
+ *     attempts (attempt counts are geometric with a heavy tail) and appends
+ *     the observation to the tail list.
+ *   - Tail phase (same cooperative launch, grid barriers between rounds): the attempts of
+ *     every pending observation are searched by all warps of the GPU.  A warp takes a pool
+ *     of consecutive attempts of ONE observation from a global counter (pool size shrinks
+ *     as the round drains), its lanes draw attempt indices from the pool with a ballot (no
+ *     memory traffic), the lowest surviving attempt wins through atomicMin; one thread per
+ *     observation then advances its MH state machine.  Attempts per observation double per
+ *     round.
  *   - Statistics: N, B in shared-memory integer atomics; z per path in a per-lane shared
  *     slab (bit-identical to the reference's z2), then added as int64 fixed point, so the
  *     sweep totals do not depend on scheduling or on the number of GPUs.
  *
- * Roofline: FP64/issue bound (one log + ~n compares per jump-step, 12 B of HBM per path).
+ * Roofline: FP64/issue bound (one log + one Philox block per jump-step, 9 B of HBM per path).
  */
 #include <cooperative_groups.h>
 #include "engine_internal.h"
@@ -45,64 +51,89 @@
 namespace cg = cooperative_groups;
 
 #define MHRS_THREADS 256
+#define MHRS_WARPS (MHRS_THREADS / 32)
 #ifndef MHRS_MIN_BLOCKS
 #define MHRS_MIN_BLOCKS 3                /* 80 registers: 24 warps per SM */
 #endif
-#define RUN_LEN 4u                  /* attempts per tail work unit (short: a round ends when its slowest run does) */
 #define GUIDE 64                    /* buckets of the scan guide table */
+#define OBS_CHUNK 64u               /* observations a warp takes from the global counter at once */
+#define END_CAP 8u                   /* attempts a lane still tries once no observations are left */
+#define RING 96                     /* per-warp ring of accepted attempts awaiting replay */
+#define RING_TRIGGER 64
+#define TAIL_CH 256u                /* attempts per tail chunk (a pool never crosses a chunk) */
 #define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
 #define TAIL_KMAX (1u << 24)
-#define OBS_CHUNK 64u               /* observations a warp takes from the global counter at once */
+#define POOL_MIN 32u
+#define POOL_MAX 2048u
 #define FOUND_NONE 0xFFFFFFFFFFFFFFFFull
 
-enum { IDLE = 0, SEARCH = 1, REPLAY = 2 };
-
 struct Smem {
-    double *scale, *s, *cum, *z2;
+    double *scale, *cum, *z2;
     long long *zacc; unsigned int *Nacc, *Bacc;
-    unsigned char *guide;            /* (n+1) x GUIDE lower bounds of the scan result */
+    double *ybuf; double *ring_y; uint32_t *ring_obs, *ring_a; unsigned int *ring_n;
+    unsigned char *cbuf, *ring_fl, *guide;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
 }
 
+__host__ __device__ inline size_t mhrs_smem_bytes_of(int n) {
+    size_t o = 0;
+    o += sizeof(double) * (size_t)(n + (n + 1) * (n + 1) + n * MHRS_THREADS + n + MHRS_WARPS * OBS_CHUNK + MHRS_WARPS * RING);
+    o += sizeof(unsigned int) * (size_t)(n * n + n + 2 * MHRS_WARPS * RING + MHRS_WARPS);
+    o += (size_t)(MHRS_WARPS * OBS_CHUNK + MHRS_WARPS * RING + (n + 1) * GUIDE);
+    return (o + 15) & ~(size_t)15;
+}
 __device__ __forceinline__ Smem carve(unsigned char *raw, int n) {
     Smem sm; double *d = reinterpret_cast<double *>(raw);
     sm.scale = d; d += n;
-    sm.s = d; d += n;
     sm.cum = d; d += (n + 1) * (n + 1);
     sm.z2 = d; d += n * MHRS_THREADS;
     sm.zacc = reinterpret_cast<long long *>(d); d += n;
-    sm.Nacc = reinterpret_cast<unsigned int *>(d);
-    sm.Bacc = sm.Nacc + n * n;
-    sm.guide = reinterpret_cast<unsigned char *>(sm.Bacc + n);
+    sm.ybuf = d; d += MHRS_WARPS * OBS_CHUNK;
+    sm.ring_y = d; d += MHRS_WARPS * RING;
+    unsigned int *u = reinterpret_cast<unsigned int *>(d);
+    sm.Nacc = u; u += n * n;
+    sm.Bacc = u; u += n;
+    sm.ring_obs = u; u += MHRS_WARPS * RING;
+    sm.ring_a = u; u += MHRS_WARPS * RING;
+    sm.ring_n = u; u += MHRS_WARPS;
+    unsigned char *c = reinterpret_cast<unsigned char *>(u);
+    sm.cbuf = c; c += MHRS_WARPS * OBS_CHUNK;
+    sm.ring_fl = c; c += MHRS_WARPS * RING;
+    sm.guide = c;
     return sm;
 }
-size_t pht_mhrs_smem_bytes(int n) {
-    return sizeof(double) * (size_t)(2 * n + (n + 1) * (n + 1) + n * MHRS_THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n) + (size_t)(n + 1) * GUIDE;
+size_t pht_mhrs_smem_bytes(int n) { return mhrs_smem_bytes_of(n); }
+
+/* Philox4x32-10 block (b, a, observation, sweep) with the round keys taken from the kernel parameters */
+__device__ __forceinline__ pht_u32x4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SweepParams &p) {
+    PHT_PHILOX_ROUND(p.rk.k[0], p.rk.k[1])   PHT_PHILOX_ROUND(p.rk.k[2], p.rk.k[3])   PHT_PHILOX_ROUND(p.rk.k[4], p.rk.k[5])
+    PHT_PHILOX_ROUND(p.rk.k[6], p.rk.k[7])   PHT_PHILOX_ROUND(p.rk.k[8], p.rk.k[9])   PHT_PHILOX_ROUND(p.rk.k[10], p.rk.k[11])
+    PHT_PHILOX_ROUND(p.rk.k[12], p.rk.k[13]) PHT_PHILOX_ROUND(p.rk.k[14], p.rk.k[15]) PHT_PHILOX_ROUND(p.rk.k[16], p.rk.k[17])
+    PHT_PHILOX_ROUND(p.rk.k[18], p.rk.k[19])
+    pht_u32x4 out; out.v[0] = c0; out.v[1] = c1; out.v[2] = c2; out.v[3] = c3;
+    return out;
 }
 
-struct Lane {
-    double y, t, lastt, spare;
-    uint32_t spare_hi;          /* high random word behind `spare` (guide-table bucket) */
-    uint32_t obs_local, obs_global;
-    uint32_t a, b;              /* attempt (= sub-stream) and next Philox block inside it */
-    uint32_t a_end;             /* tail phase: first attempt index beyond this lane's run */
-    uint32_t cur_a, tries;
-    int j, B;
-    int mode;
-    int cur_pre, kprop;
-    bool cens, odd, fresh, off, have_cur, cur_off;
+/* the chain of one attempt: sub-stream a, next Philox block b, time t of the pending exit from state j */
+struct Walk {
+    double t, spare;
+    uint32_t spare_hi, a, b;
+    int j;
+    bool odd, fresh;
 };
+/* recording state of a replayed path */
+struct Rec { double lastt; int B; long out_idx; };
 
-/* position the lane on the first draw of attempt L.a; off = the MH accept uniform of the
- * previous proposal occupies draw 0 of this sub-stream (src/Simulate_AbsCTMC_eq_Bladt_MHRS.c:79) */
-__device__ __forceinline__ void begin_attempt(Lane &L, const SweepParams &p, uint32_t iter) {
-    L.fresh = true; L.b = 0; L.odd = false;
-    if (L.off) {
-        pht_u32x4 r = pht_philox4x32_10(0u, L.a, L.obs_global, iter, p.k0, p.k1);
-        L.spare = pht_u01(r.v[2], r.v[3]); L.spare_hi = r.v[3]; L.odd = true; L.b = 1;
+/* position the walk on the first draw of attempt a; off = the MH accept uniform of the previous proposal
+ * occupies draw 0 of this sub-stream (src/Simulate_AbsCTMC_eq_Bladt_MHRS.c:79) */
+__device__ __forceinline__ void walk_begin(Walk &w, uint32_t a, bool off, uint32_t obs_global, const SweepParams &p, uint32_t iter) {
+    w.a = a; w.fresh = true; w.b = 0; w.odd = false; w.t = 0.0; w.j = 0;
+    if (off) {
+        pht_u32x4 r = philox_block(0u, a, obs_global, iter, p);
+        w.spare = pht_u01(r.v[2], r.v[3]); w.spare_hi = r.v[3]; w.odd = true; w.b = 1;
     }
 }
 
@@ -130,103 +161,139 @@ __device__ __forceinline__ double log_unit(double x) {
     return dk * LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LN2_LO)) - f);
 }
 
-/* One jump-step.  Returns true when the lane needs the (divergent) event handler: a searching attempt that
- * survived, a replay that finished, or a failed attempt that must not simply restart (`stop_on_fail`, or the
- * lane's run of attempts [a, a_end) is used up).  A failed attempt otherwise restarts on sub-stream a+1 right
- * here.  No control flow around the expensive parts (Philox, scan, log): every lane of the warp runs the same
- * instructions and differs only in selects. */
-__device__ __forceinline__ bool jump_step(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n, bool stop_on_fail,
-                                          unsigned long long &c_attempts) {
-    pht_u32x4 r = pht_philox4x32_10(L.b, L.a, L.obs_global, iter, p.k0, p.k1);
-    L.b++;
+/* One jump-step of a walk; returns true when the attempt ended on this step (w.t, w.j are then the exit time
+ * and the state occupied at the end).  No control flow around the expensive parts (Philox, scan, log). */
+template <bool RECORD>
+__device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t obs_global, const SweepParams &p, const Smem &sm,
+                                          uint32_t iter, int n, Rec &rec) {
+    pht_u32x4 r = philox_block(w.b, w.a, obs_global, iter, p);
+    w.b++;
     const double f = pht_u01(r.v[0], r.v[1]), g = pht_u01(r.v[2], r.v[3]);
-    const double uA = L.odd ? L.spare : f;               /* start state / next state */
-    const uint32_t hiA = L.odd ? L.spare_hi : r.v[1];
-    const double uB = L.odd ? f : g;                     /* next exponential */
-    L.spare = g; L.spare_hi = r.v[3];
-    const bool fresh = L.fresh;
-    const int row = fresh ? n : L.j;
+    const double uA = w.odd ? w.spare : f;               /* start state / next state */
+    const uint32_t hiA = w.odd ? w.spare_hi : r.v[1];
+    const double uB = w.odd ? f : g;                     /* next exponential */
+    w.spare = g; w.spare_hi = r.v[3];
+    const bool fresh = w.fresh;
+    const int row = fresh ? n : w.j;
     const int last = fresh ? n - 1 : n;
     const double *c = sm.cum + row * (n + 1);
     /* reference scan `while (sofar < target) sofar += p[k++]` = number of running sums below the target among the
      * first `last` (the sums are non-decreasing).  The guide entry counts the sums <= bucket floor < uA. */
     int k = sm.guide[row * GUIDE + (hiA >> 26)];
     while (k < last && c[k] < uA) k++;
-    const bool cont = (k < n) && (L.t < L.y || L.cens);             /* gt_Bladt_MHRS.c:75,111 */
+    const bool cont = (k < n) && (w.t < y || cens);                /* gt_Bladt_MHRS.c:75,111 */
     const bool ended = !fresh && !cont;
     const bool advance = !fresh && cont;
-    if (advance && L.mode == REPLAY) {
-        sm.z2[L.j * MHRS_THREADS + threadIdx.x] += L.t - L.lastt;                  /* :112 */
-        if (p.outN != nullptr) p.outN[(size_t)(L.obs_local - p.first) * n * n + L.j + k * n]++;
-        else atomicAdd(&sm.Nacc[L.j + k * n], 1u);                                 /* :113 */
+    if (RECORD) {
+        if (advance) {
+            sm.z2[w.j * MHRS_THREADS + threadIdx.x] += w.t - rec.lastt;            /* :112 */
+            if (p.outN != nullptr) p.outN[(size_t)rec.out_idx * n * n + w.j + k * n]++;
+            else atomicAdd(&sm.Nacc[w.j + k * n], 1u);                             /* :113 */
+        }
+        rec.lastt = fresh ? 0.0 : (advance ? w.t : rec.lastt);
+        rec.B = fresh ? k : rec.B;
     }
-    const double tb = fresh ? 0.0 : L.t;
-    L.lastt = fresh ? 0.0 : (advance ? L.t : L.lastt);
-    L.j = ended ? L.j : k;
-    L.B = fresh ? k : L.B;
-    const double tn = tb + sm.scale[L.j] * (-log_unit(uB));         /* :80, rexp(1/-S_jj) */
-    L.t = ended ? L.t : tn;
-    /* an ended searching attempt survives when it reached y in a state that can exit (eq_Bladt_MHRS.c:66,74) */
-    const bool searching = L.mode == SEARCH;
-    const bool ok = (L.t >= L.y) && (sm.s[L.j] != 0.0);
-    const bool failed = ended && searching && !ok;
-    c_attempts += (ended && searching) ? 1ull : 0ull;
-    L.tries += failed ? 1u : 0u;
-    const bool restart = failed && !stop_on_fail && (L.a + 1u < L.a_end);
-    /* restart on the next sub-stream (begin_attempt with off = false) */
-    L.a += failed ? 1u : 0u;
-    L.off = failed ? false : L.off;
-    L.fresh = restart;
-    L.b = restart ? 0u : L.b;
-    L.odd = restart ? false : L.odd;
-    return ended && !restart;
+    const double tb = fresh ? 0.0 : w.t;
+    const int jn = ended ? w.j : k;
+    const double tn = tb + sm.scale[jn] * (-log_unit(uB));         /* :80, rexp(1/-S_jj) */
+    w.t = ended ? w.t : tn;
+    w.j = jn;
+    w.fresh = false;
+    return ended;
 }
 
 /* close a replayed path: gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110 */
-__device__ __forceinline__ void finish_replay(Lane &L, const SweepParams &p, const Smem &sm, int n, long out_idx) {
+__device__ __forceinline__ void finish_replay(const Walk &w, const Rec &rec, double y, bool cens, const SweepParams &p, const Smem &sm, int n) {
     const int tid = threadIdx.x;
-    sm.z2[L.j * MHRS_THREADS + tid] += (L.cens ? L.t : L.y) - L.lastt;
+    sm.z2[w.j * MHRS_THREADS + tid] += (cens ? w.t : y) - rec.lastt;
     if (p.outB != nullptr) {
-        p.outB[out_idx] = L.B;
-        p.outN[out_idx * n * n + L.j + L.j * n]++;
-        for (int i = 0; i < n; i++) p.outz[out_idx * n + i] = sm.z2[i * MHRS_THREADS + tid];
+        p.outB[rec.out_idx] = rec.B;
+        p.outN[rec.out_idx * n * n + w.j + w.j * n]++;
+        for (int i = 0; i < n; i++) { p.outz[rec.out_idx * n + i] = sm.z2[i * MHRS_THREADS + tid]; sm.z2[i * MHRS_THREADS + tid] = 0.0; }
     } else {
-        atomicAdd(&sm.Nacc[L.j + L.j * n], 1u);
-        atomicAdd(&sm.Bacc[L.B], 1u);
+        atomicAdd(&sm.Nacc[w.j + w.j * n], 1u);
+        atomicAdd(&sm.Bacc[rec.B], 1u);
         const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
         for (int i = 0; i < n; i++) {
             const double v = sm.z2[i * MHRS_THREADS + tid];
             if (v != 0.0) {
                 if (!(v * zs < 4.0e18)) atomicOr(&p.state->error, 2);
                 atomicAdd(reinterpret_cast<unsigned long long *>(&sm.zacc[i]), (unsigned long long)__double2ll_rn(v * zs));
+                sm.z2[i * MHRS_THREADS + tid] = 0.0;
             }
         }
     }
 }
 
-__device__ __forceinline__ void start_replay(Lane &L, const SweepParams &p, const Smem &sm, uint32_t iter, int n) {
-    L.mode = REPLAY; L.a = L.cur_a; L.off = L.cur_off; L.a_end = 0xFFFFFFFFu;
-    begin_attempt(L, p, iter);
-    for (int i = 0; i < n; i++) sm.z2[i * MHRS_THREADS + threadIdx.x] = 0.0;
+/* replay one accepted attempt start to end (the lane's z2 slab is all zero on entry and on exit) */
+__device__ __forceinline__ unsigned replay_path(uint32_t obs_local, uint32_t a, bool off, double y, bool cens, const SweepParams &p,
+                                                const Smem &sm, uint32_t iter, int n) {
+    Walk w; Rec rec; rec.lastt = 0.0; rec.B = 0; rec.out_idx = (long)obs_local - p.first;
+    const uint32_t og = p.obs_rank + obs_local * p.obs_world;
+    walk_begin(w, a, off, og, p, iter);
+    unsigned steps = 1;
+    while (!walk_step<true>(w, y, cens, og, p, sm, iter, n, rec)) steps++;
+    finish_replay(w, rec, y, cens, p, sm, n);
+    return steps;
 }
 
-__device__ __forceinline__ uint32_t pack_flags(const Lane &L) {
-    return (L.have_cur ? 1u : 0u) | (L.cur_off ? 2u : 0u) | (L.off ? 4u : 0u) |
-           ((uint32_t)(L.cur_pre & 0xff) << 8) | ((uint32_t)L.kprop << 16);
+/* the whole warp replays the accepted attempts waiting in its ring */
+__device__ __forceinline__ void replay_session(const SweepParams &p, const Smem &sm, uint32_t iter, int n, int warp,
+                                               unsigned &c_jumps, unsigned &c_paths) {
+    const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const unsigned count = sm.ring_n[warp];
+    unsigned next = 0;
+    Walk w; Rec rec; double y = 0.0; bool cens = false, active = false; uint32_t og = 0;
+    rec.lastt = 0.0; rec.B = 0; rec.out_idx = 0;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && next < count) {
+            const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+            if (!active && next + rank < count) {
+                const unsigned e = warp * RING + next + rank;
+                const uint32_t ol = sm.ring_obs[e]; const unsigned fl = sm.ring_fl[e];
+                y = sm.ring_y[e]; cens = fl & 1u; og = p.obs_rank + ol * p.obs_world;
+                rec.lastt = 0.0; rec.B = 0; rec.out_idx = (long)ol - p.first;
+                walk_begin(w, sm.ring_a[e], (fl & 2u) != 0u, og, p, iter);
+                active = true;
+            }
+            const unsigned cnt = __popc(idle);
+            next = next + cnt < count ? next + cnt : count;
+            idle = __ballot_sync(FULL, !active);
+        }
+        if (idle == FULL) break;
+        if (!active) continue;
+        const bool ended = walk_step<true>(w, y, cens, og, p, sm, iter, n, rec);
+        c_jumps++;
+        if (ended) { finish_replay(w, rec, y, cens, p, sm, n); c_paths++; active = false; }
+    }
+    __syncwarp();
+    if (lane == 0) sm.ring_n[warp] = 0u;
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t pack_flags(bool have_cur, bool cur_off, bool off, int cur_pre, int kprop) {
+    return (have_cur ? 1u : 0u) | (cur_off ? 2u : 0u) | (off ? 4u : 0u) | ((uint32_t)(cur_pre & 0xff) << 8) | ((uint32_t)kprop << 16);
 }
 
 __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::grid_group grid = cg::this_grid();
-    const int n = p.n, tid = threadIdx.x, lane = tid & 31;
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const ModelLayout ML = ModelLayout::make(n, p.m);
     Smem sm = carve(smem_raw, n);
     const uint32_t iter = p.state->iter;
 
-    for (int i = tid; i < n; i += MHRS_THREADS) { sm.scale[i] = p.model[ML.scale + i]; sm.s[i] = p.model[ML.s + i]; sm.zacc[i] = 0; sm.Bacc[i] = 0u; }
+    for (int i = tid; i < n; i += MHRS_THREADS) { sm.scale[i] = p.model[ML.scale + i]; sm.zacc[i] = 0; sm.Bacc[i] = 0u; }
     for (int i = tid; i < (n + 1) * (n + 1); i += MHRS_THREADS) sm.cum[i] = p.model[ML.cum + i];
     for (int i = tid; i < n * n; i += MHRS_THREADS) sm.Nacc[i] = 0u;
+    for (int i = 0; i < n; i++) sm.z2[i * MHRS_THREADS + tid] = 0.0;
+    if (tid < MHRS_WARPS) sm.ring_n[tid] = 0u;
+    /* states that can exit: bit j of smask (the accept tests of eq_Bladt_MHRS.c:66,74 need s[j] != 0) */
+    uint32_t smask = 0u;
+    for (int i = 0; i < n; i++) smask |= (p.model[ML.s + i] != 0.0) ? (1u << i) : 0u;
     __syncthreads();
     /* guide[row][b] = #{ i < last(row) : cum[row][i] <= b / GUIDE }: every uniform of bucket b is > b / GUIDE */
     for (int e = tid; e < (n + 1) * GUIDE; e += MHRS_THREADS) {
@@ -238,90 +305,119 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
     }
     __syncthreads();
 
-    unsigned long long c_attempts = 0, c_jumps = 0, c_paths = 0, c_deferred = 0;
+    unsigned c_attempts = 0, c_jumps = 0, c_paths = 0, c_deferred = 0;      /* per thread and sweep: far below 2^32 */
     const unsigned long long t_start = gtimer();
     const bool per_obs = p.outB != nullptr;
     const unsigned long long obs_begin = per_obs ? (unsigned long long)p.first : 0ull;
     const unsigned long long obs_end = per_obs ? (unsigned long long)(p.first + p.count) : (unsigned long long)p.l_local;
     const uint32_t cap = (uint32_t)p.mhrs_cap;
+    const double *s_model = p.model + ML.s;
+    Rec norec; norec.lastt = 0.0; norec.B = 0; norec.out_idx = 0;
 
     /* ---------------------------------------------------------------- lane phase */
     {
-        Lane L; L.mode = IDLE; L.tries = 0; L.a_end = 0xFFFFFFFFu;
-        unsigned long long chunk_next = 0, chunk_end = 0;      /* warp-uniform */
-        bool exhausted = false;
+        Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
+        bool active = false, cens = false, off = false, have_cur = false, cur_off = false;
+        double y = 0.0; uint32_t obs_local = 0, og = 0, tries = 0, cur_a = 0; int cur_pre = 0, kprop = 0;
+        unsigned long long chunk_base = 0; unsigned chunk_next = 0, chunk_len = 0;      /* warp-uniform */
+        bool exhausted = false, dry = false;      /* this warp found the stream empty / some warp did */
+        unsigned it_count = 0;
         for (;;) {
-            unsigned idle = __ballot_sync(FULL, L.mode == IDLE);
+            /* every 64 steps, look whether the observation stream has run dry elsewhere: a warp whose lanes are all
+             * busy would otherwise never notice and grind on to `cap` while the rest of the grid waits */
+            if (((++it_count) & 63u) == 0u && !dry) {
+                unsigned long long nx = 0;
+                if (lane == 0) nx = __ldcg(&p.state->next_obs);
+                dry = obs_begin + __shfl_sync(FULL, nx, 0) >= obs_end;
+            }
+            unsigned idle = __ballot_sync(FULL, !active);
             if (idle && !exhausted) {
-                if (chunk_next == chunk_end) {
+                if (chunk_next == chunk_len) {
                     unsigned long long base = 0;
                     if (lane == 0) base = obs_begin + atomicAdd(&p.state->next_obs, (unsigned long long)OBS_CHUNK);
                     base = __shfl_sync(FULL, base, 0);
-                    chunk_next = base < obs_end ? base : obs_end;
-                    chunk_end = base + OBS_CHUNK < obs_end ? base + OBS_CHUNK : obs_end;
-                    if (chunk_next == chunk_end) exhausted = true;
+                    chunk_base = base < obs_end ? base : obs_end;
+                    const unsigned long long end = base + OBS_CHUNK < obs_end ? base + OBS_CHUNK : obs_end;
+                    chunk_len = (unsigned)(end > chunk_base ? end - chunk_base : 0ull); chunk_next = 0;
+                    if (chunk_len == 0u) exhausted = true;
+                    /* prefetch the chunk's observations (coalesced) into this warp's staging buffer */
+                    __syncwarp();
+                    for (unsigned q = lane; q < chunk_len; q += 32u) {
+                        sm.ybuf[warp * OBS_CHUNK + q] = p.y[chunk_base + q];
+                        sm.cbuf[warp * OBS_CHUNK + q] = p.cens[chunk_base + q];
+                    }
+                    __syncwarp();
                 }
-                const unsigned avail = (unsigned)(chunk_end - chunk_next);
+                const unsigned avail = chunk_len - chunk_next;
                 const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-                if (L.mode == IDLE && rank < avail) {
-                    L.obs_local = (uint32_t)(chunk_next + rank);
-                    L.obs_global = p.obs_rank + L.obs_local * p.obs_world;
-                    L.y = p.y[L.obs_local]; L.cens = p.cens[L.obs_local] != 0;
-                    L.mode = SEARCH; L.a = 0; L.off = false; L.have_cur = false; L.kprop = 0; L.tries = 0;
-                    L.cur_a = 0; L.cur_off = false; L.cur_pre = 0; L.a_end = 0xFFFFFFFFu;
-                    begin_attempt(L, p, iter);
+                if (!active && rank < avail) {
+                    const unsigned q = chunk_next + rank;
+                    obs_local = (uint32_t)(chunk_base + q);
+                    og = p.obs_rank + obs_local * p.obs_world;
+                    y = sm.ybuf[warp * OBS_CHUNK + q]; cens = sm.cbuf[warp * OBS_CHUNK + q] != 0;
+                    active = true; off = false; have_cur = false; kprop = 0; tries = 0; cur_a = 0; cur_off = false; cur_pre = 0;
+                    walk_begin(w, 0u, false, og, p, iter);
                 }
-                const unsigned taken = __popc(idle) < avail ? __popc(idle) : avail;
-                chunk_next += taken;
-                idle = __ballot_sync(FULL, L.mode == IDLE);
+                const unsigned cnt = __popc(idle);
+                chunk_next += cnt < avail ? cnt : avail;
+                idle = __ballot_sync(FULL, !active);
             }
             if (idle == FULL) { if (exhausted) break; else continue; }
-            if (L.mode == IDLE) continue;
-
-            /* a failed attempt restarts inside the step unless the lane is due to hand the observation over: after
-             * `cap` attempts, or as soon as the observation stream has run dry (a lone lane grinding through
-             * attempts would hold the whole grid at the barrier) */
-            const bool stop_on_fail = cap != 0u && (L.tries + 1u >= cap || exhausted);
-            const bool event = jump_step(L, p, sm, iter, n, stop_on_fail, c_attempts);
-            c_jumps++;
-            if (!event) continue;
-
-            if (L.mode == REPLAY) {
-                finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
-                c_paths++; L.mode = IDLE;
-                continue;
+            if (active) {
+                const bool ended = walk_step<false>(w, y, cens, og, p, sm, iter, n, norec);
+                c_jumps++;
+                /* an ended attempt survives when it reached y in a state that can exit (eq_Bladt_MHRS.c:66,74) */
+                const bool ok = (w.t >= y) && ((smask >> w.j) & 1u);
+                const bool failed = ended && !ok;
+                c_attempts += ended ? 1u : 0u;
+                tries += failed ? 1u : 0u;
+                /* a failed attempt restarts on the next sub-stream right here, unless the lane is due to hand the
+                 * observation over: after `cap` attempts, or after END_CAP once the observation stream has run dry
+                 * (a lone lane grinding through attempts would hold the whole grid at the barrier) */
+                const bool handover = cap != 0u && (tries >= cap || ((exhausted || dry) && tries >= END_CAP));
+                const bool restart = failed && !handover;
+                w.a += failed ? 1u : 0u;
+                off = failed ? false : off;
+                w.fresh = restart; w.b = restart ? 0u : w.b; w.odd = restart ? false : w.odd;
+                if (ended && !restart) {
+                    bool accepted = false;
+                    if (!ok) {
+                        const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
+                        if (idx < p.item_cap) {
+                            TailItem it; it.obs_local = obs_local; it.a = w.a; it.cur_a = cur_a;
+                            it.flags = pack_flags(have_cur, cur_off, false, cur_pre, kprop);
+                            p.items[idx] = it; p.found[idx] = FOUND_NONE;
+                        } else atomicOr(&p.state->error, 4);
+                        c_deferred++; active = false;
+                    } else if (!have_cur) {
+                        have_cur = true; cur_a = w.a; cur_off = off; cur_pre = w.j;
+                        if (cens || p.mhit == 0) accepted = true;                              /* :70 */
+                        else { off = false; walk_begin(w, w.a + 1u, false, og, p, iter); }
+                    } else {
+                        /* a valid proposal: accept test with draw 0 of the next sub-stream (:79-82) */
+                        pht_u32x4 r = philox_block(0u, w.a + 1u, og, iter, p);
+                        const double U = pht_u01(r.v[0], r.v[1]);
+                        if (U < s_model[w.j] / s_model[cur_pre]) { cur_a = w.a; cur_off = off; cur_pre = w.j; }
+                        kprop++;
+                        if (kprop >= p.mhit) accepted = true;
+                        else {
+                            /* next proposal: sub-stream a+1 from draw 1 (the spare half of the block just computed) */
+                            off = true; w.a++; w.fresh = true; w.b = 1; w.odd = true; w.t = 0.0;
+                            w.spare = pht_u01(r.v[2], r.v[3]); w.spare_hi = r.v[3];
+                        }
+                    }
+                    if (accepted) {
+                        const unsigned e = warp * RING + atomicAdd(&sm.ring_n[warp], 1u);
+                        sm.ring_y[e] = y; sm.ring_obs[e] = obs_local; sm.ring_a[e] = cur_a;
+                        sm.ring_fl[e] = (unsigned char)((cens ? 1u : 0u) | (cur_off ? 2u : 0u));
+                        active = false;
+                    }
+                }
             }
-            /* SEARCH: an attempt just ended (gt_Bladt_MHRS.c:49 decides whether it survives) */
-            const bool ok = (L.t >= L.y) && (sm.s[L.j] != 0.0);            /* eq_Bladt_MHRS.c:66,74 */
-            if (!ok) {
-                /* (the step already moved the lane to attempt a+1, off = false) */
-                if (stop_on_fail) {
-                    const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
-                    if (idx < p.item_cap) {
-                        TailItem it; it.obs_local = L.obs_local; it.a = L.a; it.cur_a = L.cur_a; it.flags = pack_flags(L);
-                        p.items[idx] = it; p.found[idx] = FOUND_NONE;
-                    } else atomicOr(&p.state->error, 4);
-                    c_deferred++; L.mode = IDLE;
-                } else begin_attempt(L, p, iter);
-                continue;
-            }
-            const int pre = L.j;
-            if (!L.have_cur) {
-                L.have_cur = true; L.cur_a = L.a; L.cur_off = L.off; L.cur_pre = pre;
-                if (L.cens || p.mhit == 0) { start_replay(L, p, sm, iter, n); continue; }      /* :70 */
-                L.a++; L.off = false; begin_attempt(L, p, iter);
-                continue;
-            }
-            /* a valid proposal: accept test with draw 0 of the next sub-stream (:79-82) */
-            pht_u32x4 r = pht_philox4x32_10(0u, L.a + 1u, L.obs_global, iter, p.k0, p.k1);
-            const double U = pht_u01(r.v[0], r.v[1]);
-            if (U < sm.s[pre] / sm.s[L.cur_pre]) { L.cur_a = L.a; L.cur_off = L.off; L.cur_pre = pre; }
-            L.kprop++;
-            if (L.kprop >= p.mhit) { start_replay(L, p, sm, iter, n); continue; }
-            /* next proposal: sub-stream a+1 from draw 1 (the spare half of the block just computed) */
-            L.a++; L.off = true;
-            L.fresh = true; L.b = 1; L.odd = true; L.spare = pht_u01(r.v[2], r.v[3]); L.spare_hi = r.v[3];
+            __syncwarp();
+            if (sm.ring_n[warp] >= RING_TRIGGER) replay_session(p, sm, iter, n, warp, c_jumps, c_paths);
         }
+        replay_session(p, sm, iter, n, warp, c_jumps, c_paths);
     }
 
     /* ---------------------------------------------------------------- tail phase */
@@ -333,6 +429,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
     if (n_items != 0u) {
         const unsigned long long gtid = (unsigned long long)blockIdx.x * MHRS_THREADS + tid;
         const unsigned long long gsize = (unsigned long long)gridDim.x * MHRS_THREADS;
+        const unsigned long long nwarps = gsize / 32ull;
         for (unsigned long long i = gtid; i < n_items; i += gsize) p.pend0[i] = (uint32_t)i;
         if (gtid == 0) { p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u; }
         grid.sync();
@@ -342,46 +439,89 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (P == 0u) break;
             const uint32_t *pend = cur ? p.pend1 : p.pend0;
             uint32_t *pend_next = cur ? p.pend0 : p.pend1;
-            /* run length: RUN_LEN attempts per work unit while there is plenty of work, down to single attempts when
-             * only a few heavy observations remain */
-            uint32_t rl = RUN_LEN;
-            while (rl > 1u && (unsigned long long)P * (K / rl) < 2ull * gsize) rl >>= 1;
-            const unsigned long long rpi = K / rl, total_runs = (unsigned long long)P * rpi;
-            /* --- search: lanes take runs of attempts; the first surviving attempt wins */
+            /* The round's work is K attempts for each of the P pending observations, numbered as units in chunk-major
+             * order: unit u belongs to chunk u / TAIL_CH; chunk c covers attempts [ (c / P) TAIL_CH, +TAIL_CH ) beyond
+             * the start attempt of observation pend[c % P].  So the first chunk of every observation is handed out
+             * before any second chunk, and later chunks are mostly skipped once an earlier one has survived. */
+            const unsigned long long total_units = (unsigned long long)P * K;
+            /* --- search: each warp works through pools of consecutive attempts of one observation; a lane keeps the
+             * observation of the pool it drew its attempt from, so the warp moves on to the next pool while slower lanes
+             * are still finishing attempts of the previous one */
             {
-                Lane L; L.mode = IDLE; L.tries = 0;
-                uint32_t item = 0; bool out_of_runs = false;
+                Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
+                bool active = false;
+                uint32_t my_item = 0, my_og = 0; double my_y = 0.0; bool my_cens = false;
+                /* warp-uniform: the units this warp holds, and the pool being handed out */
+                unsigned long long u_next = 0, u_end = 0, last_base = 0;
+                bool out_of_units = false;
+                uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; double y = 0.0; bool cens = false, first_off = false;
                 for (;;) {
-                    unsigned idle = __ballot_sync(FULL, L.mode == IDLE);
-                    if (idle && !out_of_runs) {
-                        unsigned long long base = 0;
-                        if (lane == 0) base = atomicAdd(&p.state->unit_counter, (unsigned long long)__popc(idle));
-                        base = __shfl_sync(FULL, base, 0);
-                        if (base >= total_runs) out_of_runs = true;
-                        const unsigned long long run = base + __popc(idle & ((1u << lane) - 1u));
-                        if (L.mode == IDLE && run < total_runs) {
-                            /* chunk-major order: the first chunk of every pending observation is handed out before
-                             * any second chunk, so later chunks are mostly skipped once an earlier one has survived */
-                            item = pend[run % P];
+                    unsigned idle = __ballot_sync(FULL, !active);
+                    if (idle && pool_next >= pool_end && !out_of_units) {
+                        /* take the next pool (skipping pools that an earlier survivor made moot) */
+                        bool have = false;
+                        while (!have) {
+                            if (u_next >= u_end) {
+                                const unsigned long long remaining = total_units > last_base ? total_units - last_base : 0ull;
+                                unsigned long long want = remaining / (2ull * nwarps);
+                                want = want < POOL_MIN ? POOL_MIN : (want > POOL_MAX ? POOL_MAX : want);
+                                unsigned long long base = 0;
+                                if (lane == 0) base = atomicAdd(&p.state->unit_counter, want);
+                                base = __shfl_sync(FULL, base, 0);
+                                last_base = base;
+                                if (base >= total_units) { out_of_units = true; break; }
+                                u_next = base; u_end = base + want < total_units ? base + want : total_units;
+                            }
+                            const unsigned long long chunk = u_next / TAIL_CH;
+                            const unsigned long long chunk_end_u = (chunk + 1ull) * TAIL_CH;
+                            const unsigned long long stop = u_end < chunk_end_u ? u_end : chunk_end_u;
+                            item = pend[chunk % P];
                             const TailItem it = p.items[item];
-                            L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
-                            L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
-                            L.a = it.a + (uint32_t)(run / P) * rl; L.a_end = L.a + rl;
-                            L.off = (L.a == it.a) && (it.flags & 4u);
-                            /* skip the run when an earlier attempt has already survived (checked once per run) */
-                            if ((__ldcg(&p.found[item]) >> 8) >= (unsigned long long)L.a) { L.mode = SEARCH; begin_attempt(L, p, iter); }
+                            a_first = it.a; first_off = (it.flags & 4u) != 0u;
+                            pool_next = it.a + (uint32_t)(chunk / P) * TAIL_CH + (uint32_t)(u_next - chunk * TAIL_CH);
+                            pool_end = pool_next + (uint32_t)(stop - u_next);
+                            u_next = stop;
+                            if ((__ldcg(&p.found[item]) >> 8) >= (unsigned long long)pool_next) {
+                                have = true;
+                                y = p.y[it.obs_local]; cens = p.cens[it.obs_local] != 0; og = p.obs_rank + it.obs_local * p.obs_world;
+                            } else pool_end = pool_next;
                         }
-                        idle = __ballot_sync(FULL, L.mode == IDLE);
                     }
-                    if (idle == FULL) { if (out_of_runs) break; else continue; }
-                    if (L.mode == IDLE) continue;
-                    const bool event = jump_step(L, p, sm, iter, n, false, c_attempts);
-                    c_jumps++;
-                    if (!event) continue;
-                    /* the run's last attempt failed, or an attempt survived */
-                    if ((L.t >= L.y) && (sm.s[L.j] != 0.0))
-                        atomicMin(&p.found[item], ((unsigned long long)L.a << 8) | (unsigned long long)L.j);
-                    L.mode = IDLE;
+                    if (idle == FULL && pool_next >= pool_end) break;          /* nothing in flight, nothing left to hand out */
+                    if (idle && pool_next < pool_end) {
+                        /* idle lanes draw the next attempt indices of the pool (ballot only, no memory traffic) */
+                        const uint32_t avail = pool_end - pool_next;
+                        const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+                        if (!active && rank < avail) {
+                            const uint32_t a = pool_next + rank;
+                            my_item = item; my_y = y; my_cens = cens; my_og = og;
+                            walk_begin(w, a, first_off && a == a_first, og, p, iter);
+                            active = true;
+                        }
+                        const uint32_t cnt = __popc(idle);
+                        pool_next += cnt < avail ? cnt : avail;
+                    }
+                    bool survived = false;
+                    if (active) {
+                        const bool ended = walk_step<false>(w, my_y, my_cens, my_og, p, sm, iter, n, norec);
+                        c_jumps++;
+                        c_attempts += ended ? 1u : 0u;
+                        survived = ended && (w.t >= my_y) && ((smask >> w.j) & 1u);
+                        active = !ended;
+                    }
+                    const unsigned smk = __ballot_sync(FULL, survived);
+                    if (smk) {
+                        /* every survivor competes for "lowest surviving attempt" of its observation; the first one in
+                         * the warp also calls off the later attempts of the same observation that are in flight here */
+                        if (survived) atomicMin(&p.found[my_item], ((unsigned long long)w.a << 8) | (unsigned long long)w.j);
+                        const int src = __ffs(smk) - 1;
+                        const uint32_t s_item = __shfl_sync(FULL, my_item, src), s_a = __shfl_sync(FULL, w.a, src);
+                        if (active && my_item == s_item && w.a > s_a) active = false;
+                        if (s_item == item && pool_next < pool_end) {
+                            pool_end = pool_end < s_a ? pool_end : s_a;
+                            pool_next = pool_next < pool_end ? pool_next : pool_end;
+                        }
+                    }
                 }
             }
             grid.sync();
@@ -408,14 +548,13 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                         done = cens || p.mhit == 0;
                     } else {
                         const uint32_t og = p.obs_rank + it.obs_local * p.obs_world;
-                        pht_u32x4 r = pht_philox4x32_10(0u, a + 1u, og, iter, p.k0, p.k1);
+                        pht_u32x4 r = philox_block(0u, a + 1u, og, iter, p);
                         const double U = pht_u01(r.v[0], r.v[1]);
-                        if (U < sm.s[pre] / sm.s[cur_pre]) { it.cur_a = a; cur_off = off; cur_pre = pre; }
+                        if (U < s_model[pre] / s_model[cur_pre]) { it.cur_a = a; cur_off = off; cur_pre = pre; }
                         kprop++; done = (int)kprop >= p.mhit; next_off = true;
                     }
                     it.a = a + 1u;
-                    it.flags = (have_cur ? 1u : 0u) | (cur_off ? 2u : 0u) | (next_off ? 4u : 0u) |
-                               ((uint32_t)(cur_pre & 0xff) << 8) | (kprop << 16);
+                    it.flags = pack_flags(have_cur, cur_off, next_off, cur_pre, (int)kprop);
                     p.found[item] = FOUND_NONE;
                 }
                 p.items[item] = it;
@@ -434,15 +573,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             const uint32_t n_done = p.state->n_done;
             for (unsigned long long i = gtid; i < n_done; i += gsize) {
                 const TailItem it = p.items[p.done[i]];
-                Lane L; L.tries = 0;
-                L.obs_local = it.obs_local; L.obs_global = p.obs_rank + it.obs_local * p.obs_world;
-                L.y = p.y[it.obs_local]; L.cens = p.cens[it.obs_local] != 0;
-                L.cur_a = it.cur_a; L.cur_off = it.flags & 2u;
-                start_replay(L, p, sm, iter, n);
-                unsigned long long dummy = 0;
-                while (!jump_step(L, p, sm, iter, n, false, dummy)) c_jumps++;
-                c_jumps++;
-                finish_replay(L, p, sm, n, (long)L.obs_local - p.first);
+                c_jumps += replay_path(it.obs_local, it.cur_a, (it.flags & 2u) != 0u, p.y[it.obs_local], p.cens[it.obs_local] != 0, p, sm, iter, n);
                 c_paths++;
             }
         }
@@ -460,13 +591,14 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (sm.zacc[i]) atomicAdd(&gN[n * n + n + i], (unsigned long long)sm.zacc[i]);
         }
     }
+    unsigned long long w_attempts = c_attempts, w_jumps = c_jumps, w_paths = c_paths, w_deferred = c_deferred;
     for (int o = 16; o > 0; o >>= 1) {
-        c_attempts += __shfl_down_sync(FULL, c_attempts, o); c_jumps += __shfl_down_sync(FULL, c_jumps, o);
-        c_paths += __shfl_down_sync(FULL, c_paths, o); c_deferred += __shfl_down_sync(FULL, c_deferred, o);
+        w_attempts += __shfl_down_sync(FULL, w_attempts, o); w_jumps += __shfl_down_sync(FULL, w_jumps, o);
+        w_paths += __shfl_down_sync(FULL, w_paths, o); w_deferred += __shfl_down_sync(FULL, w_deferred, o);
     }
     if (lane == 0) {
-        atomicAdd(&p.state->counters[PHT_CNT_ATTEMPTS], c_attempts); atomicAdd(&p.state->counters[PHT_CNT_JUMPS], c_jumps);
-        atomicAdd(&p.state->counters[PHT_CNT_PATHS], c_paths); atomicAdd(&p.state->counters[PHT_CNT_DEFERRED], c_deferred);
+        atomicAdd(&p.state->counters[PHT_CNT_ATTEMPTS], w_attempts); atomicAdd(&p.state->counters[PHT_CNT_JUMPS], w_jumps);
+        atomicAdd(&p.state->counters[PHT_CNT_PATHS], w_paths); atomicAdd(&p.state->counters[PHT_CNT_DEFERRED], w_deferred);
     }
 }
 

@@ -59,12 +59,25 @@ PHT_HD pht_u32x4 pht_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32
     return out;
 }
 
+/* Philox4x32-10 with the ten round keys precomputed (rk[2r] = k0 + r W0, rk[2r+1] = k1 + r W1): the kernels
+ * read them from the kernel-parameter constant bank as immediate operands of the XORs. */
+#define PHT_PHILOX_ROUND(RK0, RK1) { \
+        const uint64_t p0_ = (uint64_t)PHT_PHILOX_M0 * c0, p1_ = (uint64_t)PHT_PHILOX_M1 * c2; \
+        const uint32_t n0_ = (uint32_t)(p1_ >> 32) ^ c1 ^ (RK0), n2_ = (uint32_t)(p0_ >> 32) ^ c3 ^ (RK1); \
+        c1 = (uint32_t)p1_; c3 = (uint32_t)p0_; c0 = n0_; c2 = n2_; }
+typedef struct { uint32_t k[20]; } pht_roundkeys;
+PHT_HD void pht_roundkeys_init(pht_roundkeys *rk, uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) { rk->k[2 * r] = k0 + (uint32_t)r * PHT_PHILOX_W0; rk->k[2 * r + 1] = k1 + (uint32_t)r * PHT_PHILOX_W1; }
+}
+
 /* map 64 random bits to the open interval (0,1): 52 bits, centred */
 PHT_HD double pht_u01(uint32_t lo, uint32_t hi) {
     /* (x + 0.5) * 2^-52 with x the top 52 bits, built without an int->double conversion:
      * 1.x (a double in [1,2)) minus 1 is x * 2^-52 exactly, and adding 2^-53 is exact too */
     const uint64_t x = (((uint64_t)hi << 32) | lo) >> 12;
-    return (pht_u2d(0x3ff0000000000000ULL | x) - 1.0) + 1.1102230246251565e-16;   /* + 2^-53 */
+    /* 1.x - (1 - 2^-53) = (2x + 1) * 2^-53 is exactly representable, so this single subtraction is exact
+     * (and equal to the two-step form (1.x - 1) + 2^-53) */
+    return pht_u2d(0x3ff0000000000000ULL | x) - 0.99999999999999988898;
 }
 
 /* A positioned stream: draws are numbered 0,1,2,... inside (iter, obs, sub). */
