@@ -8,53 +8,58 @@
  * and the sojourn by inverting its CDF with Brent's method (src/utility.c:233-338).  exp{xS} is evaluated
  * spectrally, Q diag(exp(x evals)) Q^-1, exactly like the reference; the censoring flag is ignored (:132-133).
  *
- * GPU organisation: one observation per lane, persistent warps refilled from a global counter.  The model
- * (S, Q, Q^-1, evals, s) lives in shared memory; each lane owns four shared-memory slabs of n doubles
- * (E_i = exp(evals_i T) reused by every CDF evaluation of the jump, J_i, the jump weights p_i, and the path's
- * sojourn totals z_i).  All sums run in the reference's index order inside one thread, so every decision and
- * every z is bit-identical to the host; lanes run the Brent loop in lock step until the slowest converges.
+ * GPU organisation.  One observation per lane, persistent warps refilled from a global counter.  The work of a
+ * path is a chain of UNITS that all start with the same expensive thing -- n exponentials exp(alpha ev_i + beta)
+ * of the spectrum with lane-specific (alpha, beta):
+ *      NEW    alpha = y             end state b and start state of a new path
+ *      JUMP   alpha = T = y - t     E_i = exp(ev_i T): stay test, jump weights, next state, root-finder set-up
+ *      BRENT  alpha = T - x, beta = S_jj x     one evaluation of the sojourn CDF inside Brent's iteration
+ * Every lane is a little state machine that executes one unit per loop iteration: the exponential batch runs
+ * converged over the whole warp whatever the lanes are doing, and only the short kind-specific tails diverge.
+ * (Running whole Brent loops in lock step instead left 7 of 32 lanes active: profiles/r1a_dcs_ncu_full.md.)
+ * Brent's bookkeeping between two evaluations is one shared stage for lanes coming from JUMP and from BRENT.
+ * The O(n^2) part of a JUMP unit (P_ab, the J_i with their divisions, the n jump-weight dot products) is served by
+ * the whole warp: the per-lane vectors live in shared-memory slabs, so a group of G >= n lanes takes one requesting
+ * lane each, lane i of the group computes term i, and the sums the reference accumulates in index order are
+ * accumulated in index order with shuffles.
+ * Quantities that do not depend on the observation are tabulated once per block: ev_i - S_jj, the degenerate
+ * test |(ev_i - S_jj)/S_jj| < 1e-13 (gt_Hobolth_DCS.c:29,139) and pi^T Q.  All sums run in the reference's index
+ * order inside one thread, so every decision and every z is bit-identical to the host.
  *
- * Roofline: FP64 issue bound: ~n exp per CDF evaluation, ~10 evaluations per jump; 8 B of HBM per path.
+ * Roofline: FP64 issue bound: n exp per unit, ~11.5 units per jump; 8 B of HBM per path.
  */
 #include "path_common.cuh"
 
+#ifndef DCS_WARPS_PER_SM
+#define DCS_WARPS_PER_SM 20          /* launch bound: resident warps per SM the register allocation must allow */
+#endif
+#ifndef DCS_UNROLL
+#define DCS_UNROLL 2                 /* independent exp chains in flight per lane in the batch */
+#endif
+
+enum { K_IDLE = 0, K_NEW = 1, K_JUMP = 2, K_BRENT = 3 };
+constexpr int kBatchUnroll = DCS_UNROLL;
+
 template <int THREADS>
 struct DcsSmem {
-    double *S, *Q, *Qinv, *evals, *s, *pi;
-    double *E, *J, *P, *Z;
-    long long *zacc; unsigned int *Nacc, *Bacc;
+    double *S, *Q, *Qinv, *evals, *s, *pi, *PIQ, *D;
+    double *X, *E, *P, *Z;
+    long long *zacc; unsigned int *Nacc, *Bacc, *deg;
     __device__ __forceinline__ void carve(unsigned char *raw, int n) {
         double *d = reinterpret_cast<double *>(raw);
-        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * n;
-        evals = d; d += n; s = d; d += n; pi = d; d += n;
-        E = d; d += n * THREADS; J = d; d += n * THREADS; P = d; d += n * THREADS; Z = d; d += n * THREADS;
+        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * n; D = d; d += n * n;
+        evals = d; d += n; s = d; d += n; pi = d; d += n; PIQ = d; d += n;
+        X = d; d += n * THREADS; E = d; d += n * THREADS; P = d; d += n * THREADS; Z = d; d += n * THREADS;
         zacc = reinterpret_cast<long long *>(d); d += n;
-        Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n;
+        Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n; deg = Bacc + n;
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(3 * n * n + 3 * n + 4 * n * THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n);
+        return sizeof(double) * (size_t)(4 * n * n + 4 * n + 4 * n * THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
     }
 };
 
-/* sojourn-time CDF minus u at x (gt_Hobolth_DCS.c:23-40); E_i = exp(evals_i T) comes from the slab */
 template <int THREADS>
-__device__ __forceinline__ double hob_cdf(const DcsSmem<THREADS> &sm, int n, int k, int wcol, double x, double T,
-                                          double Sll, double Slk, double prob, double Pab, double u) {
-    const int tid = threadIdx.x;
-    double tmp = 0.0;
-    for (int i = 0; i < n; i++) {
-        const double ev = sm.evals[i];
-        const double Ei = sm.E[i * THREADS + tid];
-        double Ji;
-        if (fabs((ev - Sll) / Sll) < 1e-13) Ji = x * Ei;
-        else Ji = (Ei - pht_exp((T - x) * ev + Sll * x)) / (ev - Sll);
-        tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + wcol * n];
-    }
-    return 1 / prob * Slk / Pab * tmp - u;
-}
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_dcs_sweep(SweepParams p) {
+__global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dcs_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
@@ -69,103 +74,192 @@ __global__ void __launch_bounds__(THREADS) k_dcs_sweep(SweepParams p) {
         sm.zacc[i] = 0; sm.Bacc[i] = 0u;
     }
     __syncthreads();
+    /* observation-independent tables: D[j][i] = ev_i - S_jj, the degenerate flags, and pi^T Q in reference-BLAS order */
+    for (int e = tid; e < n * n; e += THREADS) {
+        const int j = e / n, i = e % n;
+        sm.D[j * n + i] = sm.evals[i] - sm.S[j + j * n];
+    }
+    for (int c = tid; c < n; c += THREADS) {
+        double acc = 0.0;
+        for (int i = 0; i < n; i++) acc += sm.Q[i + c * n] * sm.pi[i];
+        sm.PIQ[c] = 0.0 + 1.0 * acc;
+        const double Sjj = sm.S[c + c * n];
+        unsigned m = 0u;
+        for (int i = 0; i < n; i++) m |= (fabs((sm.evals[i] - Sjj) / Sjj) < 1e-13) ? (1u << i) : 0u;
+        sm.deg[c] = m;
+    }
+    __syncthreads();
 
-    unsigned long long c_jumps = 0, c_evals = 0, c_paths = 0, c_fail = 0;
+    unsigned c_jumps = 0, c_evals = 0, c_paths = 0, c_fail = 0;
     Dispenser disp; disp.init(p);
     PathRng rng; rng.seek(0);
-    bool active = false;
-    double y = 0.0, t = 0.0; int j = 0, b = 0, B = 0; long out_idx = 0;
+    int kind = K_IDLE;
+    double y = 0.0, t = 0.0, T = 0.0, alpha = 0.0, beta = 0.0, u = 0.0, coef = 0.0;
+    double ba = 0.0, bb = 0.0, bc = 0.0, fa = 0.0, fb = 0.0, fc = 0.0;
+    int j = 0, b = 0, k = 0, B = 0, left = 0; long out_idx = 0; bool conv = false;
     const double EPS = 2.220446049250313e-16;
 
+    /* sub-warp groups of G >= n lanes serve the JUMP units cooperatively: lane i of a group handles eigen-index i */
+    int G = 4; while (G < n) G <<= 1;
+    const int lane = tid & 31, gi = lane & (G - 1), gbase = lane & ~(G - 1), ngroups = 32 / G, mygroup = lane / G;
+    const int wtid = tid & ~31;               /* slab column of lane 0 of this warp */
+
     for (;;) {
-        unsigned idle = __ballot_sync(FULL, !active);
+        unsigned idle = __ballot_sync(FULL, kind == K_IDLE);
         if (idle && !disp.exhausted) {
-            const unsigned long long o = disp.take(p, idle, !active);
+            const unsigned long long o = disp.take(p, idle, kind == K_IDLE);
             if (o != ~0ull) {
-                /* ---- new path: end state b (eq_AslettHobolth_DCS.c:11-51), then the start state */
-                active = true; y = p.y[o]; out_idx = (long)o - p.first; t = 0.0;
+                kind = K_NEW; y = p.y[o]; out_idx = (long)o - p.first; t = 0.0;
                 rng.seek(p.obs_rank + (uint32_t)o * p.obs_world);
-                double *pv = sm.P + tid, *tv = sm.J + tid;                 /* p and tmp of the reference */
-                for (int c = 0; c < n; c++) {                              /* p = pi^T Q, reference-BLAS order */
-                    double acc = 0.0;
-                    for (int i = 0; i < n; i++) acc += sm.Q[i + c * n] * sm.pi[i];
-                    pv[c * THREADS] = (0.0 + 1.0 * acc) * pht_exp(sm.evals[c] * y);
-                }
-                double sum = 0.0;
-                for (int c = 0; c < n; c++) {                              /* tmp = p^T Q^-1, then times s */
-                    double acc = 0.0;
-                    for (int i = 0; i < n; i++) acc += sm.Qinv[i + c * n] * pv[i * THREADS];
-                    const double v = (0.0 + 1.0 * acc) * sm.s[c];
-                    tv[c * THREADS] = v; sum += v;
-                }
-                for (int c = 0; c < n; c++) tv[c * THREADS] = tv[c * THREADS] / sum;
-                b = slab_scan<THREADS>(sm.J, n, rng.next(p, iter));
-                /* start state from pi (gt_Hobolth_DCS.c:88-95) */
-                {
-                    const double target = rng.next(p, iter);
-                    double sofar = 0.0; int k = 0;
-                    while (sofar < target && k <= n - 1) { sofar += sm.pi[k]; k++; }
-                    B = k - 1 < 0 ? 0 : k - 1;
-                }
-                j = B;
-                for (int i = 0; i < n; i++) sm.Z[i * THREADS + tid] = 0.0;
+                alpha = y; beta = 0.0;
             }
-            idle = __ballot_sync(FULL, !active);
+            idle = __ballot_sync(FULL, kind == K_IDLE);
         }
         if (idle == FULL) { if (disp.exhausted) break; else continue; }
-        if (!active) continue;
+        const int kind0 = kind;
 
-        /* ---- one jump of the path (gt_Hobolth_DCS.c:112-214) */
-        bool finished = !(t < y);                                          /* loop exit without the stay step: reference prints an error */
-        int k = j; double jtime = 0.0;
-        if (!finished) {
-            const double T = y - t, Sjj = sm.S[j + j * n];
-            double Pab = 0.0;
+        /* ---- the unit's exponential batch: exp(alpha ev_i + beta), into E for a JUMP unit, else into X */
+        if (kind0 != K_IDLE) {
+            double *dst = (kind0 == K_JUMP ? sm.E : sm.X) + tid;
+#pragma unroll kBatchUnroll
+            for (int i = 0; i < n; i++) dst[i * THREADS] = pht_exp(alpha * sm.evals[i] + beta);
+        }
+        __syncwarp();
+
+        /* ---- JUMP and NEW units, served by the whole warp (gt_Hobolth_DCS.c:112-159, eq_AslettHobolth_DCS.c:16-40):
+         * up to 32/G requesting lanes at a time; group lane i computes term i of P_ab, J_i and the jump weight of
+         * candidate state i (JUMP), or component i of the end-state weights (NEW); sums that the reference accumulates
+         * in index order are accumulated in index order over the group's lanes */
+        double sv_Pab = 0.0, sv_eS = 0.0, sv_psum = 0.0;
+        unsigned need = __ballot_sync(FULL, kind0 == K_JUMP || kind0 == K_NEW);
+        while (need) {
+            int r = -1; unsigned served = 0u;
+            {
+                unsigned m = need;
+#pragma unroll 1
+                for (int g = 0; g < ngroups && m; g++) { const int bit = __ffs(m) - 1; m &= m - 1u; served |= 1u << bit; if (g == mygroup) r = bit; }
+            }
+            const int rr = r < 0 ? 0 : r;
+            const int j_r = __shfl_sync(FULL, j, rr), b_r = __shfl_sync(FULL, b, rr), kind_r = __shfl_sync(FULL, kind0, rr);
+            const double T_r = __shfl_sync(FULL, T, rr);
+            const int col = wtid + rr;
+            const bool work = (r >= 0) && (gi < n);
+            const bool wj = work && kind_r == K_JUMP, wn = work && kind_r == K_NEW;
+            double val1 = 0.0, eS = 0.0, Ei = 0.0;
+            if (wj) {
+                const double Sjj = sm.S[j_r + j_r * n];
+                eS = pht_exp(Sjj * T_r);
+                Ei = sm.E[gi * THREADS + col];
+                val1 = sm.Q[j_r + gi * n] * Ei * sm.Qinv[gi + b_r * n];                                      /* :118-121 */
+            }
+            if (wn) sm.X[gi * THREADS + col] = sm.PIQ[gi] * sm.X[gi * THREADS + col];                        /* p = (pi^T Q) o exp(ev y) */
+            __syncwarp();
+            if (wn) {                                                                                        /* (p^T Q^-1)_i s_i */
+                double acc = 0.0;
+#pragma unroll 1
+                for (int q = 0; q < n; q++) acc += sm.Qinv[q + gi * n] * sm.X[q * THREADS + col];
+                val1 = (0.0 + 1.0 * acc) * sm.s[gi];
+            }
+            double sum1 = 0.0;                                                                               /* P_ab, or the weights' total */
+#pragma unroll 1
+            for (int q = 0; q < n; q++) sum1 += __shfl_sync(FULL, val1, gbase + q);
+            if (wj) {
+                const unsigned dg = sm.deg[j_r];
+                sm.X[gi * THREADS + col] = ((dg >> gi) & 1u) ? T_r * Ei : (Ei - eS) / sm.D[j_r * n + gi];    /* :137-144 */
+            }
+            if (wn) sm.P[gi * THREADS + col] = val1 / sum1;
+            __syncwarp();
+            double v = 0.0;
+            if (wj) {
+                if (gi != j_r) {                                                                              /* :148-159 */
+                    double tmp = 0.0;
+#pragma unroll 1
+                    for (int q = 0; q < n; q++) tmp += sm.Q[gi + q * n] * sm.X[q * THREADS + col] * sm.Qinv[q + b_r * n];
+                    v = sm.S[j_r + gi * n] / sum1 * tmp;
+                }
+                sm.P[gi * THREADS + col] = v;
+            }
+            double p_sum = 0.0;
+#pragma unroll 1
+            for (int q = 0; q < n; q++) p_sum += __shfl_sync(FULL, v, gbase + q);      /* the term of state j is +0.0 */
+            __syncwarp();
+            /* hand the three scalars back to the requesting lanes */
+#pragma unroll 1
+            for (int g = 0; g < ngroups; g++) {
+                const int src = g * G;
+                const int r_g = __shfl_sync(FULL, r, src);
+                const double a0 = __shfl_sync(FULL, sum1, src), a1 = __shfl_sync(FULL, eS, src), a2 = __shfl_sync(FULL, p_sum, src);
+                if (r_g == lane) { sv_Pab = a0; sv_eS = a1; sv_psum = a2; }
+            }
+            need &= ~served;
+        }
+
+        bool advance = false, enter = false, flush = false;
+        if (kind0 == K_BRENT) {
+            /* ---- one evaluation of the sojourn CDF at x = bb (gt_Hobolth_DCS.c:23-40), then Brent's bracket update */
+            const unsigned dg = sm.deg[j];
+            double tmp = 0.0;
+#pragma unroll 1
             for (int i = 0; i < n; i++) {
-                const double Ei = pht_exp(sm.evals[i] * T);
-                sm.E[i * THREADS + tid] = Ei;
-                Pab += sm.Q[j + i * n] * Ei * sm.Qinv[i + b * n];                      /* :118-121 */
+                const double Ei = sm.E[i * THREADS + tid];
+                const double Ji = ((dg >> i) & 1u) ? bb * Ei : (Ei - sm.X[i * THREADS + tid]) / sm.D[j * n + i];
+                tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + b * n];
             }
-            if (j == b) {                                                              /* :124-132 */
-                if (rng.next(p, iter) < pht_exp(Sjj * T) / Pab) {
-                    sm.Z[j * THREADS + tid] += T;
-                    count_transition(p, n, sm.Nacc, out_idx, j, j);
-                    finished = true;
-                }
-            }
-            if (!finished) {
-                const double eS = pht_exp(Sjj * T);
-                for (int i = 0; i < n; i++) {                                          /* :137-144 */
-                    const double ev = sm.evals[i], Ei = sm.E[i * THREADS + tid];
-                    sm.J[i * THREADS + tid] = (fabs((ev - Sjj) / Sjj) < 1e-13) ? T * Ei : (Ei - eS) / (ev - Sjj);
-                }
-                double p_sum = 0.0;
-                for (int i = 0; i < n; i++) {                                          /* :148-159 */
-                    double v = 0.0;
-                    if (i != j) {
-                        double tmp = 0.0;
-                        for (int q = 0; q < n; q++) tmp += sm.Q[i + q * n] * sm.J[q * THREADS + tid] * sm.Qinv[q + b * n];
-                        v = sm.S[j + i * n] / Pab * tmp;
-                        p_sum += v;
-                    }
-                    sm.P[i * THREADS + tid] = v;
-                }
+            fb = coef * tmp - u;
+            c_evals++;
+            if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) { bc = ba; fc = fa; }
+            advance = true;
+        } else if (kind0 == K_JUMP) {
+            /* ---- the requesting lane's own part of the jump: stay test, next state, root-finder set-up (:124-190) */
+            const double Pab = sv_Pab, eS = sv_eS, p_sum = sv_psum;
+            bool stay = false;
+            if (j == b) stay = rng.next(p, iter) < eS / Pab;                                   /* :124-132 */
+            if (stay) {
+                sm.Z[j * THREADS + tid] += T;
+                count_transition(p, n, sm.Nacc, out_idx, j, j);
+                flush = true;
+            } else {
                 const double target = (p_sum == 0.0) ? 0.0 : 0.0 + (p_sum - 0.0) * rng.next(p, iter);   /* runif(0, p_sum), :164 */
                 k = slab_scan<THREADS>(sm.P, n, target);
                 const double prob = sm.P[k * THREADS + tid], Slk = sm.S[j + k * n];
-                const double u = rng.next(p, iter);                                    /* :184 */
+                u = rng.next(p, iter);                                                         /* :184 */
+                coef = 1 / prob * Slk / Pab;                                                   /* the constant factor of :39 */
                 /* Brent's zeroin on [0, T] with f(0) = -u, f(T) = 1-u, Tol = 0, Maxit = 1000 (utility.c:233-338) */
-                double ba = 0.0, bb = T, bc = 0.0, fa = -u, fb = 1.0 - u, fc = -u;
-                bool conv = (fa == 0.0) || (fb == 0.0);
+                ba = 0.0; bb = T; bc = 0.0; fa = -u; fb = 1.0 - u; fc = -u;
+                conv = (fa == 0.0) || (fb == 0.0);
                 if (fa == 0.0) bb = ba;
-                int left = 1001;
-                while (!conv && left > 0) {
-                    left--;
-                    const double prev_step = bb - ba;
-                    if (fabs(fc) < fabs(fb)) { ba = bb; bb = bc; bc = ba; fa = fb; fb = fc; fc = fa; }
-                    const double tol_act = 2 * EPS * fabs(bb) + 0.0 / 2;
-                    double new_step = (bc - bb) / 2;
-                    if (fabs(new_step) <= tol_act || fb == 0.0) { conv = true; break; }
+                left = 1001;
+                advance = true;
+            }
+        } else if (kind0 == K_NEW) {
+            /* ---- new path: end state b from the weights the warp just formed (eq_AslettHobolth_DCS.c:41-50), then the
+             * start state (gt_Hobolth_DCS.c:88-95) */
+            b = slab_scan<THREADS>(sm.P, n, rng.next(p, iter));
+            {
+                const double target = rng.next(p, iter);
+                double sofar = 0.0; int q = 0;
+#pragma unroll 1
+                while (sofar < target && q <= n - 1) { sofar += sm.pi[q]; q++; }
+                B = q - 1 < 0 ? 0 : q - 1;
+            }
+            j = B;
+#pragma unroll 1
+            for (int i = 0; i < n; i++) sm.Z[i * THREADS + tid] = 0.0;
+            enter = true;
+        }
+
+        if (advance) {
+            /* ---- Brent's bookkeeping up to the next evaluation point (the loop head of utility.c:263-331) */
+            bool done = conv;
+            if (!done && left == 0) { c_fail++; done = true; }
+            if (!done) {
+                left--;
+                const double prev_step = bb - ba;
+                if (fabs(fc) < fabs(fb)) { ba = bb; bb = bc; bc = ba; fa = fb; fb = fc; fc = fa; }
+                const double tol_act = 2 * EPS * fabs(bb) + 0.0 / 2;
+                double new_step = (bc - bb) / 2;
+                if (fabs(new_step) <= tol_act || fb == 0.0) done = true;
+                else {
                     if (fabs(prev_step) >= tol_act && fabs(fa) > fabs(fb)) {
                         double pp, qq; const double cb = bc - bb;
                         if (ba == bc) { const double t1 = fb / fa; pp = cb * t1; qq = 1.0 - t1; }
@@ -180,35 +274,42 @@ __global__ void __launch_bounds__(THREADS) k_dcs_sweep(SweepParams p) {
                     if (fabs(new_step) < tol_act) new_step = (new_step > 0.0) ? tol_act : -tol_act;
                     ba = bb; fa = fb;
                     bb += new_step;
-                    fb = hob_cdf<THREADS>(sm, n, k, b, bb, T, Sjj, Slk, prob, Pab, u);
-                    c_evals++;
-                    if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) { bc = ba; fc = fa; }
+                    kind = K_BRENT; alpha = T - bb; beta = sm.S[j + j * n] * bb;                /* argument of :33 */
                 }
-                if (!conv) c_fail++;
-                jtime = bb;
+            }
+            if (done) {
+                double jtime = bb;
                 int guard = 0;
-                while (t + jtime >= y && guard++ < 2000) jtime = jtime / 2;             /* :204-206 */
-                count_transition(p, n, sm.Nacc, out_idx, j, k);                         /* :209 */
-                sm.Z[j * THREADS + tid] += jtime;                                       /* :210 */
+#pragma unroll 1
+                while (t + jtime >= y && guard++ < 2000) jtime = jtime / 2;                     /* :204-206 */
+                count_transition(p, n, sm.Nacc, out_idx, j, k);                                 /* :209 */
+                sm.Z[j * THREADS + tid] += jtime;                                               /* :210 */
                 t += jtime; j = k;
                 c_jumps++;
+                enter = true;
             }
         }
-        if (finished) {
+        if (enter) {
+            /* ---- next unit is a JUMP from (j, t), unless the clock has run out (the reference prints an error there) */
+            if (!(t < y)) flush = true;
+            else { T = y - t; alpha = T; beta = 0.0; kind = K_JUMP; }
+        }
+        if (flush) {
             path_flush<THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
-            c_paths++; active = false;
+            c_paths++; kind = K_IDLE;
         }
     }
 
     __syncthreads();
     block_flush<THREADS>(p, n, sm.Nacc, sm.Bacc, sm.zacc);
+    unsigned long long w_jumps = c_jumps, w_evals = c_evals, w_paths = c_paths, w_fail = c_fail;
     for (int o = 16; o > 0; o >>= 1) {
-        c_jumps += __shfl_down_sync(FULL, c_jumps, o); c_evals += __shfl_down_sync(FULL, c_evals, o);
-        c_paths += __shfl_down_sync(FULL, c_paths, o); c_fail += __shfl_down_sync(FULL, c_fail, o);
+        w_jumps += __shfl_down_sync(FULL, w_jumps, o); w_evals += __shfl_down_sync(FULL, w_evals, o);
+        w_paths += __shfl_down_sync(FULL, w_paths, o); w_fail += __shfl_down_sync(FULL, w_fail, o);
     }
     if ((tid & 31) == 0) {
-        atomicAdd(&p.state->counters[PHT_CNT_JUMPS], c_jumps); atomicAdd(&p.state->counters[PHT_CNT_BRENT_EVALS], c_evals);
-        atomicAdd(&p.state->counters[PHT_CNT_PATHS], c_paths); atomicAdd(&p.state->counters[PHT_CNT_NONFINITE], c_fail);
+        atomicAdd(&p.state->counters[PHT_CNT_JUMPS], w_jumps); atomicAdd(&p.state->counters[PHT_CNT_BRENT_EVALS], w_evals);
+        atomicAdd(&p.state->counters[PHT_CNT_PATHS], w_paths); atomicAdd(&p.state->counters[PHT_CNT_NONFINITE], w_fail);
     }
 }
 

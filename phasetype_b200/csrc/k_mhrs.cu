@@ -137,29 +137,8 @@ __device__ __forceinline__ void walk_begin(Walk &w, uint32_t a, bool off, uint32
     }
 }
 
-/* log of a uniform in (0,1): the normal, positive branch of pht_log (bit-identical on that domain) */
-__device__ __forceinline__ double log_unit(double x) {
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01, L3 = 2.857142874366239149e-01,
-                 L4 = 2.222219843214978396e-01, L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
-                 L7 = 1.479819860511658591e-01;
-    const uint64_t ux = pht_d2u(x);
-    uint32_t hx = (uint32_t)(ux >> 32);
-    hx += 0x3ff00000u - 0x3fe6a09eu;
-    const int e = (int)(hx >> 20) - 0x3ff;
-    hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
-    const double m = pht_u2d(((uint64_t)hx << 32) | (ux & 0xffffffffULL));
-    const double f = m - 1.0;
-    const double hfsq = 0.5 * f * f;
-    const double s = f / (2.0 + f);
-    const double z = s * s;
-    const double w = z * z;
-    const double t1 = w * PHT_FMA(w, PHT_FMA(w, L6, L4), L2);
-    const double t2 = z * PHT_FMA(w, PHT_FMA(w, PHT_FMA(w, L7, L5), L3), L1);
-    const double R = t2 + t1;
-    const double dk = (double)e;
-    return dk * LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LN2_LO)) - f);
-}
+/* log of a uniform in (0,1): always a positive normal number, so the core of pht_log applies directly */
+__device__ __forceinline__ double log_unit(double x) { return pht_log_core(pht_d2u(x), 0); }
 
 /* One jump-step of a walk; returns true when the attempt ended on this step (w.t, w.j are then the exit time
  * and the state occupied at the end).  No control flow around the expensive parts (Philox, scan, log). */

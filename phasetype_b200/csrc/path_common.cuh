@@ -42,13 +42,20 @@ struct Dispenser {
     }
 };
 
+/* One out-of-line copy of the Philox block function: the path kernels draw uniforms at many places of a large,
+ * divergent loop body, and inlining ~70 instructions at each of them costs instruction-cache misses (the DCS loop
+ * stalled on `no_instruction` more than on anything else: profiles/r1c_dcs_ncu_full.md). */
+static __device__ __noinline__ pht_u32x4 pht_philox_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    return pht_philox4x32_10(c0, c1, c2, c3, k0, k1);
+}
+
 /* sequential uniforms of one path: sub-stream 0 of (iter, observation) */
 struct PathRng {
     uint32_t obs, b; double spare; bool odd;
     __device__ __forceinline__ void seek(uint32_t obs_global) { obs = obs_global; b = 0; odd = false; spare = 0.0; }
     __device__ __forceinline__ double next(const SweepParams &p, uint32_t iter) {
         if (odd) { odd = false; return spare; }
-        pht_u32x4 r = pht_philox4x32_10(b++, 0u, obs, iter, p.k0, p.k1);
+        pht_u32x4 r = pht_philox_call(b++, 0u, obs, iter, p.k0, p.k1);
         spare = pht_u01(r.v[2], r.v[3]); odd = true;
         return pht_u01(r.v[0], r.v[1]);
     }
@@ -58,6 +65,7 @@ struct PathRng {
 template <int THREADS>
 __device__ __forceinline__ int slab_scan(const double *slab, int n, double target) {
     double sofar = 0.0; int k = 0;
+#pragma unroll 1
     while (sofar < target && k <= n - 1) { sofar += slab[k * THREADS + threadIdx.x]; k++; }
     k--;
     return k < 0 ? 0 : k;
@@ -70,10 +78,12 @@ __device__ __forceinline__ void path_flush(const SweepParams &p, int n, const do
     const int tid = threadIdx.x;
     if (p.outB != nullptr) {
         p.outB[out_idx] = B;
+#pragma unroll 1
         for (int i = 0; i < n; i++) p.outz[out_idx * n + i] = zslab[i * THREADS + tid];
     } else {
         atomicAdd(&Bacc[B], 1u);
         const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
+#pragma unroll 1
         for (int i = 0; i < n; i++) {
             const double v = zslab[i * THREADS + tid];
             if (v != 0.0) {

@@ -51,11 +51,38 @@ PHT_HD double pht_u2d(uint64_t u) {
 #endif
 }
 
-/* exp(x).  k = round(x/ln2); r = x - k ln2 (two-step, fma); Taylor degree 13 on
- * |r| <= ln2/2 (remainder < 5e-18 relative); scaling by 2^k in two exact
- * halves so that k = 1024 and subnormal results are handled without branches
- * on the common path. */
-PHT_HD double pht_exp(double x) {
+/* Polynomial coefficients.  On the device they live in constant memory so that each one is an operand of its
+ * FMA (a 64-bit literal would cost two moves per use); the host uses the same values as literals. */
+#define PHT_EXP_COEFFS \
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, \
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, \
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1.0, 1.0      /* 1/13! ... 1/2!, 1, 1 */
+#define PHT_LOG_COEFFS \
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01, \
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01                  /* L1 ... L7 (fdlibm e_log.c) */
+#if defined(__CUDACC__)
+static __constant__ double pht_exp_cd[14] = { PHT_EXP_COEFFS };
+static __constant__ double pht_log_cd[7] = { PHT_LOG_COEFFS };
+#endif
+static const double pht_exp_ch[14] = { PHT_EXP_COEFFS };
+static const double pht_log_ch[7] = { PHT_LOG_COEFFS };
+#if defined(__CUDA_ARCH__)
+#define PHT_EC(i) pht_exp_cd[i]
+#define PHT_LC(i) pht_log_cd[i]
+#define PHT_SLOW __device__ __noinline__
+#else
+#define PHT_EC(i) pht_exp_ch[i]
+#define PHT_LC(i) pht_log_ch[i]
+#define PHT_SLOW static
+#endif
+
+/* exp(x).  k = round(x/ln2); r = x - k ln2 (two-step, fma); Taylor degree 13 on |r| <= ln2/2 (remainder < 5e-18
+ * relative); result p * 2^k.
+ * Fast path |x| <= 708: p is in [0.70, 1.42] and |k| <= 1021, so p * 2^k is a normal number and the scaling is
+ * exact: it is done by adding k to the exponent field.  Everything else (NaN, overflow, results near or below
+ * the subnormal range) takes the general path, which scales in two exact halves.  Both paths compute the same
+ * value wherever both apply, so the split is invisible in the results. */
+PHT_SLOW double pht_exp_general(double x) {
     if (!(x == x)) return x + x;                          /* NaN */
     if (x > 709.782712893384) return pht_u2d(0x7ff0000000000000ULL);
     if (x < -745.1332191019412) return 0.0;
@@ -66,20 +93,8 @@ PHT_HD double pht_exp(double x) {
     double kd = PHT_FMA(x, LOG2E, SHIFT) - SHIFT;          /* round-to-nearest integer */
     double r = PHT_FMA(-kd, LN2_HI, x);
     r = PHT_FMA(-kd, LN2_LO, r);
-    double p = 1.6059043836821613e-10;                    /* 1/13! */
-    p = PHT_FMA(p, r, 2.08767569878681e-09);              /* 1/12! */
-    p = PHT_FMA(p, r, 2.505210838544172e-08);             /* 1/11! */
-    p = PHT_FMA(p, r, 2.755731922398589e-07);             /* 1/10! */
-    p = PHT_FMA(p, r, 2.7557319223985893e-06);            /* 1/9!  */
-    p = PHT_FMA(p, r, 2.48015873015873e-05);              /* 1/8!  */
-    p = PHT_FMA(p, r, 1.984126984126984e-04);             /* 1/7!  */
-    p = PHT_FMA(p, r, 1.388888888888889e-03);             /* 1/6!  */
-    p = PHT_FMA(p, r, 8.333333333333333e-03);             /* 1/5!  */
-    p = PHT_FMA(p, r, 4.1666666666666664e-02);            /* 1/4!  */
-    p = PHT_FMA(p, r, 1.6666666666666666e-01);            /* 1/3!  */
-    p = PHT_FMA(p, r, 0.5);
-    p = PHT_FMA(p, r, 1.0);
-    p = PHT_FMA(p, r, 1.0);
+    double p = PHT_EC(0);
+    for (int i = 1; i < 14; i++) p = PHT_FMA(p, r, PHT_EC(i));
     int k = (int)kd;
     int k1 = k >> 1, k2 = k - k1;                         /* both within [-538, 512] */
     double s1 = pht_u2d((uint64_t)(int64_t)(k1 + 1023) << 52);
@@ -87,46 +102,74 @@ PHT_HD double pht_exp(double x) {
     return (p * s1) * s2;
 }
 
+PHT_HD double pht_exp(double x) {
+    const double LOG2E  = 1.4426950408889634074;
+    const double LN2_HI = 6.93147180559945286227e-01;
+    const double LN2_LO = 2.31904681384629955842e-17;
+    const double SHIFT  = 6755399441055744.0;
+    if (!(__builtin_fabs(x) <= 708.0)) return pht_exp_general(x);
+    const double t = PHT_FMA(x, LOG2E, SHIFT);
+    const double kd = t - SHIFT;
+    double r = PHT_FMA(-kd, LN2_HI, x);
+    r = PHT_FMA(-kd, LN2_LO, r);
+    double p = PHT_EC(0);
+    p = PHT_FMA(p, r, PHT_EC(1));  p = PHT_FMA(p, r, PHT_EC(2));  p = PHT_FMA(p, r, PHT_EC(3));
+    p = PHT_FMA(p, r, PHT_EC(4));  p = PHT_FMA(p, r, PHT_EC(5));  p = PHT_FMA(p, r, PHT_EC(6));
+    p = PHT_FMA(p, r, PHT_EC(7));  p = PHT_FMA(p, r, PHT_EC(8));  p = PHT_FMA(p, r, PHT_EC(9));
+    p = PHT_FMA(p, r, PHT_EC(10)); p = PHT_FMA(p, r, PHT_EC(11)); p = PHT_FMA(p, r, PHT_EC(12));
+    p = PHT_FMA(p, r, PHT_EC(13));
+    /* the low mantissa word of t = k + 1.5 * 2^52 holds k in two's complement */
+#if defined(__CUDA_ARCH__)
+    const int k = __double2loint(t);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    const int k = (int)(uint32_t)pht_d2u(t);
+    return pht_u2d(pht_d2u(p) + ((uint64_t)(int64_t)k << 52));
+#endif
+}
+
 /* log(x).  x = 2^e * m, m in [sqrt(1/2), sqrt(2)); f = m - 1; s = f/(2+f);
  * log(1+f) = f - f^2/2 + s*(f^2/2 + R(s^2)) with the degree-7 even polynomial
- * R from fdlibm (e_log.c; Sun Microsystems 1993, freely distributable). */
-PHT_HD double pht_log(double x) {
+ * R from fdlibm (e_log.c; Sun Microsystems 1993, freely distributable).
+ * pht_log_core is the computation for a positive normal x; pht_log adds the special cases. */
+PHT_HD double pht_log_core(uint64_t ux, int e) {
     const double LN2_HI = 6.93147180369123816490e-01;     /* 0x3fe62e42fee00000 */
     const double LN2_LO = 1.90821492927058770002e-10;     /* 0x3dea39ef35793c76 */
-    const double L1 = 6.666666666666735130e-01, L2 = 3.999999999940941908e-01,
-                 L3 = 2.857142874366239149e-01, L4 = 2.222219843214978396e-01,
-                 L5 = 1.818357216161805012e-01, L6 = 1.531383769920937332e-01,
-                 L7 = 1.479819860511658591e-01;
+    /* bring the mantissa into [sqrt(1/2), sqrt(2)) */
+    uint32_t hx = (uint32_t)(ux >> 32);
+    hx += 0x3ff00000u - 0x3fe6a09eu;
+    e += (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+    double m = pht_u2d(((uint64_t)hx << 32) | (ux & 0xffffffffULL));
+    double f = m - 1.0;
+    double hfsq = 0.5 * f * f;
+    double s = f / (2.0 + f);
+    double z = s * s;
+    double w = z * z;
+    double t1 = w * PHT_FMA(w, PHT_FMA(w, PHT_LC(5), PHT_LC(3)), PHT_LC(1));
+    double t2 = z * PHT_FMA(w, PHT_FMA(w, PHT_FMA(w, PHT_LC(6), PHT_LC(4)), PHT_LC(2)), PHT_LC(0));
+    double R = t2 + t1;
+    double dk = (double)e;
+    return dk * LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LN2_LO)) - f);
+}
+
+PHT_SLOW double pht_log_special(double x) {
     uint64_t ux = pht_d2u(x);
-    int e = 0;
     if (ux >= 0x7ff0000000000000ULL) {                    /* inf, NaN, negative */
         if (ux == 0x7ff0000000000000ULL) return x;        /* +inf */
         if (!(x == x)) return x + x;                      /* NaN */
         if (x == 0.0) return -pht_u2d(0x7ff0000000000000ULL);   /* -0 */
         return pht_u2d(0x7ff8000000000000ULL);            /* x < 0 */
     }
-    if (ux < 0x0010000000000000ULL) {                     /* zero or subnormal */
-        if (ux == 0) return -pht_u2d(0x7ff0000000000000ULL);
-        x *= 18014398509481984.0;                         /* 2^54 */
-        ux = pht_d2u(x);
-        e = -54;
-    }
-    /* bring the mantissa into [sqrt(1/2), sqrt(2)) */
-    uint64_t hx = ux >> 32;
-    hx += 0x3ff00000 - 0x3fe6a09e;
-    e += (int)(hx >> 20) - 0x3ff;
-    hx = (hx & 0x000fffff) + 0x3fe6a09e;
-    double m = pht_u2d((hx << 32) | (ux & 0xffffffffULL));
-    double f = m - 1.0;
-    double hfsq = 0.5 * f * f;
-    double s = f / (2.0 + f);
-    double z = s * s;
-    double w = z * z;
-    double t1 = w * PHT_FMA(w, PHT_FMA(w, L6, L4), L2);
-    double t2 = z * PHT_FMA(w, PHT_FMA(w, PHT_FMA(w, L7, L5), L3), L1);
-    double R = t2 + t1;
-    double dk = (double)e;
-    return dk * LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LN2_LO)) - f);
+    if (ux == 0) return -pht_u2d(0x7ff0000000000000ULL);  /* +0 */
+    x *= 18014398509481984.0;                             /* subnormal: scale by 2^54 */
+    return pht_log_core(pht_d2u(x), -54);
+}
+
+PHT_HD double pht_log(double x) {
+    const uint64_t ux = pht_d2u(x);
+    if (ux - 0x0010000000000000ULL >= 0x7fe0000000000000ULL) return pht_log_special(x);   /* not a positive normal */
+    return pht_log_core(ux, 0);
 }
 
 #endif /* PHT_MATH_H */
