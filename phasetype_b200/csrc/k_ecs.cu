@@ -12,7 +12,8 @@
  *
  * Both use a per-lane ARMS (Gilks' adaptive rejection Metropolis sampling, src/arms.c) with the reference's
  * settings (4 starting abscissae, up to 100 envelope points, convex = 1, Metropolis on, xprev = 0).  The
- * envelope is an index-linked array in the lane's local memory (typically 9-13 live points, L1 resident);
+ * envelope is an index-linked array in the lane's local memory (typically 9-13 live points; a compact
+ * shared-memory envelope was tried and lost to the occupancy it costs);
  * log-density evaluations read the lane's hoisted row vector p^T Q from a shared-memory slab and the spectrum
  * from shared memory.  Exact and censored observations are separate launches over index lists built at upload,
  * so a warp never serialises the two samplers.  All sums run in the reference's order inside one thread:
@@ -51,31 +52,42 @@ struct ArmsPt { double x, y, ey, cum; int f, pl, pr; };
 
 struct EcsCounters { unsigned long long jumps, evals, updates, calls, rejects, nonfinite, paths; };
 
-/* log-density closures (state kept in registers; the row vector lives in the PQ slab) */
-struct DensExact {      /* eq_Aslett_ECS.c:150-171 */
+/* log-density closures.  The evaluation itself is ONE out-of-line function per sampler: ARMS calls its density from
+ * five places, and five inlined copies of an n-term exp loop made the kernels' loop bodies larger than the
+ * instruction cache (`no_instruction` was the top stall: profiles/r1a_ecs_ncu_full.md). */
+static __device__ __noinline__ double ecs_dens_exact(const double *pq, const double *evals, const double *qinv_s, int n,
+                                                     double y_t, double Sjj, double d) {      /* eq_Aslett_ECS.c:150-171 */
+    double term1 = 0.0;
+    const double a = y_t - d;
+#pragma unroll 2
+    for (int i = 0; i < n; i++) term1 += (pq[i * ECS_THREADS] * pht_exp(evals[i] * a)) * qinv_s[i];
+    return pht_log(term1) + Sjj * d;
+}
+static __device__ __noinline__ double ecs_dens_gt(const double *pq, const double *evals, const double *qinv_1, int n,
+                                                  double rem, double scale, double d) {        /* gt_Aslett_DCS.c:111-132 */
+    const double x1 = rem - d;
+    double r1 = 1.0;
+    if (x1 > 0) {
+        r1 = 0.0;
+#pragma unroll 2
+        for (int i = 0; i < n; i++) r1 += pq[i * ECS_THREADS] * pht_exp(x1 * evals[i]) * qinv_1[i];
+    }
+    double dens;                                     /* dexp(d, scale, log = TRUE) */
+    if (scale <= 0.0) dens = pht_u2d(0x7ff8000000000000ULL);
+    else if (d < 0.0) dens = -pht_u2d(0x7ff0000000000000ULL);
+    else dens = (-d / scale) - pht_log(scale);
+    return pht_log(r1) + dens;
+}
+struct DensExact {
     double y_t, Sjj;
     __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
-        double term1 = 0.0;
-        for (int i = 0; i < n; i++)
-            term1 += (sm.PQ[i * ECS_THREADS + threadIdx.x] * pht_exp(sm.evals[i] * (y_t - d))) * sm.Qinv_s[i];
-        return pht_log(term1) + Sjj * d;
+        return ecs_dens_exact(sm.PQ + threadIdx.x, sm.evals, sm.Qinv_s, n, y_t, Sjj, d);
     }
 };
-struct DensGt {         /* gt_Aslett_DCS.c:111-132 */
+struct DensGt {
     double rem, scale;
     __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
-        const double x1 = rem - d;
-        double r1 = 1.0;
-        if (x1 > 0) {
-            r1 = 0.0;
-            for (int i = 0; i < n; i++)
-                r1 += sm.PQ[i * ECS_THREADS + threadIdx.x] * pht_exp(x1 * sm.evals[i]) * sm.Qinv_1[i];
-        }
-        double dens;                                     /* dexp(d, scale, log = TRUE) */
-        if (scale <= 0.0) dens = pht_u2d(0x7ff8000000000000ULL);
-        else if (d < 0.0) dens = -pht_u2d(0x7ff0000000000000ULL);
-        else dens = (-d / scale) - pht_log(scale);
-        return pht_log(r1) + dens;
+        return ecs_dens_gt(sm.PQ + threadIdx.x, sm.evals, sm.Qinv_1, n, rem, scale, d);
     }
 };
 
@@ -255,6 +267,7 @@ __device__ __forceinline__ void ecs_finish(const SweepParams &p, int n, EcsSmem 
 /* start state from pi: `while (sofar < target) sofar += pi[k++]` bounded at n-1 */
 __device__ __forceinline__ int start_state(const EcsSmem &sm, int n, double target) {
     double sofar = 0.0; int k = 0;
+#pragma unroll 1
     while (sofar < target && k <= n - 1) { sofar += sm.pi[k]; k++; }
     return k - 1 < 0 ? 0 : k - 1;
 }
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
                 rng.seek(p.obs_rank + o * p.obs_world);
                 B = start_state(sm, n, rng.next(p, iter));                              /* eq_Aslett_ECS.c:231-238 */
                 j = B;
+#pragma unroll 1
                 for (int i = 0; i < n; i++) sm.Z[i * ECS_THREADS + tid] = 0.0;
             }
             idle = __ballot_sync(FULL, !active);
@@ -324,6 +338,7 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
         if (sm.s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
             const double num = (Sjj * y_t) + pht_log(sm.s[j]);
             double den = 0.0;
+#pragma unroll 1
             for (int i = 0; i < n; i++) den += sm.Q[j + i * n] * pht_exp(sm.evals[i] * y_t) * sm.Qinv_s[i];
             absorb = rng.next(p, iter) < pht_exp(num - pht_log(den));
         }
@@ -335,9 +350,12 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
             continue;
         }
         /* p_j = S[j,.]/(-S_jj) with p_jj = 0 (:292-295); PQ = p_j^T Q in reference-BLAS order (:160) */
+#pragma unroll 1
         for (int i = 0; i < n; i++) sm.W[i * ECS_THREADS + tid] = (i == j) ? 0.0 : sm.S[j + i * n] / (-Sjj);
+#pragma unroll 1
         for (int col = 0; col < n; col++) {
             double acc = 0.0;
+#pragma unroll 1
             for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.W[i * ECS_THREADS + tid];
             sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
         }
@@ -348,13 +366,18 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
         t += d;
         /* next state (moveMass :21-41): W_r = sum_c Q[r,c] exp(evals_c rem) (Q^-1 s)_c, accumulated over c */
         const double rem = y_t - d;
+#pragma unroll 1
         for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] = 0.0;
+#pragma unroll 1
         for (int col = 0; col < n; col++) {
             const double tv = 1.0 * (pht_exp(sm.evals[col] * rem) * sm.Qinv_s[col]);
+#pragma unroll 1
             for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] += tv * sm.Q[r + col * n];
         }
         double sum = 0.0;
+#pragma unroll 1
         for (int i = 0; i < n; i++) { const double v = sm.W[i * ECS_THREADS + tid] * sm.P[j + i * n]; sm.W[i * ECS_THREADS + tid] = v; sum += v; }
+#pragma unroll 1
         for (int i = 0; i < n; i++) sm.W[i * ECS_THREADS + tid] = sm.W[i * ECS_THREADS + tid] / sum;
         const int k = slab_scan<ECS_THREADS>(sm.W, n, rng.next(p, iter));               /* :352-358 */
         sm.Z[j * ECS_THREADS + tid] += d;                                               /* :362 */
@@ -388,6 +411,7 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList l
                 rng.seek(p.obs_rank + o * p.obs_world);
                 B = start_state(sm, n, rng.next(p, iter));                              /* gt_Aslett_DCS.c:313-320 */
                 j = B;
+#pragma unroll 1
                 for (int i = 0; i < n; i++) sm.Z[i * ECS_THREADS + tid] = 0.0;
             }
             idle = __ballot_sync(FULL, !active);
@@ -408,8 +432,10 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList l
             if (rng.next(p, iter) < pht_exp(Sjj * (y - t)) / denom)                     /* :200-204 */
                 d = y - t + (1.0 / -Sjj) * (-pht_log(rng.next(p, iter)));
             else {
+#pragma unroll 1
                 for (int col = 0; col < n; col++) {                                     /* P[j,.]^T Q */
                     double acc = 0.0;
+#pragma unroll 1
                     for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.P[j + i * n];
                     sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
                 }
@@ -425,28 +451,34 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList l
         int k;
         if (t < y) {                                                                    /* :353-369 */
             const double x1 = y - t;
+#pragma unroll 1
             for (int col = 0; col < n; col++) {
                 double acc = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.P[lastj + i * n];
                 sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
             }
             double r2 = 0.0;
+#pragma unroll 1
             for (int i = 0; i < n; i++) {
                 const double ex = pht_exp(x1 * sm.evals[i]);
                 sm.W[i * ECS_THREADS + tid] = ex;
                 r2 += sm.PQ[i * ECS_THREADS + tid] * ex * sm.Qinv_1[i];
             }
             double sofar = 0.0; k = 0;
+#pragma unroll 1
             while (sofar < target && k <= n - 1) {
                 const double Plk = sm.P[lastj + k * n];
                 if (Plk == 0.0) { k++; continue; }
                 double r1 = 0.0;
+#pragma unroll 1
                 for (int i = 0; i < n; i++) r1 += sm.Q[k + i * n] * sm.W[i * ECS_THREADS + tid] * sm.Qinv_1[i];
                 sofar += r1 * Plk / r2; k++;
             }
             k--; if (k < 0) k = 0;
         } else {                                                                        /* :370-375 */
             double sofar = 0.0; k = 0;
+#pragma unroll 1
             while (sofar < target && k <= n) { sofar += sm.Pfull[lastj + k * n]; k++; }
             k--; if (k < 0) k = 0;
         }
