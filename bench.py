@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- Gibbs-sweep throughput of the B200 engine on BASELINE.json's headline workload.
 
-A "step" is one Gibbs sweep (reference src/PHT_MCMC_Aslett.c:268-405) over all observations:
-one conditioned latent-path draw per observation + the conjugate parameter update.
-Metric: path draws per second (= l x sweeps / time); Gibbs iterations/s is reported beside it.
+A "step" is one Gibbs sweep (reference src/PHT_MCMC_Aslett.c:268-405) over all observations: one conditioned
+latent-path draw per observation + the conjugate parameter update.  Metric: path draws per second
+(= observations x sweeps / time); Gibbs iterations/s is reported beside it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--method MHRS|ECS|DCS] [--config 3] [--obs L]
   python bench.py --impl reference ...      # the reference's own C on the host cores
 
-Contract details are in the task statement; the JSON line carries `roofline`, `cpu_baseline`,
-`e2e`, `clocks`, `gpu_launches`.  Only the cpu_baseline / --impl reference legs touch oracle/.
+Headline (N = 1): BASELINE.json configs[2] = 8-phase general PHT, 10^7 observations, 20 % right-censored, method
+MHRS (the one sampler the reference's phtMCMC() uses); ECS and DCS on the same shape are measured in the same run and
+reported under "other_methods".  N > 1: one process per GPU (torchrun); every rank holds 10^7 observations of its own
+(weak scaling, observation i of the global set -> rank i mod N) and the one exchange per sweep is the NCCL all-reduce
+of the statistics block inside the captured sweep; a strong-scaling run (the same 10^7 observations sharded N ways)
+is timed too and reported under "strong".
+
+The JSON line carries `roofline` (FP64-issue bound kernel: see DESIGN.md section 5), `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches`.  Only the cpu_baseline / --impl reference legs and the event counting for the work model touch oracle/.
 """
 import argparse
 import json
@@ -17,7 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -27,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 METHOD_CODE = {"MHRS": 1, "ECS": 2, "DCS": 4}
 SEED = 0x5048B200
+FLUSH_BYTES = 256 << 20          # > the 126 MB L2
 
 
 # ----------------------------------------------------------------------------- work model
@@ -53,8 +60,9 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)          # let the sampler take its first readings before the timed region starts
         except Exception:
             self.proc = None
 
@@ -67,14 +75,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[1])); smax.append(float(f[2]))
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
                 except ValueError:
                     continue
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
@@ -85,7 +93,7 @@ class ClockSampler:
             pass
         if sm:
             out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                   "samples": len(sm), "power_w_max": float(max(power)) if power else None}
         return out
 
 
@@ -106,7 +114,6 @@ def cpu_sweeps(wl, method, mhit, sample, cores, steps, warmup, kind):
     """Time `steps` sweeps of the CPU implementation over the first `sample` observations, split over
     `cores` independent processes.  Returns (paths_per_s, ms_per_step)."""
     import multiprocessing as mp
-    from oracle import pyoracle as po
     S, s = model_matrices(wl)
     y = wl.y[:sample]; c = wl.censored[:sample]
     bounds = np.linspace(0, sample, cores + 1).astype(int)
@@ -138,6 +145,129 @@ def ref_kind():
     return "ref" if po.have_ref() else "oracle"
 
 
+def oracle_events(wl, method, mhit, ns):
+    """Event counts per path on the first ns observations of the benchmark's own inputs (the work model's input)."""
+    from oracle import pyoracle as po
+    po.build()
+    S, s = model_matrices(wl)
+    ns = min(wl.l, ns)
+    if method == "MHRS":
+        cnt = po.mhrs_paths("oracle", SEED, 1, wl.y[:ns], wl.censored[:ns], S, s, mhit=mhit, want=False)[-1]
+    else:
+        cnt = po.spectral_paths("oracle", method, SEED, 1, wl.y[:ns], wl.censored[:ns], S, s, want=False)[-1]
+    return {k: v / float(ns) for k, v in cnt.items()}
+
+
+def ncu_traffic(method, l_local):
+    """DRAM bytes per launch of the path kernel from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, written by tools/ncu_traffic.py); None when there is no capture at this size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get("%s:%d" % (method, l_local))
+        return None if e is None else e["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def _peak_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- one measured configuration
+class Runner:
+    def __init__(self, args, rank, world, local_rank):
+        self.a = args; self.rank = rank; self.world = world; self.local_rank = local_rank
+        self.torch = None; self.dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.torch = torch; self.dist = dist
+
+    def barrier(self):
+        if self.world > 1:
+            self.torch.cuda.synchronize(); self.dist.barrier(); self.torch.cuda.synchronize()
+
+    def reduce(self, x, op="max"):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def make_engine(self, wl, method, y_loc, c_loc, sum_y, graph, flush):
+        import phasetype_b200 as pb
+        e = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, y_loc, c_loc, method=METHOD_CODE[method], mhit=self.a.mhit, seed=SEED,
+                      device=self.local_rank, rank=self.rank, world=self.world, use_graph=graph, sum_y_global=sum_y)
+        if self.world > 1:
+            torch, dist = self.torch, self.dist
+            buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                import ctypes as C
+                raw = (C.c_char * 128)()
+                if pb.lib().pht_comm_unique_id(raw) != 0:
+                    raise RuntimeError(pb.lib().pht_last_error().decode())
+                buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+            dist.broadcast(buf, 0)
+            e.comm_init(bytes(buf.cpu().numpy().tobytes()))
+        if flush:
+            e.set_l2_flush(FLUSH_BYTES)
+        e.set_theta(wl.theta, next_iter=1)
+        return e
+
+    def timed(self, wl, method, y_loc, c_loc, sum_y, steps, warmup, clocks=False):
+        """W warm-up sweeps, then exactly `steps` sweeps between barriers; device time from CUDA events on the sweep
+        stream, max over ranks.  Returns a dict."""
+        eng = self.make_engine(wl, method, y_loc, c_loc, sum_y, True, True)
+        eng.run(warmup)
+        c0 = eng.counters()
+        sampler = ClockSampler(self.local_rank) if (clocks and self.rank == 0) else None
+        if sampler:
+            sampler.start()
+        self.barrier()
+        t0 = time.perf_counter()
+        eng.enqueue(steps); eng.sync()
+        wall = time.perf_counter() - t0
+        self.barrier()
+        clk = sampler.stop() if sampler else None
+        total_ms, _ = eng.last_ms()
+        total_ms = self.reduce(total_ms)
+        c1 = eng.counters()
+        eng.close()
+        # instrumented pass: duration of the path kernel alone (CUDA events around each launch, no graph)
+        eng2 = self.make_engine(wl, method, y_loc, c_loc, sum_y, False, True)
+        eng2.run(warmup)
+        self.barrier()
+        k = min(steps, 32)
+        eng2.enqueue(k); eng2.sync()
+        tot2, kern_ms = eng2.last_ms()
+        kern_ms = self.reduce(kern_ms)
+        eng2.close()
+        nloc = max(1, y_loc.shape[0])
+        return {"total_ms": total_ms, "wall": wall, "clocks": clk, "launches": int(c1["launches"] - c0["launches"]),
+                "kern_ms": kern_ms, "share": kern_ms * k / max(tot2, 1e-9),
+                "events": {q: (c1[q] - c0[q]) / float(steps * nloc) for q in ("attempts", "jumps", "deferred", "dens_evals", "brent_evals")},
+                "tail_rounds": (c1["tail_rounds"] - c0["tail_rounds"]) / float(steps)}
+
+    def roofline(self, wl, method, res, l_local, fma_rate):
+        ev = oracle_events(wl, method, self.a.mhit, 20000)
+        W = work_per_path(method, wl.n, ev)
+        achieved = W * l_local / (res["kern_ms"] * 1e-3)
+        hbm_peak, hbm_src = _peak_hbm()
+        kernel = {"MHRS": "k_mhrs_sweep", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
+        return {"bound": "fp64_issue", "achieved": achieved / 1e9, "peak": fma_rate / 1e9, "unit": "G FP64-instr-equiv/s",
+                "frac": achieved / fma_rate, "traffic": ncu_traffic(method, l_local),
+                "peak_source": "measured in this run: dependent FP64 FMA chains on all SMs (pht_fp64_fma_rate); burst figure",
+                "kernel": kernel, "kernel_ms": res["kern_ms"], "kernel_share_of_step": res["share"],
+                "work_per_path": W, "events_per_path": ev,
+                "hbm": {"algorithmic_bytes_per_launch": 9 * l_local, "achieved_GBs": 9e-9 * l_local / (res["kern_ms"] * 1e-3),
+                        "peak_GBs": hbm_peak, "peak_source": hbm_src}}
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -147,192 +277,132 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="MHRS", choices=["MHRS", "ECS", "DCS"])
     ap.add_argument("--config", type=int, default=3)
-    ap.add_argument("--obs", dest="l", type=int, default=None, help="override the number of observations")
+    ap.add_argument("--obs", dest="l", type=int, default=None, help="observations per GPU (default: the config's own count)")
     ap.add_argument("--mhit", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the ECS / DCS side measurements at N = 1")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling side measurement at N > 1")
     args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = max(args.warmup, 1)
+    args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from phasetype_b200 import synth
+    full_l = args.l or {1: 100, 2: 10 ** 6, 3: 10 ** 7, 4: 10 ** 7, 5: 10 ** 8}[args.config]
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        wl = synth.config(args.config, args.method, l=min(args.l or 10 ** 7, 2 * 10 ** 6))
-        full_l = args.l or {1: 100, 2: 10 ** 6, 3: 10 ** 7, 4: 10 ** 7, 5: 10 ** 8}[args.config]
+        wl = synth.config(args.config, args.method, l=min(full_l, 2 * 10 ** 6))
         cores = os.cpu_count() or 1
         kind = ref_kind()
         sample = args.cpu_sample or min(wl.l, 20000 * cores)
         pps, ms = cpu_sweeps(wl, args.method, args.mhit, sample, cores, args.steps, args.warmup, kind)
         line = {"impl": "reference", "metric": "path_draws_per_sec", "value": pps, "unit": "paths/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "gibbs_iters_per_sec_extrapolated": pps / full_l,
                 "config": {"workload": wl.name, "method": args.method, "mhit": args.mhit, "phases": wl.n,
                            "observations": full_l, "sample_per_step": sample},
                 "cpu_baseline": {"value": pps, "unit": "paths/s", "cores": cores,
                                  "kind": "reference" if kind == "ref" else "port",
-                                 "sample": "%d observations per step, %d single-threaded processes" % (sample, cores)},
+                                 "sample": "%d observations per step, %d single-threaded processes (the reference is single-threaded and not re-entrant)" % (sample, cores)},
                 "e2e": {"value": pps, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ B200 arm
     import phasetype_b200 as pb
-    dist = None; torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = synth.config(args.config, args.method, l=args.l)
-    l = wl.l
-    y_loc, c_loc = wl.shard(rank, world)
-    y_loc = np.ascontiguousarray(y_loc); c_loc = np.ascontiguousarray(c_loc)
-    sum_y = float(wl.y.sum())
-    code = METHOD_CODE[args.method]
+    R = Runner(args, rank, world, local_rank)
+    method = args.method
+    # weak scaling: rank r owns an independent data set of the same model (global observation r + k * world)
+    wl = synth.config(args.config, method, l=full_l, shard=(rank if world > 1 else None))
+    y_loc = np.ascontiguousarray(wl.y); c_loc = np.ascontiguousarray(wl.censored)
+    l_local = int(y_loc.shape[0]); l_global = l_local * world
+    sum_y = R.reduce(float(y_loc.sum()), "max") * world * 1.0000001 if world > 1 else float(y_loc.sum())
 
-    def make_engine(graph):
-        e = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, y_loc, c_loc, method=code, mhit=args.mhit, seed=SEED,
-                      device=local_rank, rank=rank, world=world, use_graph=graph, sum_y_global=sum_y)
-        if world > 1:
-            buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                import ctypes as C
-                raw = (C.c_char * 128)()
-                if pb.lib().pht_comm_unique_id(raw) != 0:
-                    raise RuntimeError(pb.lib().pht_last_error().decode())
-                buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-            dist.broadcast(buf, 0)
-            e.comm_init(bytes(buf.cpu().numpy().tobytes()))
-        e.set_theta(wl.theta, next_iter=1)
-        return e
-
-    def barrier():
-        if world > 1:
-            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    eng = make_engine(True)
-    eng.run(args.warmup)
-    c0 = eng.counters()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    t_wall0 = time.perf_counter()
-    eng.enqueue(args.steps); eng.sync()
-    t_wall = time.perf_counter() - t_wall0
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms, _ = eng.last_ms()
-    total_ms = max_over_ranks(total_ms)
-    c1 = eng.counters()
-    launches = c1["launches"] - c0["launches"]
-    ev_gpu = {k: (c1[k] - c0[k]) / float(args.steps * max(1, y_loc.shape[0])) for k in ("attempts", "jumps", "deferred")}
-    tail_rounds = (c1["tail_rounds"] - c0["tail_rounds"]) / float(args.steps)
-    value = l * args.steps / (total_ms * 1e-3)
-    eng.close()
-
-    # ---- instrumented pass: average duration of the path kernel alone (CUDA events around each launch)
-    eng2 = make_engine(False)
-    eng2.run(args.warmup)
-    barrier()
-    eng2.enqueue(min(args.steps, 32)); eng2.sync()
-    tot2, kern_ms = eng2.last_ms()
-    kern_ms = max_over_ranks(kern_ms)
-    share = kern_ms * min(args.steps, 32) / max(tot2, 1e-9)
-    eng2.close()
+    res = R.timed(wl, method, y_loc, c_loc, sum_y, args.steps, args.warmup, clocks=True)
+    value = l_global * args.steps / (res["total_ms"] * 1e-3)
 
     line = None
     if rank == 0:
         fma_rate = pb.fp64_fma_rate(local_rank)
         line = {"metric": "path_draws_per_sec", "value": value, "unit": "paths/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "gibbs_iters_per_sec": args.steps / (total_ms * 1e-3),
-                "config": {"workload": wl.name, "method": args.method, "mhit": args.mhit, "phases": wl.n,
-                           "parameters": wl.m, "observations": l, "sharding": "observation i -> rank i mod %d" % world,
-                           "l2_note": "inputs (%.0f MB per GPU) are streamed once per sweep; each sweep re-reads them after ~%.1f ms of unrelated work, and at l >= 1e7 they exceed no cache assumption because the kernel is FP64-issue bound (12 B per path)" % (9e-6 * y_loc.shape[0], total_ms / args.steps)},
-                "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * t_wall / args.steps,
-                "device_events_per_path": ev_gpu, "tail_rounds_per_sweep": tail_rounds,
-                "clocks": clocks}
-    # ---- roofline (rank 0): algorithmic work from oracle event counts on the benchmark's own inputs
-    if rank == 0:
-        from oracle import pyoracle as po
-        po.build()
-        S, s = model_matrices(wl)
-        ns = min(l, 20000)
-        if args.method == "MHRS":
-            _, _, _, cnt = po.mhrs_paths("oracle", SEED, 1, wl.y[:ns], wl.censored[:ns], S, s, mhit=args.mhit, want=False)
-        else:
-            cnt = po.spectral_paths("oracle", args.method, SEED, 1, wl.y[:ns], wl.censored[:ns], S, s, want=False)[-1]
-        ev = {k: v / float(ns) for k, v in cnt.items()}
-        W = work_per_path(args.method, wl.n, ev)
-        per_launch = W * y_loc.shape[0]
-        achieved = per_launch / (kern_ms * 1e-3)
-        line["roofline"] = {"bound": "fp64_issue", "achieved": achieved / 1e9, "peak": fma_rate / 1e9, "unit": "G FP64-instr-equiv/s",
-                            "frac": achieved / fma_rate, "traffic": None,
-                            "peak_source": "measured in this run: dependent FP64 FMA chains on all SMs (pht_fp64_fma_rate)",
-                            "kernel": "k_%s_sweep" % args.method.lower(), "kernel_ms": kern_ms, "kernel_share_of_step": share,
-                            "work_per_path": W, "events_per_path": ev,
-                            "hbm": {"algorithmic_bytes_per_launch": 9 * y_loc.shape[0],
-                                    "achieved_GBs": 9e-9 * y_loc.shape[0] / (kern_ms * 1e-3), "peak_GBs": _peak_hbm()}}
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["total_ms"] / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "gibbs_iters_per_sec": args.steps / (res["total_ms"] * 1e-3),
+                "config": {"workload": wl.name, "method": method, "mhit": args.mhit, "phases": wl.n, "parameters": wl.m,
+                           "observations": l_global, "observations_per_gpu": l_local,
+                           "sharding": "observation i of the global set -> rank i mod %d; one NCCL all-reduce of n^2+2n int64 per sweep" % world
+                           if world > 1 else "single GPU",
+                           "l2": "flushed: a %d MiB memset on the sweep stream before every sweep, inside the timed region" % (FLUSH_BYTES >> 20)},
+                "gpu_launches": res["launches"], "wall_ms_per_step": 1e3 * res["wall"] / args.steps,
+                "device_events_per_path": res["events"], "tail_rounds_per_sweep": res["tail_rounds"],
+                "clocks": res["clocks"]}
+        line["roofline"] = R.roofline(wl, method, res, l_local, fma_rate)
+
+    # ---- strong scaling beside it (N > 1): the config's own 10^7 observations sharded N ways
+    if world > 1 and not args.no_strong:
+        wls = synth.config(args.config, method, l=full_l)
+        ys, cs = wls.shard(rank, world)
+        rs = R.timed(wls, method, np.ascontiguousarray(ys), np.ascontiguousarray(cs), float(wls.y.sum()), args.steps, args.warmup)
+        if rank == 0:
+            line["strong"] = {"observations": full_l, "value": full_l * args.steps / (rs["total_ms"] * 1e-3), "unit": "paths/s",
+                              "ms_per_step": rs["total_ms"] / args.steps, "kernel_ms": rs["kern_ms"]}
+        del wls
 
     # ---- end to end through the drop-in routine with host buffers (upload, sweeps, download)
     e2e = None
     if not args.no_e2e:
-        barrier()
+        R.barrier()
+        code = METHOD_CODE[method]
         t0 = time.perf_counter()
         if world == 1:
             os.environ["PHT_B200_SEED"] = str(SEED); os.environ["PHT_B200_QUIET"] = "1"
             os.environ["PHT_B200_DEVICE"] = str(local_rank)
-            res = pb.ljma_gibbs(args.steps + 1, args.mhit, code, wl.n, wl.m, wl.nu, wl.zeta, wl.T, wl.C, wl.y,
+            out = pb.ljma_gibbs(args.steps + 1, args.mhit, code, wl.n, wl.m, wl.nu, wl.zeta, wl.T, wl.C, wl.y,
                                 wl.censored, wl.theta, silent=True)
-            assert np.isfinite(res).all() and (res[1:] > 0).all()
+            assert np.isfinite(out).all() and (out[1:] > 0).all()
         else:
-            e3 = make_engine(True)
-            res = e3.run(args.steps)
+            e3 = R.make_engine(wl, method, y_loc, c_loc, sum_y, True, False)
+            out = e3.run(args.steps)
             e3.close()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            dt = max_over_ranks(dt)
-        e2e = {"value": l * args.steps / dt, "unit": "paths/s", "h2d_bytes_per_step": int(12 * l / args.steps),
-               "d2h_bytes_per_step": int(8 * wl.m),
-               "note": "LJMA_Gibbs(it=%d) on host vectors: engine creation, upload of y/censored, %d sweeps, download of res" % (args.steps + 1, args.steps)
-               if world == 1 else "engine create from host shards + sweeps + result download on every rank"}
+        dt = R.reduce(time.perf_counter() - t0)
+        e2e = {"value": l_global * args.steps / dt, "unit": "paths/s", "h2d_bytes_per_step": int(12 * l_global / args.steps),
+               "d2h_bytes_per_step": int(8 * wl.m), "seconds": dt,
+               "note": ("LJMA_Gibbs(it=%d) on host vectors: engine creation, upload of y/censored (once per call, amortised over the sweeps), %d sweeps, download of res"
+                        % (args.steps + 1, args.steps)) if world == 1 else "engine creation from host shards + sweeps + result download on every rank"}
     if rank == 0:
         line["e2e"] = e2e
+        # ---- the other two samplers on the same shape (N = 1 only; fewer sweeps)
+        if world == 1 and not args.no_others:
+            others = {}
+            wl_sym = None
+            for m2 in ("ECS", "DCS"):
+                if m2 == method:
+                    continue
+                if wl_sym is None:
+                    wl_sym = synth.config(args.config, m2, l=full_l)
+                r2 = R.timed(wl_sym, m2, np.ascontiguousarray(wl_sym.y), np.ascontiguousarray(wl_sym.censored), float(wl_sym.y.sum()), 5, 3)
+                rf = R.roofline(wl_sym, m2, r2, wl_sym.l, fma_rate)
+                others[m2] = {"value": wl_sym.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,
+                              "workload": wl_sym.name, "steps": 5, "warmup": 3, "gpu_launches": r2["launches"],
+                              "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_ms", "work_per_path")}}
+            line["other_methods"] = others
         if not args.no_cpu:
-            cores = 1
+            from oracle import pyoracle as po
             kind = "ref" if po.have_ref() else "oracle"
-            sample = args.cpu_sample or min(l, 100000)
-            pps, ms = cpu_sweeps(wl, args.method, args.mhit, sample, cores, 3, 1, kind)
-            line["cpu_baseline"] = {"value": pps, "unit": "paths/s", "cores": cores,
+            sample = args.cpu_sample or min(l_local, 100000)
+            pps, ms = cpu_sweeps(wl, method, args.mhit, sample, 1, 3, 1, kind)
+            line["cpu_baseline"] = {"value": pps, "unit": "paths/s", "cores": 1,
                                     "kind": "reference" if kind == "ref" else "port",
-                                    "sample": "first %d observations, 3 sweeps, 1 process (the reference is single-threaded)" % sample}
+                                    "sample": "first %d observations of the workload, 3 sweeps, 1 process (the reference is single-threaded)" % sample}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        R.dist.barrier(); R.dist.destroy_process_group()
     return 0
-
-
-def _peak_hbm():
-    try:
-        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
-        return 6650.0
 
 
 if __name__ == "__main__":

@@ -88,6 +88,9 @@ int pht_engine_run(pht_engine *e, int nsweeps, double *out);
 /* asynchronous halves of pht_engine_run for timing with CUDA events */
 int pht_engine_enqueue(pht_engine *e, int nsweeps);
 int pht_engine_sync(pht_engine *e);
+/* measurement aid: write `bytes` of scratch (larger than L2) on the sweep stream before every sweep, so that no sweep
+ * finds its observations in L2 from the previous one; 0 switches it off (default) */
+int pht_engine_set_l2_flush(pht_engine *e, unsigned long long bytes);
 /* device time in ms of the sweeps enqueued by the last pht_engine_enqueue (after sync) */
 int pht_engine_last_ms(pht_engine *e, float *total_ms, float *path_kernel_ms);
 

@@ -22,6 +22,7 @@
 
 double pho_exp(double x) { return pht_exp(x); }
 double pho_log(double x) { return pht_log(x); }
+double pho_exp_general(double x) { return pht_exp_general(x); }      /* the all-range path, for the fast-path equivalence test */
 void pho_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
     pht_u32x4 r = pht_philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
     memcpy(out, r.v, sizeof(r.v));

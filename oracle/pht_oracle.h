@@ -41,6 +41,7 @@ enum {
 
 double pho_exp(double x);
 double pho_log(double x);
+double pho_exp_general(double x);
 void pho_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double pho_unif_at(uint64_t seed, uint32_t iter, uint32_t obs, uint32_t sub, uint32_t d);
 double pho_rgamma_at(uint64_t seed, uint32_t iter, uint32_t sub, double shape, double scale);

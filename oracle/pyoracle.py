@@ -76,6 +76,7 @@ def oracle():
         L = o.lib
         L.pho_exp.restype = C.c_double; L.pho_exp.argtypes = [C.c_double]
         L.pho_log.restype = C.c_double; L.pho_log.argtypes = [C.c_double]
+        L.pho_exp_general.restype = C.c_double; L.pho_exp_general.argtypes = [C.c_double]
         L.pho_unif_at.restype = C.c_double
         L.pho_unif_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.pho_rgamma_at.restype = C.c_double

@@ -18,7 +18,7 @@ SYMBOLS = [
     "pht_engine_destroy", "pht_comm_unique_id", "pht_engine_comm_init", "pht_engine_set_theta",
     "pht_engine_get_theta", "pht_engine_run", "pht_engine_enqueue", "pht_engine_sync", "pht_engine_last_ms",
     "pht_engine_sweep_stats", "pht_engine_paths", "pht_engine_set_spectral", "pht_engine_get_model",
-    "pht_engine_counters", "pht_fp64_fma_rate",
+    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush",
 ]
 CNT_NAMES = ["paths", "attempts", "jumps", "dens_evals", "env_updates", "brent_evals", "arms_calls",
              "metrop_rejects", "nonfinite", "deferred", "tail_rounds", "errors", "launches", "ns_lane", "ns_tail", "ns_replay"]
@@ -69,6 +69,7 @@ def lib():
     L.pht_engine_get_model.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     L.pht_engine_counters.argtypes = [C.c_void_p, _up]
     L.pht_fp64_fma_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.pht_engine_set_l2_flush.argtypes = [C.c_void_p, C.c_ulonglong]
     _lib = L
     return L
 
@@ -140,6 +141,9 @@ class Engine:
 
     def sync(self):
         _check(lib().pht_engine_sync(self._h))
+
+    def set_l2_flush(self, nbytes):
+        _check(lib().pht_engine_set_l2_flush(self._h, int(nbytes)))
 
     def last_ms(self):
         t = C.c_float(); k = C.c_float()

@@ -71,10 +71,12 @@ struct pht_engine {
     uint32_t *d_idx_exact = nullptr, *d_idx_cens = nullptr; unsigned long long n_exact = 0, n_cens = 0;   /* ECS launch lists */
     std::vector<uint8_t> h_cens;       /* host copy of the flags (ECS parity ranges) */
     double *d_inject = nullptr;        /* host-supplied evals | Q | Qinv (parity hook), else nullptr */
+    void *d_flush = nullptr; size_t flush_bytes = 0;   /* L2 flush scratch (measurement aid) */
     ModelLayout L;
     int grid_blocks = 0;
     /* graph */
     cudaGraphExec_t graph_exec = nullptr; int graph_res_rows = -1; double *graph_res = nullptr;
+    unsigned long long graph_launches = 0;      /* kernels one replay of the captured sweep launches */
     /* nccl */
     ncclComm_t comm = nullptr;
     /* timing */
@@ -178,7 +180,7 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     void *bufs[] = { e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens };
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -347,7 +349,9 @@ extern "C" int pht_engine_enqueue(pht_engine *e, int nsweeps) {
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long before = e->launches;
         int rc = enqueue_sweep(e, e->d_res, e->res_rows, false);
+        e->graph_launches = e->launches - before; e->launches = before;      /* counted per replay below */
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         if (rc != 0) { if (g) cudaGraphDestroy(g); return -1; }
         if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
@@ -358,7 +362,8 @@ extern "C" int pht_engine_enqueue(pht_engine *e, int nsweeps) {
     }
     CU(cudaEventRecord(e->ev0, e->stream));
     for (int k = 0; k < nsweeps; k++) {
-        if (graph) { CU(cudaGraphLaunch(e->graph_exec, e->stream)); }
+        if (e->d_flush) CU(cudaMemsetAsync(e->d_flush, k & 0xff, e->flush_bytes, e->stream));
+        if (graph) { CU(cudaGraphLaunch(e->graph_exec, e->stream)); e->launches += e->graph_launches; }
         else if (enqueue_sweep(e, e->d_res, e->res_rows, k < 64)) return -1;
     }
     CU(cudaEventRecord(e->ev1, e->stream));
@@ -384,6 +389,15 @@ extern "C" int pht_engine_sync(pht_engine *e) {
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaStreamSynchronize(e->stream));
     return check_state(e);
+}
+
+extern "C" int pht_engine_set_l2_flush(pht_engine *e, unsigned long long bytes) {
+    if (!e) return fail("null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->d_flush) { CU(cudaFree(e->d_flush)); e->d_flush = nullptr; e->flush_bytes = 0; }
+    if (bytes) { CU(cudaMalloc(&e->d_flush, (size_t)bytes)); e->flush_bytes = (size_t)bytes; }
+    return 0;
 }
 
 extern "C" int pht_engine_last_ms(pht_engine *e, float *total_ms, float *path_kernel_ms) {

@@ -63,7 +63,9 @@ def _general_T(R, s):
     return T, np.ones((n + 1, n + 1)), np.array(theta)
 
 
-def _finish(name, R, s, T, C, theta, l, frac_cens, rng):
+def _finish(name, R, s, T, C, theta, l, frac_cens, rng, shard=None):
+    if shard is not None:           # weak-scaling runs: same model, an independent data stream per shard
+        rng = np.random.default_rng([SEED0, 0x5348, int(shard)])
     y = simulate_pht(R, s, l, rng)
     cens = np.zeros(l, dtype=np.int32)
     if frac_cens > 0:
@@ -76,7 +78,7 @@ def _finish(name, R, s, T, C, theta, l, frac_cens, rng):
     return Workload(name, s.shape[0], T.ravel(order="F").copy(), C.ravel(order="F").copy(), theta, nu, zeta, y, cens, R, s)
 
 
-def dense(n, l, frac_cens, symmetric, seed, name):
+def dense(n, l, frac_cens, symmetric, seed, name, shard=None):
     rng = np.random.default_rng(seed)
     R = rng.uniform(0.2, 1.2, (n, n))
     if symmetric:
@@ -84,18 +86,19 @@ def dense(n, l, frac_cens, symmetric, seed, name):
     np.fill_diagonal(R, 0.0)
     s = rng.uniform(0.2, 1.2, n)
     T, C, theta = _general_T(R, s)
-    return _finish(name, R, s, T, C, theta, l, frac_cens, rng)
+    return _finish(name, R, s, T, C, theta, l, frac_cens, rng, shard)
 
 
-def config(cid, method="MHRS", l=None):
-    """Workload of BASELINE.json configs[cid-1] (cid = 1..5); l overrides the observation count."""
+def config(cid, method="MHRS", l=None, shard=None):
+    """Workload of BASELINE.json configs[cid-1] (cid = 1..5); l overrides the observation count; shard = k gives the
+    k-th independent data set of the same model (rank k of a weak-scaling run)."""
     sym = method in ("ECS", "DCS")
     if cid == 1:
         S = np.array([[-3.6, 1.8, 1.8], [9.5, -11.3, 0.0], [9.5, 0.0, -11.3]])
         R = S.copy(); np.fill_diagonal(R, 0.0)
         s = -S.sum(1)
         T, C, theta = _general_T(R, s)
-        return _finish("C1: 3-phase package example", R, s, T, C, theta, l or 100, 0.0, np.random.default_rng(SEED0 + 1))
+        return _finish("C1: 3-phase package example", R, s, T, C, theta, l or 100, 0.0, np.random.default_rng(SEED0 + 1), shard)
     if cid == 2:
         n = 4
         R = np.zeros((n, n)); s = np.full(n, 0.3)
@@ -103,17 +106,17 @@ def config(cid, method="MHRS", l=None):
             R[i, i + 1] = 1.0 + 0.37 * i
         s[n - 1] = 1.5
         T, C, theta = _general_T(R, s)
-        return _finish("C2: 4-phase Coxian, exact", R, s, T, C, theta, l or 10 ** 6, 0.0, np.random.default_rng(SEED0 + 2))
+        return _finish("C2: 4-phase Coxian, exact", R, s, T, C, theta, l or 10 ** 6, 0.0, np.random.default_rng(SEED0 + 2), shard)
     if cid == 3:
-        return dense(8, l or 10 ** 7, 0.2, sym, SEED0 + 3, "C3: 8-phase dense%s, 20%% right-censored" % (" symmetric" if sym else ""))
+        return dense(8, l or 10 ** 7, 0.2, sym, SEED0 + 3, "C3: 8-phase dense%s, 20%% right-censored" % (" symmetric" if sym else ""), shard)
     if cid == 5:
-        return dense(32, l or 10 ** 8, 0.0, sym, SEED0 + 5, "C5: 32-phase dense%s" % (" symmetric" if sym else ""))
+        return dense(32, l or 10 ** 8, 0.0, sym, SEED0 + 5, "C5: 32-phase dense%s" % (" symmetric" if sym else ""), shard)
     if cid == 4:
-        return series_parallel(l or 10 ** 7)
+        return series_parallel(l or 10 ** 7, shard=shard)
     raise ValueError("config id must be 1..5")
 
 
-def series_parallel(l, seed=SEED0 + 4, f=0.5, r=4.0):
+def series_parallel(l, seed=SEED0 + 4, f=0.5, r=4.0, shard=None):
     """C4: two 2-out-of-3 blocks in series (6 independent repairable components): the system is up while
     each block has at most one failed component, which gives 4 x 4 = 16 up-states = the transient phases.
     Every failure cell is the tied parameter F and every repair cell R (the structure of
@@ -146,4 +149,4 @@ def series_parallel(l, seed=SEED0 + 4, f=0.5, r=4.0):
                 T[i, idx[nxt]] = R_ID; R[i, idx[nxt]] = r
     theta = np.array([f, r])
     rng = np.random.default_rng(seed)
-    return _finish("C4: 16-state series-parallel, tied F/R", R, s, T, C, theta, l, 0.0, rng)
+    return _finish("C4: 16-state series-parallel, tied F/R", R, s, T, C, theta, l, 0.0, rng, shard)

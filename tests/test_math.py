@@ -35,6 +35,34 @@ def test_exp_log_within_one_ulp_of_libm():
     assert abs(L.pho_log(5e-324) - np.log(5e-324)) < 1e-12
 
 
+def test_exp_fast_path_is_bit_identical_to_the_general_path():
+    """pht_exp scales by the exponent field for |x| <= 708 and falls back to the two-step scaling elsewhere; wherever
+    both apply they must agree to the last bit (the golden vectors were produced with the general path)."""
+    L = po.oracle()
+    rng = np.random.default_rng(2)
+    xs = np.concatenate([rng.uniform(-708, 708, 60000), rng.uniform(-1, 1, 20000), np.nextafter(708.0, 0) * np.array([1.0, -1.0]),
+                         np.array([708.0, -708.0, 0.0, -0.0, 1e-300, -1e-300, 0.5 * np.log(2), -0.5 * np.log(2)]),
+                         np.log(2.0) * rng.integers(-1021, 1021, 2000) + rng.normal(0, 1e-12, 2000)])
+    for x in xs:
+        a = L.pho_exp(float(x)); b = L.pho_exp_general(float(x))
+        assert a == b and np.signbit(a) == np.signbit(b), x
+    for x in (708.0000001, -708.0000001, 709.5, -740.0, -745.2, 710.0, np.inf, -np.inf):
+        assert L.pho_exp(x) == L.pho_exp_general(x)
+    assert np.isnan(L.pho_exp(np.nan))
+
+
+def test_uniform_single_subtraction_is_exact():
+    """pht_u01 builds (x + 0.5) 2^-52 as 1.x - (1 - 2^-53); check against exact integer arithmetic."""
+    L = po.oracle()
+    from fractions import Fraction
+    for k in range(300):
+        c = (C.c_uint32 * 4)(k, 0, 5, 1); key = (C.c_uint32 * 2)(7, 0); out = (C.c_uint32 * 4)()
+        L.lib.pho_philox(c, key, out)
+        x = ((int(out[1]) << 32) | int(out[0])) >> 12
+        want = Fraction(2 * x + 1, 2 ** 53)
+        assert Fraction(L.pho_unif_at(7, 1, 5, 0, 2 * k)) == want
+
+
 def test_uniforms_are_open_interval_and_keyed():
     L = po.oracle()
     u = np.array([L.pho_unif_at(7, 1, k, 0, d) for k in range(200) for d in range(6)])
