@@ -94,3 +94,20 @@ def test_wrapper_argument_checks_follow_the_r_code():
         api.phtMCMC(x, 3, [1, 0, 0], [1.0] * 8, [1.0] * 3, 5)
     with pytest.raises(ValueError):                      # 11 states: "S111" names collide, as upstream (R/phtMCMC.R:17)
         api.phtMCMC(x, 11, np.ones(11), np.ones(121), np.ones(11), 5)
+
+
+@pytest.mark.parametrize("kw,msg", [(dict(n=0), "outside 1.."), (dict(n=33), "outside 1.."), (dict(method=8), "unknown sampling method"),
+                                    (dict(mhit=-1), "mhit"), (dict(rank=2, world=2), "bad shard"), (dict(zbits=60), "zbits")])
+def test_engine_rejects_bad_arguments_before_touching_the_device(kw, msg):
+    a = dict(n=3, method=1, mhit=1, rank=0, world=1, zbits=30); a.update(kw)
+    n1 = max(a["n"], 1) + 1
+    with pytest.raises(pb.EngineError, match=msg):
+        pb.Engine(a["n"], np.zeros(n1 * n1, dtype=np.int32), np.ones(n1 * n1), [1.0], [1.0], [1.0], [0], method=a["method"],
+                  mhit=a["mhit"], rank=a["rank"], world=a["world"], zbits=a["zbits"])
+
+
+def test_weak_scaling_shards_share_the_model():
+    from phasetype_b200 import synth
+    a = synth.config(3, "MHRS", l=500); b = synth.config(3, "MHRS", l=500, shard=1); c = synth.config(3, "MHRS", l=500, shard=1)
+    assert np.array_equal(a.theta, b.theta) and np.array_equal(a.T, b.T)
+    assert not np.array_equal(a.y, b.y) and np.array_equal(b.y, c.y)

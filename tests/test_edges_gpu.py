@@ -1,0 +1,123 @@
+"""Edge cases of the path on the GPU, each checked against the oracle: a single phase, single and zero observations,
+every observation censored, an empty shard, a complex spectrum under a spectral sampler, and the L2-flush aid."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from phasetype_b200 import synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+CODE = {"MHRS": 1, "ECS": 2, "DCS": 4}
+
+
+def _paths(method, R, s, y, cens, seed=11, it=3, mhit=1, cap=0):
+    import phasetype_b200 as pb
+    n = s.shape[0]
+    T, C, theta = util.general_model(R, s)
+    m = theta.shape[0]
+    eng = pb.Engine(n, T, C, np.full(m, 2.0), np.full(m, 2.0), y, cens, method=CODE[method], mhit=mhit, seed=seed, mhrs_cap=cap)
+    S, sv = util.assemble(T, C, theta, n)
+    spec = None
+    if method != "MHRS":
+        spec = po.eigen("oracle", S, n)
+        eng.set_spectral(*spec)
+    eng.set_theta(theta, next_iter=it)
+    B, N, z = eng.paths()
+    eng.close()
+    if method == "MHRS":
+        Bo, No, zo, _ = po.mhrs_paths("oracle", seed, it, y, cens, S, sv, mhit=mhit)
+    else:
+        Bo, No, zo, _ = po.spectral_paths("oracle", method, seed, it, y, cens, S, sv, spectral=spec)
+    return (B, N, z), (Bo, No, zo)
+
+
+@pytest.mark.parametrize("method", ["MHRS", "ECS", "DCS"])
+def test_single_phase_is_the_exponential_distribution(method):
+    """n = 1: the only path is 'stay in state 1 until y' (exact) -- N = [1], z = [y]."""
+    R = np.zeros((1, 1)); s = np.array([0.7])
+    rng = np.random.default_rng(1)
+    y = rng.exponential(1.0 / 0.7, 300) + 1e-3
+    cens = np.zeros(300, dtype=np.int32)
+    got, want = _paths(method, R, s, y, cens)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert (got[1] == 1).all() and np.array_equal(got[2][:, 0], y)
+
+
+@pytest.mark.parametrize("method", ["MHRS", "ECS", "DCS"])
+def test_one_observation(method):
+    rng = np.random.default_rng(2)
+    R, s = util.dense_rates(4, rng, symmetric=True)
+    got, want = _paths(method, R, s, np.array([0.83]), np.zeros(1, dtype=np.int32))
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("method", ["MHRS", "ECS", "DCS"])
+def test_every_observation_censored(method):
+    """MHRS and ECS draw paths absorbed after y; DCS ignores the flag (src/Simulate_AbsCTMC_eq_AslettHobolth_DCS.c:132-133)."""
+    rng = np.random.default_rng(3)
+    R, s = util.dense_rates(5, rng, symmetric=True)
+    y = rng.exponential(0.8, 800) + 0.01
+    cens = np.ones(800, dtype=np.int32)
+    got, want = _paths(method, R, s, y, cens, cap=8)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    if method != "DCS":
+        assert (got[2].sum(1) >= y - 1e-12).all()          # the latent chain lives at least until the censoring time
+    else:
+        assert np.allclose(got[2].sum(1), y, rtol=1e-12)
+
+
+@pytest.mark.parametrize("method", ["MHRS", "DCS", "ECS"])
+def test_zero_observations_and_empty_shard(method):
+    """No data: the sweep statistics are zero and the update is a prior draw; a rank whose shard is empty still runs."""
+    import phasetype_b200 as pb
+    # prior draws are not symmetric, so the spectral samplers get the Coxian shape (triangular S: real spectrum always)
+    wl = synth.config(3 if method == "MHRS" else 2, method, l=64)
+    none = np.zeros(0)
+    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, none, none.astype(np.int32), method=CODE[method], seed=5, sum_y_global=1.0)
+    eng.set_theta(wl.theta, next_iter=1)
+    N, B, z = eng.sweep_stats()
+    assert not N.any() and not B.any() and not z.any()
+    got = eng.run(3)
+    eng.close()
+    want, _ = po.gibbs(5, 4, 1, CODE[method], wl.n, wl.nu, wl.zeta, wl.T, wl.C, none, none.astype(np.int32), wl.theta)
+    assert np.array_equal(got, want[1:])
+    # world = 3 over 2 observations: rank 2 owns nothing
+    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y[2:2:3], wl.censored[2:2:3], method=CODE[method], seed=5, rank=2, world=3,
+                    sum_y_global=float(wl.y[:2].sum()))
+    eng.set_theta(wl.theta, next_iter=1)
+    N, B, z = eng.sweep_stats()
+    eng.close()
+    assert not N.any() and not B.any() and not z.any()
+
+
+def test_complex_spectrum_is_reported_not_sampled():
+    """The reference carries on with a meaningless Q when S has complex eigenvalues (src/utility.c:118-121); the engine's
+    solver raises the error word instead."""
+    import phasetype_b200 as pb
+    wl = synth.config(3, "MHRS", l=256)          # unsymmetrised dense 8-phase generator: complex pairs
+    ev = np.linalg.eigvals(np.array(util.assemble(wl.T, wl.C, wl.theta, wl.n)[0]).reshape(wl.n, wl.n, order="F"))
+    if np.abs(ev.imag).max() < 1e-9:
+        pytest.skip("this generator happens to have a real spectrum")
+    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=2, seed=1)
+    eng.set_theta(wl.theta, next_iter=1)
+    with pytest.raises(pb.EngineError, match="complex eigenvalues"):
+        eng.run(1)
+    eng.close()
+
+
+def test_l2_flush_does_not_change_the_chain():
+    import phasetype_b200 as pb
+    wl = synth.config(2, "MHRS", l=4000)
+    out = []
+    for flush in (0, 8 << 20):
+        eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=1, seed=77)
+        eng.set_l2_flush(flush)
+        eng.set_theta(wl.theta, next_iter=1)
+        out.append(eng.run(4))
+        eng.close()
+    assert np.array_equal(out[0], out[1])
