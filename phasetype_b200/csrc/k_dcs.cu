@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
         }
         if (idle == FULL) { if (disp.exhausted) break; else continue; }
         const int kind0 = kind;
+        __syncwarp();                       /* refilled lanes and the rest take the unit together */
 
         /* ---- the unit's exponential batch: exp(alpha ev_i + beta), into E for a JUMP unit, else into X */
         if (kind0 != K_IDLE) {

@@ -330,12 +330,17 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
             idle = __ballot_sync(FULL, !active);
         }
         if (idle == FULL) { if (disp.exhausted) break; else continue; }
-        if (!active) continue;
+        /* Structured from here on (no `continue` out of the step): the lanes that have just been refilled, the lanes
+         * that absorb and the lanes that go on to a sojourn must run each stage TOGETHER, and the explicit warp
+         * barriers make the reconvergence points unmistakable for the compiler (without them the refilled lanes ran
+         * the whole step body on their own: every stage showed ~15 of 32 lanes, profiles/r1_final_ecs_1e7_ncu_full.md). */
+        __syncwarp();
+        const bool step = active;
 
         /* ---- one step of the path (eq_Aslett_ECS.c:247-364) */
-        const double y_t = y - t, Sjj = sm.S[j + j * n];
+        const double y_t = y - t, Sjj = step ? sm.S[j + j * n] : -1.0;
         bool absorb = false;
-        if (sm.s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
+        if (step && sm.s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
             const double num = (Sjj * y_t) + pht_log(sm.s[j]);
             double den = 0.0;
 #pragma unroll 1
@@ -347,8 +352,9 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
             sm.Z[j * ECS_THREADS + tid] += y - t;                                       /* :369 */
             path_flush<ECS_THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
             c.paths++; active = false;
-            continue;
         }
+        __syncwarp();
+        if (step && !absorb) {
         /* p_j = S[j,.]/(-S_jj) with p_jj = 0 (:292-295); PQ = p_j^T Q in reference-BLAS order (:160) */
 #pragma unroll 1
         for (int i = 0; i < n; i++) sm.W[i * ECS_THREADS + tid] = (i == j) ? 0.0 : sm.S[j + i * n] / (-Sjj);
@@ -383,6 +389,7 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
         sm.Z[j * ECS_THREADS + tid] += d;                                               /* :362 */
         count_transition(p, n, sm.Nacc, out_idx, j, k);                                 /* :363 */
         j = k; c.jumps++;
+        }
     }
     ecs_finish(p, n, sm, c);
 }
@@ -417,8 +424,8 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList l
             idle = __ballot_sync(FULL, !active);
         }
         if (idle == FULL) { if (disp.exhausted) break; else continue; }
-        if (!active) continue;
-
+        __syncwarp();                       /* refilled and continuing lanes take the step together (see k_ecs_exact) */
+        if (active) {
         /* ---- one step (gt_Aslett_DCS.c:339-384 with censored = 1) */
         const double lastt = t; const int lastj = j;
         const double Sjj = sm.S[j + j * n];
@@ -487,11 +494,12 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList l
             count_transition(p, n, sm.Nacc, out_idx, lastj, lastj);
             path_flush<ECS_THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
             c.paths++; active = false;
-            continue;
+        } else {
+            sm.Z[lastj * ECS_THREADS + tid] += t - lastt;                               /* :382 */
+            count_transition(p, n, sm.Nacc, out_idx, lastj, k);                         /* :383 */
+            j = k;
         }
-        sm.Z[lastj * ECS_THREADS + tid] += t - lastt;                                   /* :382 */
-        count_transition(p, n, sm.Nacc, out_idx, lastj, k);                             /* :383 */
-        j = k;
+        }
     }
     ecs_finish(p, n, sm, c);
 }

@@ -242,10 +242,12 @@ __device__ __forceinline__ void replay_session(const SweepParams &p, const Smem 
             idle = __ballot_sync(FULL, !active);
         }
         if (idle == FULL) break;
-        if (!active) continue;
-        const bool ended = walk_step<true>(w, y, cens, og, p, sm, iter, n, rec);
-        c_jumps++;
-        if (ended) { finish_replay(w, rec, y, cens, p, sm, n); c_paths++; active = false; }
+        __syncwarp();
+        if (active) {
+            const bool ended = walk_step<true>(w, y, cens, og, p, sm, iter, n, rec);
+            c_jumps++;
+            if (ended) { finish_replay(w, rec, y, cens, p, sm, n); c_paths++; active = false; }
+        }
     }
     __syncwarp();
     if (lane == 0) sm.ring_n[warp] = 0u;
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                 idle = __ballot_sync(FULL, !active);
             }
             if (idle == FULL) { if (exhausted) break; else continue; }
+            __syncwarp();                   /* lanes that have just taken an observation step together with the rest */
             if (active) {
                 const bool ended = walk_step<false>(w, y, cens, og, p, sm, iter, n, norec);
                 c_jumps++;
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                         pool_next += cnt < avail ? cnt : avail;
                     }
                     bool survived = false;
+                    __syncwarp();           /* lanes that have just drawn an attempt step together with the rest */
                     if (active) {
                         const bool ended = walk_step<false>(w, my_y, my_cens, my_og, p, sm, iter, n, norec);
                         c_jumps++;
