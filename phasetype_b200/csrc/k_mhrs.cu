@@ -50,7 +50,9 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef MHRS_THREADS
 #define MHRS_THREADS 256
+#endif
 #define MHRS_WARPS (MHRS_THREADS / 32)
 #ifndef MHRS_MIN_BLOCKS
 #define MHRS_MIN_BLOCKS 3                /* 80 registers: 24 warps per SM */
