@@ -158,15 +158,14 @@ def oracle_events(wl, method, mhit, ns):
     return {k: v / float(ns) for k, v in cnt.items()}
 
 
-def ncu_traffic(method, l_local):
-    """DRAM bytes per launch of the path kernel from the committed `ncu --set full` capture of this workload
-    (profiles/traffic.json, written by tools/ncu_traffic.py); None when there is no capture at this size."""
+def ncu_capture(method, l_local):
+    """What the committed `ncu --set full` capture of this workload recorded for the path kernel (profiles/traffic.json,
+    written by tools/ncu_traffic.py): DRAM bytes and warp instructions per launch; {} when there is no capture."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        e = t.get("%s:%d" % (method, l_local))
-        return None if e is None else e["dram_bytes_per_launch"]
+        return t.get("%s:%d" % (method, l_local)) or {}
     except Exception:
-        return None
+        return {}
 
 
 def _peak_hbm():
@@ -261,8 +260,17 @@ class Runner:
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
         kernel = {"MHRS": "k_mhrs_sweep", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
+        cap = ncu_capture(method, l_local)
+        issue = None
+        mhz = (res.get("clocks") or {}).get("sm_mhz") or getattr(self, "sm_mhz", None)
+        if cap.get("warp_instructions_per_launch") and mhz:
+            # second view of the same kernel: share of the SMs' warp-instruction issue slots it fills (148 SMs x 4 schedulers
+            # x clock); instruction count from the committed capture, time and clock from this run
+            slots = res["kern_ms"] * 1e-3 * 148 * 4 * mhz * 1e6
+            issue = {"warp_instructions_per_launch": cap["warp_instructions_per_launch"], "issue_slot_utilisation": cap["warp_instructions_per_launch"] / slots,
+                     "active_lanes_per_instruction": cap.get("active_lanes_per_instruction"), "source": cap.get("source")}
         return {"bound": "fp64_issue", "achieved": achieved / 1e9, "peak": fma_rate / 1e9, "unit": "G FP64-instr-equiv/s",
-                "frac": achieved / fma_rate, "traffic": ncu_traffic(method, l_local),
+                "frac": achieved / fma_rate, "traffic": cap.get("dram_bytes_per_launch"), "issue": issue,
                 "peak_source": "measured in this run: dependent FP64 FMA chains on all SMs (pht_fp64_fma_rate); burst figure",
                 "kernel": kernel, "kernel_ms": res["kern_ms"], "kernel_share_of_step": res["share"],
                 "work_per_path": W, "events_per_path": ev,
@@ -326,6 +334,7 @@ def main():
     sum_y = R.reduce(float(y_loc.sum()), "max") * world * 1.0000001 if world > 1 else float(y_loc.sum())
 
     res = R.timed(wl, method, y_loc, c_loc, sum_y, args.steps, args.warmup, clocks=True)
+    R.sm_mhz = (res.get("clocks") or {}).get("sm_mhz")
     value = l_global * args.steps / (res["total_ms"] * 1e-3)
 
     line = None
@@ -396,7 +405,7 @@ def main():
                 rf = R.roofline(wl_sym, m2, r2, wl_sym.l, fma_rate)
                 others[m2] = {"value": wl_sym.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,
                               "workload": wl_sym.name, "steps": 5, "warmup": 3, "gpu_launches": r2["launches"],
-                              "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_ms", "work_per_path")}}
+                              "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "issue", "kernel", "kernel_ms", "work_per_path")}}
             line["other_methods"] = others
         if not args.no_cpu:
             from oracle import pyoracle as po

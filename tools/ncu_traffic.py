@@ -8,7 +8,7 @@ rows = list(csv.reader(io.StringIO(out))); hdr, units = rows[0], rows[1]
 def to_bytes(v, u):
     v = float(v); u = u.lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-per_kernel = {}; missing = []
+per_kernel = {}; missing = []; winst = {}; lanes = {}
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     name = d["Kernel Name"].split("(")[0]
@@ -20,11 +20,18 @@ for r in rows[2:]:
     if rd != rd or wr != wr:          # ncu could not collect the counters for this launch
         missing.append(name); continue
     per_kernel.setdefault(name, []).append(rd + wr)
+    try:
+        winst.setdefault(name, []).append(float(d["smsp__inst_executed.sum"]))
+        lanes.setdefault(name, []).append(float(d["smsp__thread_inst_executed_per_inst_executed.ratio"]))
+    except (KeyError, ValueError):
+        pass
 total = sum(sum(v) / len(v) for v in per_kernel.values())      # one launch of each kernel of the method per sweep
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 t = json.load(open(path)) if os.path.exists(path) else {}
 t["%s:%d" % (method, l_local)] = {"dram_bytes_per_launch": total, "kernels": {k: sum(v) / len(v) for k, v in per_kernel.items()},
                                    "source": os.path.basename(rep), "algorithmic_bytes": 9 * l_local,
-                                   "not_collected": sorted(set(missing))}
+                                   "not_collected": sorted(set(missing)),
+                                   "warp_instructions_per_launch": sum(sum(v) / len(v) for v in winst.values()),
+                                   "active_lanes_per_instruction": {k: sum(v) / len(v) for k, v in lanes.items()}}
 json.dump(t, open(path, "w"), indent=1, sort_keys=True)
 print(json.dumps(t["%s:%d" % (method, l_local)]))
