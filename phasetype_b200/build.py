@@ -54,7 +54,7 @@ def build(force=False, verbose=False, ptxas_info=False, out=None, defines=()):
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-ldl", "-lm"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-ldl", "-lm"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
