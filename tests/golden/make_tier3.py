@@ -23,5 +23,5 @@ it = 1500
 out = {"y": y, "cens": cens, "T": T, "C": Cm, "nu": nu, "zeta": zeta, "it": it}
 for method in (1, 2, 4):
     out["chain_%d" % method] = po.ref_gibbs(5, False, it, 1, method, 3, nu, zeta, T, Cm, y, cens, [-1.0])
-np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tier3_reference_chain.npz"), **out)
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "chains", "tier3_reference_chain.npz"), **out)
 print("written", {k: np.asarray(v).shape for k, v in out.items()})

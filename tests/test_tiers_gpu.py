@@ -4,7 +4,7 @@ tests/test_{mhrs,dcs,ecs,golden,chain,edges}_gpu.py):
           with samples large enough (2e6 paths) to resolve 1e-3;
   tier 3  posterior means and an upper quantile of the engine's chain (through the drop-in LJMA_Gibbs) against the
           reference's own LJMA_Gibbs chain run in the build container and committed as a fixture
-          (tests/golden/tier3_reference_chain.npz, made by tests/golden/make_tier3.py)."""
+          (tests/golden/chains/tier3_reference_chain.npz, made by tests/golden/make_tier3.py)."""
 import os
 
 import numpy as np
@@ -49,7 +49,7 @@ def test_tier2_conditional_expectations(method, censored, mhit):
 @pytest.mark.parametrize("method", [1, 2, 4])
 def test_tier3_posterior_against_the_reference_chain(method):
     import phasetype_b200 as pb
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tier3_reference_chain.npz"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "chains", "tier3_reference_chain.npz"))
     os.environ["PHT_B200_SEED"] = "2718"; os.environ["PHT_B200_QUIET"] = "1"
     it = int(g["it"])
     res = pb.ljma_gibbs(it, 1, method, 3, 2, g["nu"], g["zeta"], g["T"], g["C"], g["y"], g["cens"], [-1.0])

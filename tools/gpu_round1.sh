@@ -1,6 +1,7 @@
 #!/bin/bash
-# round-1 evidence run: GPU tests, default bench, launch list of the bench command, full capture of each path kernel
-timeout -s KILL 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+# round-1 evidence run: smoke, GPU tests, default bench, launch list of the bench command, full capture of each path kernel
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout -s KILL 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout -s KILL 900 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench_r1.err
 BCMD="python bench.py --steps 5 --warmup 3 --no-others --no-cpu --no-e2e"
 timeout -s KILL 600 $BCMD > gpurun_out/bench_short.json 2>&1 && \
