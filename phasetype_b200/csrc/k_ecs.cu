@@ -24,6 +24,9 @@
 #include "path_common.cuh"
 
 #define ECS_THREADS 128
+#ifndef ECS_WARPS_PER_SM
+#define ECS_WARPS_PER_SM 16          /* launch bound: resident warps per SM the register allocation must allow */
+#endif
 #define A_XEPS 0.00001
 #define A_YEPS 0.1
 #define A_EYEPS 0.001
@@ -301,7 +304,7 @@ struct ListDispenser {
 };
 
 /* ------------------------------------------------------------------ exact observations */
-__global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsList list) {
+__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_ecs_exact(SweepParams p, ObsList list) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(ECS_THREADS) k_ecs_exact(SweepParams p, ObsLis
 }
 
 /* ------------------------------------------------------------------ censored observations */
-__global__ void __launch_bounds__(ECS_THREADS) k_ecs_gt(SweepParams p, ObsList list) {
+__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_ecs_gt(SweepParams p, ObsList list) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
