@@ -16,7 +16,8 @@ of the statistics block inside the captured sweep; a strong-scaling run (the sam
 is timed too and reported under "strong".
 
 The JSON line carries `roofline` (FP64-issue bound kernel: see DESIGN.md section 5), `cpu_baseline`, `e2e`, `clocks`,
-`gpu_launches`.  Only the cpu_baseline / --impl reference legs and the event counting for the work model touch oracle/.
+`gpu_launches`.  Only the cpu_baseline / --impl reference legs touch oracle/ (the work model's event counts come from
+the kernels' own counters).
 """
 import argparse
 import json
@@ -39,7 +40,7 @@ FLUSH_BYTES = 256 << 20          # > the 126 MB L2
 # ----------------------------------------------------------------------------- work model
 def work_per_path(method, n, ev):
     """FP64 instruction-equivalents per path, BASELINE.md section 4 (add/mul/fma/compare = 1, div = 8,
-    exp = 20, log = 25), from event counts per path measured by the oracle on the benchmark's inputs."""
+    exp = 20, log = 25), from event counts per path measured on the benchmark's own sweeps."""
     if method == "MHRS":
         return ev["jumps"] * (40 + n) + ev["attempts"] * (n + 2)
     if method == "ECS":
@@ -145,19 +146,6 @@ def ref_kind():
     return "ref" if po.have_ref() else "oracle"
 
 
-def oracle_events(wl, method, mhit, ns):
-    """Event counts per path on the first ns observations of the benchmark's own inputs (the work model's input)."""
-    from oracle import pyoracle as po
-    po.build()
-    S, s = model_matrices(wl)
-    ns = min(wl.l, ns)
-    if method == "MHRS":
-        cnt = po.mhrs_paths("oracle", SEED, 1, wl.y[:ns], wl.censored[:ns], S, s, mhit=mhit, want=False)[-1]
-    else:
-        cnt = po.spectral_paths("oracle", method, SEED, 1, wl.y[:ns], wl.censored[:ns], S, s, want=False)[-1]
-    return {k: v / float(ns) for k, v in cnt.items()}
-
-
 def ncu_capture(method, l_local):
     """What the committed `ncu --set full` capture of this workload recorded for the path kernel (profiles/traffic.json,
     written by tools/ncu_traffic.py): DRAM bytes and warp instructions per launch; {} when there is no capture."""
@@ -251,11 +239,13 @@ class Runner:
         nloc = max(1, y_loc.shape[0])
         return {"total_ms": total_ms, "wall": wall, "clocks": clk, "launches": int(c1["launches"] - c0["launches"]),
                 "kern_ms": kern_ms, "share": kern_ms * k / max(tot2, 1e-9),
-                "events": {q: (c1[q] - c0[q]) / float(steps * nloc) for q in ("attempts", "jumps", "deferred", "dens_evals", "brent_evals")},
+                "events": {q: (c1[q] - c0[q]) / float(steps * nloc) for q in ("attempts", "jumps", "deferred", "dens_evals", "env_updates", "brent_evals")},
                 "tail_rounds": (c1["tail_rounds"] - c0["tail_rounds"]) / float(steps)}
 
     def roofline(self, wl, method, res, l_local, fma_rate):
-        ev = oracle_events(wl, method, self.a.mhit, 20000)
+        # events per path counted by the kernels themselves over the timed sweeps (every attempt and jump-step the GPU
+        # ran, including the replay of accepted attempts): the work model needs nothing from the CPU checker
+        ev = res["events"]
         W = work_per_path(method, wl.n, ev)
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
@@ -409,6 +399,7 @@ def main():
             line["other_methods"] = others
         if not args.no_cpu:
             from oracle import pyoracle as po
+            po.build()
             kind = "ref" if po.have_ref() else "oracle"
             sample = args.cpu_sample or min(l_local, 100000)
             pps, ms = cpu_sweeps(wl, method, args.mhit, sample, 1, 3, 1, kind)
