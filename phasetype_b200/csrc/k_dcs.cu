@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 val1 = (0.0 + 1.0 * acc) * sm.s[gi];
             }
             double sum1 = 0.0;                                                                               /* P_ab, or the weights' total */
-#pragma unroll 1
+#pragma unroll 4
             for (int q = 0; q < n; q++) sum1 += __shfl_sync(FULL, val1, gbase + q);
             if (wj) {
                 const unsigned dg = sm.deg[j_r];
@@ -181,16 +181,17 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 sm.P[gi * THREADS + col] = v;
             }
             double p_sum = 0.0;
-#pragma unroll 1
+#pragma unroll 4
             for (int q = 0; q < n; q++) p_sum += __shfl_sync(FULL, v, gbase + q);      /* the term of state j is +0.0 */
             __syncwarp();
-            /* hand the three scalars back to the requesting lanes */
+            /* hand the three scalars back to the requesting lanes: find the group that served this lane, read its lane 0 */
+            int server = -1;
 #pragma unroll 1
-            for (int g = 0; g < ngroups; g++) {
-                const int src = g * G;
-                const int r_g = __shfl_sync(FULL, r, src);
+            for (int g = 0; g < ngroups; g++) if (__shfl_sync(FULL, r, g * G) == lane) server = g * G;
+            {
+                const int src = server < 0 ? 0 : server;
                 const double a0 = __shfl_sync(FULL, sum1, src), a1 = __shfl_sync(FULL, eS, src), a2 = __shfl_sync(FULL, p_sum, src);
-                if (r_g == lane) { sv_Pab = a0; sv_eS = a1; sv_psum = a2; }
+                if (server >= 0) { sv_Pab = a0; sv_eS = a1; sv_psum = a2; }
             }
             need &= ~served;
         }
