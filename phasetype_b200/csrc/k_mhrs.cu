@@ -59,12 +59,17 @@ namespace cg = cooperative_groups;
 #endif
 #define GUIDE 64                    /* buckets of the scan guide table */
 #define OBS_CHUNK 64u               /* observations a warp takes from the global counter at once */
+#ifndef END_CAP
 #define END_CAP 8u                   /* attempts a lane still tries once no observations are left */
+#endif
 #define RING 96                     /* per-warp ring of accepted attempts awaiting replay */
 #define RING_TRIGGER 64
 #define TAIL_CH 256u                /* attempts per tail chunk (a pool never crosses a chunk) */
 #define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
 #define TAIL_KMAX (1u << 24)
+#ifndef TAIL_GROWTH
+#define TAIL_GROWTH 2u               /* attempts per pending observation grow by this factor per round */
+#endif
 #define POOL_MIN 32u
 #define POOL_MAX 2048u
 #define FOUND_NONE 0xFFFFFFFFFFFFFFFFull
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (gtid == 0) { p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; }
             grid.sync();
             cur ^= 1; rounds++;
-            K = (K < TAIL_KMAX) ? K * 2u : K;
+            K = (K < TAIL_KMAX) ? K * TAIL_GROWTH : K;
         }
         if (timekeeper) { const unsigned long long t = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_TAIL], t - t_mark); t_mark = t; }
         /* --- replay the accepted attempt of every tail observation */
