@@ -51,8 +51,6 @@ struct EcsSmem {
     }
 };
 
-struct ArmsPt { double x, y, ey, cum; int f, pl, pr; };
-
 struct EcsCounters { unsigned long long jumps, evals, updates, calls, rejects, nonfinite, paths; };
 
 /* log-density closures.  The evaluation itself is ONE out-of-line function per sampler: ARMS calls its density from
@@ -97,141 +95,204 @@ struct DensGt {
 __device__ __forceinline__ double a_expshift(double y, double y0) { return (y - y0 > -2.0 * A_YCEIL) ? pht_exp(y - y0 + A_YCEIL) : 0.0; }
 __device__ __forceinline__ double a_logshift(double y, double y0) { return pht_log(y) + y0 - A_YCEIL; }
 
+/* The ARMS envelope of one lane: an index-linked list of points (x, y, cum) with links packed as
+ * f | (pl + 1) << 8 | (pr + 1) << 16, as structure-of-arrays in local memory: 28 bytes per point (the reference's
+ * POINT is 56).  exp(y - ymax) is not stored: cumulate and invert recompute it where they need it (same function of
+ * the same numbers).  Typically 9-13 points are live; the capacity is the reference's 100. */
+template <int STRIDE, int CAPACITY>
+struct Env {
+    enum { capacity = CAPACITY };
+    double *ex, *ey, *ec; unsigned int *el;
+    __device__ __forceinline__ double x(int i) const { return ex[i * STRIDE]; }
+    __device__ __forceinline__ double y(int i) const { return ey[i * STRIDE]; }
+    __device__ __forceinline__ double cum(int i) const { return ec[i * STRIDE]; }
+    __device__ __forceinline__ unsigned lk(int i) const { return el[i * STRIDE]; }
+    __device__ __forceinline__ void setx(int i, double v) { ex[i * STRIDE] = v; }
+    __device__ __forceinline__ void sety(int i, double v) { ey[i * STRIDE] = v; }
+    __device__ __forceinline__ void setcum(int i, double v) { ec[i * STRIDE] = v; }
+    __device__ __forceinline__ void setlk(int i, unsigned v) { el[i * STRIDE] = v; }
+    __device__ __forceinline__ int f(int i) const { return (int)(lk(i) & 1u); }
+    __device__ __forceinline__ int pl(int i) const { return (int)((lk(i) >> 8) & 0xffu) - 1; }
+    __device__ __forceinline__ int pr(int i) const { return (int)((lk(i) >> 16) & 0xffu) - 1; }
+    __device__ __forceinline__ void setpl(int i, int v) { setlk(i, (lk(i) & ~0xff00u) | ((unsigned)(v + 1) << 8)); }
+    __device__ __forceinline__ void setpr(int i, int v) { setlk(i, (lk(i) & ~0xff0000u) | ((unsigned)(v + 1) << 16)); }
+    __device__ __forceinline__ static unsigned pack(int f, int pl, int pr) { return (unsigned)f | ((unsigned)(pl + 1) << 8) | ((unsigned)(pr + 1) << 16); }
+};
+typedef Env<1, A_NPOINT> EnvLocal;
+
 /* chord intersection at envelope point q (arms.c:659-764, Metropolis on) */
-__device__ __noinline__ void a_meet(ArmsPt *p, int q, double convex) {
+template <class E>
+__device__ __forceinline__ void a_meet(E &e, int q, double convex) {
     double gl = 0.0, gr = 0.0, grl = 0.0, dl = 0.0, dr = 0.0;
-    const int pl = p[q].pl, pr = p[q].pr;
+    const int pl = e.pl(q), pr = e.pr(q);
     bool il = false, ir = false, irl = false;
-    if (pl != A_NIL && p[p[pl].pl].pl != A_NIL) { const int a = p[p[pl].pl].pl; gl = (p[pl].y - p[a].y) / (p[pl].x - p[a].x); il = true; }
-    if (pr != A_NIL && p[p[pr].pr].pr != A_NIL) { const int a = p[p[pr].pr].pr; gr = (p[pr].y - p[a].y) / (p[pr].x - p[a].x); ir = true; }
-    if (pl != A_NIL && pr != A_NIL) { grl = (p[pr].y - p[pl].y) / (p[pr].x - p[pl].x); irl = true; }
+    double xpl = 0.0, ypl = 0.0, xpr = 0.0, ypr = 0.0;
+    if (pl != A_NIL) { xpl = e.x(pl); ypl = e.y(pl); }
+    if (pr != A_NIL) { xpr = e.x(pr); ypr = e.y(pr); }
+    if (pl != A_NIL) { const int a = e.pl(e.pl(pl)); if (a != A_NIL) { gl = (ypl - e.y(a)) / (xpl - e.x(a)); il = true; } }
+    if (pr != A_NIL) { const int a = e.pr(e.pr(pr)); if (a != A_NIL) { gr = (ypr - e.y(a)) / (xpr - e.x(a)); ir = true; } }
+    if (pl != A_NIL && pr != A_NIL) { grl = (ypr - ypl) / (xpr - xpl); irl = true; }
     if (irl && il && (gl < grl)) gl = gl + (1.0 + convex) * (grl - gl);
     if (irl && ir && (gr > grl)) gr = gr + (1.0 + convex) * (grl - gr);
-    if (il && irl) { dr = (gl - grl) * (p[pr].x - p[pl].x); if (dr < A_YEPS) dr = A_YEPS; }
-    if (ir && irl) { dl = (grl - gr) * (p[pr].x - p[pl].x); if (dl < A_YEPS) dl = A_YEPS; }
+    if (il && irl) { dr = (gl - grl) * (xpr - xpl); if (dr < A_YEPS) dr = A_YEPS; }
+    if (ir && irl) { dl = (grl - gr) * (xpr - xpl); if (dl < A_YEPS) dl = A_YEPS; }
     if (il && ir && irl) {
-        p[q].x = (dl * p[pr].x + dr * p[pl].x) / (dl + dr);
-        p[q].y = (dl * p[pr].y + dr * p[pl].y + dl * dr) / (dl + dr);
-    } else if (il && irl) { p[q].x = p[pr].x; p[q].y = p[pr].y + dr; }
-    else if (ir && irl) { p[q].x = p[pl].x; p[q].y = p[pl].y + dl; }
-    else if (il) p[q].y = p[pl].y + gl * (p[q].x - p[pl].x);
-    else if (ir) p[q].y = p[pr].y - gr * (p[pr].x - p[q].x);
+        e.setx(q, (dl * xpr + dr * xpl) / (dl + dr));
+        e.sety(q, (dl * ypr + dr * ypl + dl * dr) / (dl + dr));
+    } else if (il && irl) { e.setx(q, xpr); e.sety(q, ypr + dr); }
+    else if (ir && irl) { e.setx(q, xpl); e.sety(q, ypl + dl); }
+    else if (il) e.sety(q, ypl + gl * (e.x(q) - xpl));
+    else if (ir) e.sety(q, ypr - gr * (xpr - e.x(q)));
 }
 
 /* exponentiate and integrate the envelope (arms.c:625-655, :768-790); returns ymax */
-__device__ __noinline__ double a_cumulate(ArmsPt *p) {
-    double ymax = p[0].y;
-    for (int q = p[0].pr; q != A_NIL; q = p[q].pr) if (p[q].y > ymax) ymax = p[q].y;
-    for (int q = 0; q != A_NIL; q = p[q].pr) p[q].ey = a_expshift(p[q].y, ymax);
-    p[0].cum = 0.;
-    for (int q = p[0].pr; q != A_NIL; q = p[q].pr) {
-        const int l = p[q].pl; double a;
-        if (p[l].x == p[q].x) a = 0.;
-        else if (fabs(p[q].y - p[l].y) < A_YEPS) a = 0.5 * (p[q].ey + p[l].ey) * (p[q].x - p[l].x);
-        else a = ((p[q].ey - p[l].ey) / (p[q].y - p[l].y)) * (p[q].x - p[l].x);
-        p[q].cum = p[l].cum + a;
+template <class E>
+__device__ __forceinline__ double a_cumulate(E &e) {
+    double ymax = e.y(0);
+#pragma unroll 1
+    for (int q = e.pr(0); q != A_NIL; q = e.pr(q)) { const double yq = e.y(q); if (yq > ymax) ymax = yq; }
+    double xl = e.x(0), yl = e.y(0), eyl = a_expshift(yl, ymax), cl = 0.;
+    e.setcum(0, 0.);
+#pragma unroll 1
+    for (int q = e.pr(0); q != A_NIL; q = e.pr(q)) {
+        const double xq = e.x(q), yq = e.y(q), eyq = a_expshift(yq, ymax);
+        double a;
+        if (xl == xq) a = 0.;
+        else if (fabs(yq - yl) < A_YEPS) a = 0.5 * (eyq + eyl) * (xq - xl);
+        else a = ((eyq - eyl) / (yq - yl)) * (xq - xl);
+        cl = cl + a;
+        e.setcum(q, cl);
+        xl = xq; yl = yq; eyl = eyq;
     }
     return ymax;
 }
 
 /* One ARMS draw on (0, xr) with the four reference abscissae xr*{1e-6, 1/3, 2/3, 1-1e-6}: arms.c:115-222 */
-template <class Dens>
-__device__ double arms_draw(const SweepParams &p, uint32_t iter, PathRng &rng, const EcsSmem &sm, int n, const Dens &f,
-                            const double xinit[4], double xr, EcsCounters &c) {
-    ArmsPt e[A_NPOINT];
+/* `overflow` is set (and the return value meaningless) when the envelope E cannot take the next point although the
+ * reference's could. */
+template <class Dens, class E>
+__device__ __forceinline__ double arms_core(E &e, const SweepParams &p, uint32_t iter, PathRng &rng, const EcsSmem &sm, int n, const Dens &f,
+                                            const double xinit[4], double xr, EcsCounters &c, bool &overflow) {
     const double xl = 0.0, convex = 1.0;
+    overflow = false;
     const int mpoint = 9, right = mpoint - 1;
     c.calls++;
     if (xinit[0] <= xl || xinit[3] >= xr) return 0.0;                /* reference error 1003: caller uses xsamp = 0 */
     for (int i = 1; i < 4; i++) if (xinit[i] <= xinit[i - 1]) return 0.0;       /* error 1004 */
-    for (int j = 0; j < mpoint; j++) { e[j].pl = j - 1; e[j].pr = (j == mpoint - 1) ? A_NIL : j + 1; e[j].f = j & 1; e[j].y = 0.0; }
-    e[0].x = xl; e[right].x = xr;
+#pragma unroll 1
+    for (int j = 0; j < mpoint; j++) { e.setlk(j, E::pack(j & 1, j - 1, (j == mpoint - 1) ? A_NIL : j + 1)); e.sety(j, 0.0); }
+    e.setx(0, xl); e.setx(right, xr);
+#pragma unroll 1
     for (int j = 1, k = 0; j < mpoint - 1; j += 2) {
-        e[j].x = xinit[k++]; e[j].y = f(sm, n, e[j].x); c.evals++;
-        if (!isfinite(e[j].y)) c.nonfinite++;
+        const double xv = xinit[k++], yv = f(sm, n, xv); c.evals++;
+        e.setx(j, xv); e.sety(j, yv);
+        if (!isfinite(yv)) c.nonfinite++;
     }
     int cpoint = mpoint;
-    for (int j = 0; j < mpoint; j += 2) a_meet(e, j, convex);
-    double ymax = a_cumulate(e);
-    double xprev = 0.0, yprev = f(sm, n, xprev); c.evals++;
-    if (!isfinite(yprev)) c.nonfinite++;
+    /* intersection points whose chords must be (re)met: up to five indices packed one per byte */
+    unsigned long long todo = 0x0806040200ull; int nt = 5;
+    const double xprev = 0.0; double yprev = 0.0; bool have_prev = false;
     for (;;) {
-        /* ---- sample from the envelope (invert, arms.c:356-420) */
-        ArmsPt w;
-        {
-            int q = right;
-            const double u = rng.next(p, iter) * e[q].cum;
-            while (e[q].pl != A_NIL && e[e[q].pl].cum > u) q = e[q].pl;
-            const int l = e[q].pl;
-            w.pl = l; w.pr = q; w.f = 0; w.cum = u;
-            const double prop = (u - e[l].cum) / (e[q].cum - e[l].cum);
-            if (e[l].x == e[q].x) { w.x = e[q].x; w.y = e[q].y; w.ey = e[q].ey; }
-            else {
-                const double xa = e[l].x, xb = e[q].x, yl = e[l].y, yr = e[q].y, eyl = e[l].ey, eyr = e[q].ey;
-                if (fabs(yr - yl) < A_YEPS) {
+#pragma unroll 1
+        for (int t = 0; t < nt; t++) a_meet(e, (int)((todo >> (8 * t)) & 0xffull), convex);
+        const double ymax = a_cumulate(e);
+        if (!have_prev) { yprev = f(sm, n, xprev); c.evals++; if (!isfinite(yprev)) c.nonfinite++; have_prev = true; }
+        bool rebuilt = false;
+        while (!rebuilt) {
+            /* ---- sample from the envelope (invert, arms.c:356-420) */
+            double wx, wy, wey; int wpl, wpr;
+            {
+                int q = right;
+                const double u = rng.next(p, iter) * e.cum(q);
+#pragma unroll 1
+                while (e.pl(q) != A_NIL && e.cum(e.pl(q)) > u) q = e.pl(q);
+                const int l = e.pl(q);
+                wpl = l; wpr = q;
+                const double cuml = e.cum(l), cumq = e.cum(q);
+                const double prop = (u - cuml) / (cumq - cuml);
+                const double xa = e.x(l), xb = e.x(q), yl = e.y(l), yr = e.y(q);
+                const double eyl = a_expshift(yl, ymax), eyr = a_expshift(yr, ymax);
+                if (xa == xb) { wx = xb; wy = yr; wey = eyr; }
+                else if (fabs(yr - yl) < A_YEPS) {
                     if (fabs(eyr - eyl) > A_EYEPS * fabs(eyr + eyl))
-                        w.x = xa + ((xb - xa) / (eyr - eyl)) * (-eyl + PHT_SQRT((1. - prop) * eyl * eyl + prop * eyr * eyr));
-                    else w.x = xa + (xb - xa) * prop;
-                    w.ey = ((w.x - xa) / (xb - xa)) * (eyr - eyl) + eyl;
-                    w.y = a_logshift(w.ey, ymax);
+                        wx = xa + ((xb - xa) / (eyr - eyl)) * (-eyl + PHT_SQRT((1. - prop) * eyl * eyl + prop * eyr * eyr));
+                    else wx = xa + (xb - xa) * prop;
+                    wey = ((wx - xa) / (xb - xa)) * (eyr - eyl) + eyl;
+                    wy = a_logshift(wey, ymax);
                 } else {
-                    w.x = xa + ((xb - xa) / (yr - yl)) * (-yl + a_logshift(((1. - prop) * eyl + prop * eyr), ymax));
-                    w.y = ((w.x - xa) / (xb - xa)) * (yr - yl) + yl;
-                    w.ey = a_expshift(w.y, ymax);
+                    wx = xa + ((xb - xa) / (yr - yl)) * (-yl + a_logshift(((1. - prop) * eyl + prop * eyr), ymax));
+                    wy = ((wx - xa) / (xb - xa)) * (yr - yl) + yl;
+                    wey = a_expshift(wy, ymax);
                 }
             }
-        }
-        /* ---- rejection / Metropolis tests (arms.c:424-521) */
-        const double ystar = a_logshift(rng.next(p, iter) * w.ey, ymax);
-        const double ynew = f(sm, n, w.x); c.evals++;
-        if (!isfinite(ynew)) c.nonfinite++;
-        if (ystar >= ynew) {
-            /* reject; add the point to the envelope (update, arms.c:525-621) */
-            w.y = ynew; w.f = 1;
-            if (cpoint <= A_NPOINT - 2) {
-                const int q = cpoint, m = cpoint + 1;
-                bool linked = true;
-                e[q].x = w.x; e[q].y = w.y; e[q].f = 1; e[m].f = 0;
-                if (e[w.pl].f && !e[w.pr].f) {
-                    e[m].pl = w.pl; e[m].pr = q; e[q].pl = m; e[q].pr = w.pr;
-                    e[e[m].pl].pr = m; e[e[q].pr].pl = q;
-                } else if (!e[w.pl].f && e[w.pr].f) {
-                    e[m].pr = w.pr; e[m].pl = q; e[q].pr = m; e[q].pl = w.pl;
-                    e[e[m].pr].pl = m; e[e[q].pl].pr = q;
-                } else linked = false;
-                if (linked) {
-                    cpoint += 2;
-                    const int ql = (e[e[q].pl].pl != A_NIL) ? e[e[q].pl].pl : e[q].pl;
-                    const int qr = (e[e[q].pr].pr != A_NIL) ? e[e[q].pr].pr : e[q].pr;
-                    if (e[q].x < (1. - A_XEPS) * e[ql].x + A_XEPS * e[qr].x) {
-                        e[q].x = (1. - A_XEPS) * e[ql].x + A_XEPS * e[qr].x; e[q].y = f(sm, n, e[q].x); c.evals++;
-                    } else if (e[q].x > A_XEPS * e[ql].x + (1. - A_XEPS) * e[qr].x) {
-                        e[q].x = A_XEPS * e[ql].x + (1. - A_XEPS) * e[qr].x; e[q].y = f(sm, n, e[q].x); c.evals++;
+            /* ---- rejection / Metropolis tests (arms.c:424-521) */
+            const double ystar = a_logshift(rng.next(p, iter) * wey, ymax);
+            const double ynew = f(sm, n, wx); c.evals++;
+            if (!isfinite(ynew)) c.nonfinite++;
+            if (ystar >= ynew) {
+                /* reject; add the point to the envelope (update, arms.c:525-621) */
+                if (cpoint <= A_NPOINT - 2) {
+                    if (cpoint + 2 > (int)E::capacity) { overflow = true; return 0.0; }
+                    const int q = cpoint, m = cpoint + 1;
+                    bool linked = true;
+                    const int fl = e.f(wpl), fr = e.f(wpr);
+                    e.setx(q, wx); e.sety(q, ynew);
+                    if (fl && !fr) {
+                        e.setlk(m, E::pack(0, wpl, q)); e.setlk(q, E::pack(1, m, wpr));
+                        e.setpr(wpl, m); e.setpl(wpr, q);
+                    } else if (!fl && fr) {
+                        e.setlk(m, E::pack(0, q, wpr)); e.setlk(q, E::pack(1, wpl, m));
+                        e.setpl(wpr, m); e.setpr(wpl, q);
+                    } else linked = false;
+                    if (linked) {
+                        cpoint += 2;
+                        const int qpl = e.pl(q), qpr = e.pr(q);
+                        const int qpll = e.pl(qpl), qprr = e.pr(qpr);
+                        const int ql = (qpll != A_NIL) ? qpll : qpl;
+                        const int qr = (qprr != A_NIL) ? qprr : qpr;
+                        const double xql = e.x(ql), xqr = e.x(qr), xq = e.x(q);
+                        if (xq < (1. - A_XEPS) * xql + A_XEPS * xqr) {
+                            const double xv = (1. - A_XEPS) * xql + A_XEPS * xqr; e.setx(q, xv); e.sety(q, f(sm, n, xv)); c.evals++;
+                        } else if (xq > A_XEPS * xql + (1. - A_XEPS) * xqr) {
+                            const double xv = A_XEPS * xql + (1. - A_XEPS) * xqr; e.setx(q, xv); e.sety(q, f(sm, n, xv)); c.evals++;
+                        }
+                        /* re-intersect the chords around the new point: q.pl, q.pr, then the next intersections outwards */
+                        todo = (unsigned long long)qpl | ((unsigned long long)qpr << 8); nt = 2;
+                        if (qpll != A_NIL) { todo |= (unsigned long long)e.pl(qpll) << (8 * nt); nt++; }
+                        if (qprr != A_NIL) { todo |= (unsigned long long)e.pr(qprr) << (8 * nt); nt++; }
+                        c.updates++;
+                        rebuilt = true;                      /* back to cumulate */
                     }
-                    a_meet(e, e[q].pl, convex); a_meet(e, e[q].pr, convex);
-                    if (e[e[q].pl].pl != A_NIL) a_meet(e, e[e[e[q].pl].pl].pl, convex);
-                    if (e[e[q].pr].pr != A_NIL) a_meet(e, e[e[e[q].pr].pr].pr, convex);
-                    ymax = a_cumulate(e);
-                    c.updates++;
                 }
+                continue;
             }
-            continue;
+            /* Metropolis step against the previous iterate xprev (always 0 here) */
+            int ql = 0;
+#pragma unroll 1
+            while (e.x(e.pr(ql)) < xprev) ql = e.pr(ql);
+            const int qr = e.pr(ql);
+            double wgt = (xprev - e.x(ql)) / (e.x(qr) - e.x(ql));
+            double zold = e.y(ql) + wgt * (e.y(qr) - e.y(ql));
+            double znew = wy;
+            if (yprev < zold) zold = yprev;
+            if (ynew < znew) znew = ynew;
+            wgt = ynew - znew - yprev + zold;
+            if (wgt > 0.0) wgt = 0.0;
+            wgt = (wgt > -A_YCEIL) ? pht_exp(wgt) : 0.0;
+            if (rng.next(p, iter) > wgt) { c.rejects++; return xprev; }
+            return wx;
         }
-        /* Metropolis step against the previous iterate xprev (always 0 here) */
-        int ql = 0;
-        while (e[e[ql].pr].x < xprev) ql = e[ql].pr;
-        const int qr = e[ql].pr;
-        double wgt = (xprev - e[ql].x) / (e[qr].x - e[ql].x);
-        double zold = e[ql].y + wgt * (e[qr].y - e[ql].y);
-        double znew = w.y;
-        if (yprev < zold) zold = yprev;
-        if (ynew < znew) znew = ynew;
-        wgt = ynew - znew - yprev + zold;
-        if (wgt > 0.0) wgt = 0.0;
-        wgt = (wgt > -A_YCEIL) ? pht_exp(wgt) : 0.0;
-        if (rng.next(p, iter) > wgt) { c.rejects++; return xprev; }
-        return w.x;
     }
+}
+
+/* One ARMS draw over a 100-point envelope (the reference's capacity) in the lane's local memory */
+template <class Dens>
+__device__ __forceinline__ double arms_draw(const SweepParams &p, uint32_t iter, PathRng &rng, const EcsSmem &sm, int n, const Dens &f,
+                                            const double xinit[4], double xr, EcsCounters &c) {
+    double lx[A_NPOINT], ly[A_NPOINT], lc[A_NPOINT]; unsigned int ll[A_NPOINT];
+    EnvLocal e; e.ex = lx; e.ey = ly; e.ec = lc; e.el = ll;
+    bool overflow;
+    return arms_core(e, p, iter, rng, sm, n, f, xinit, xr, c, overflow);
 }
 
 __device__ __forceinline__ void ecs_load_model(const SweepParams &p, EcsSmem &sm, int n) {
