@@ -26,7 +26,7 @@
  *     the sequential scan because the running sums are non-decreasing).
  *   - Lane phase: persistent warps, one observation per lane, refilled from a global
  *     counter in warp-sized chunks (prefetched into shared memory) as lanes finish.
- *     Accepted attempts go to a per-warp ring in shared memory; when the ring holds four
+ *     Accepted attempts go to a per-warp ring in shared memory; when the ring holds two
  *     warps' worth, the whole warp replays them together, so the recording code runs
  *     converged instead of on one or two lanes at a time.  A lane gives up after `cap`
  *     attempts (attempt counts are geometric with a heavy tail) and appends
@@ -62,8 +62,8 @@ namespace cg = cooperative_groups;
 #ifndef END_CAP
 #define END_CAP 8u                   /* attempts a lane still tries once no observations are left */
 #endif
-#define RING 160                    /* per-warp ring of accepted attempts awaiting replay */
-#define RING_TRIGGER 128
+#define RING 96                     /* per-warp ring of accepted attempts awaiting replay */
+#define RING_TRIGGER 64
 #define TAIL_CH 256u                /* attempts per tail chunk (a pool never crosses a chunk) */
 #define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
 #define TAIL_KMAX (1u << 24)
@@ -151,7 +151,7 @@ __device__ __forceinline__ double log_unit(double x) { return pht_log_core(pht_d
  * and the state occupied at the end).  No control flow around the expensive parts (Philox, scan, log). */
 template <bool RECORD>
 __device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t obs_global, const SweepParams &p, const Smem &sm,
-                                          uint32_t iter, int n, Rec &rec, double *first_uniform = nullptr) {
+                                          uint32_t iter, int n, Rec &rec) {
     pht_u32x4 r = philox_block(w.b, w.a, obs_global, iter, p);
     w.b++;
     const double f = pht_u01(r.v[0], r.v[1]), g = pht_u01(r.v[2], r.v[3]);
@@ -159,7 +159,6 @@ __device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t
     const uint32_t hiA = w.odd ? w.spare_hi : r.v[1];
     const double uB = w.odd ? f : g;                     /* next exponential */
     w.spare = g; w.spare_hi = r.v[3];
-    if (first_uniform != nullptr) *first_uniform = f;    /* draw 0 of the block (the MH accept uniform of a waiting lane) */
     const bool fresh = w.fresh;
     const int row = fresh ? n : w.j;
     const int last = fresh ? n - 1 : n;
@@ -307,7 +306,6 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
     {
         Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
         bool active = false, cens = false, off = false, have_cur = false, cur_off = false;
-        bool await_u = false; int prop_pre = 0; bool prop_off = false;      /* a surviving proposal waiting for its accept uniform */
         double y = 0.0; uint32_t obs_local = 0, og = 0, tries = 0, cur_a = 0; int cur_pre = 0, kprop = 0;
         unsigned long long chunk_base = 0; unsigned chunk_next = 0, chunk_len = 0;      /* warp-uniform */
         bool exhausted = false, dry = false;      /* this warp found the stream empty / some warp did */
@@ -346,7 +344,6 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                     og = p.obs_rank + obs_local * p.obs_world;
                     y = sm.ybuf[warp * OBS_CHUNK + q]; cens = sm.cbuf[warp * OBS_CHUNK + q] != 0;
                     active = true; off = false; have_cur = false; kprop = 0; tries = 0; cur_a = 0; cur_off = false; cur_pre = 0;
-                    await_u = false;
                     walk_begin(w, 0u, false, og, p, iter);
                 }
                 const unsigned cnt = __popc(idle);
@@ -356,26 +353,8 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             if (idle == FULL) { if (exhausted) break; else continue; }
             __syncwarp();                   /* lanes that have just taken an observation step together with the rest */
             if (active) {
-                double u0;
-                const bool ended = walk_step<false>(w, y, cens, og, p, sm, iter, n, norec, &u0);
+                const bool ended = walk_step<false>(w, y, cens, og, p, sm, iter, n, norec);
                 c_jumps++;
-                if (await_u) {
-                    /* The step just computed block 0 of sub-stream a (= the surviving proposal's attempt + 1): its first
-                     * uniform is the MH accept draw (eq_Bladt_MHRS.c:79-82), its second is draw 1, where the next
-                     * proposal's first attempt continues.  (Taking the uniform from the converged step instead of a
-                     * Philox call of its own keeps that call off the single-lane event path.) */
-                    await_u = false;
-                    if (u0 < s_model[prop_pre] / s_model[cur_pre]) { cur_a = w.a - 1u; cur_off = prop_off; cur_pre = prop_pre; }
-                    kprop++;
-                    if (kprop >= p.mhit) {
-                        const unsigned e = warp * RING + atomicAdd(&sm.ring_n[warp], 1u);
-                        sm.ring_y[e] = y; sm.ring_obs[e] = obs_local; sm.ring_a[e] = cur_a;
-                        sm.ring_fl[e] = (unsigned char)((cens ? 1u : 0u) | (cur_off ? 2u : 0u));
-                        active = false;
-                    } else {
-                        off = true; w.fresh = true; w.b = 1; w.odd = true; w.t = 0.0; w.j = 0;      /* spare = draw 1 already */
-                    }
-                }
                 /* an ended attempt survives when it reached y in a state that can exit (eq_Bladt_MHRS.c:66,74) */
                 const bool ok = (w.t >= y) && ((smask >> w.j) & 1u);
                 const bool failed = ended && !ok;
@@ -404,9 +383,17 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                         if (cens || p.mhit == 0) accepted = true;                              /* :70 */
                         else { off = false; walk_begin(w, w.a + 1u, false, og, p, iter); }
                     } else {
-                        /* a valid proposal: its accept uniform is draw 0 of the next sub-stream; let the next step fetch it */
-                        await_u = true; prop_pre = w.j; prop_off = off;
-                        walk_begin(w, w.a + 1u, false, og, p, iter);
+                        /* a valid proposal: accept test with draw 0 of the next sub-stream (:79-82) */
+                        pht_u32x4 r = philox_block(0u, w.a + 1u, og, iter, p);
+                        const double U = pht_u01(r.v[0], r.v[1]);
+                        if (U < s_model[w.j] / s_model[cur_pre]) { cur_a = w.a; cur_off = off; cur_pre = w.j; }
+                        kprop++;
+                        if (kprop >= p.mhit) accepted = true;
+                        else {
+                            /* next proposal: sub-stream a+1 from draw 1 (the spare half of the block just computed) */
+                            off = true; w.a++; w.fresh = true; w.b = 1; w.odd = true; w.t = 0.0;
+                            w.spare = pht_u01(r.v[2], r.v[3]); w.spare_hi = r.v[3];
+                        }
                     }
                     if (accepted) {
                         const unsigned e = warp * RING + atomicAdd(&sm.ring_n[warp], 1u);
