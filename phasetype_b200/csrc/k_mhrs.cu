@@ -70,6 +70,9 @@ namespace cg = cooperative_groups;
 #ifndef TAIL_GROWTH
 #define TAIL_GROWTH 2u               /* attempts per pending observation grow by this factor per round */
 #endif
+#ifndef FOUND_PERIOD
+#define FOUND_PERIOD 8u               /* steps between looks at the pool observation's `found` word (power of two) */
+#endif
 #define POOL_MIN 32u
 #define POOL_MAX 2048u
 #define FOUND_NONE 0xFFFFFFFFFFFFFFFFull
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                 Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
                 bool active = false;
                 uint32_t my_item = 0, my_og = 0; double my_y = 0.0; bool my_cens = false;
+                unsigned steps = 0;
                 /* warp-uniform: the units this warp holds, and the pool being handed out */
                 unsigned long long u_next = 0, u_end = 0, last_base = 0;
                 bool out_of_units = false;
@@ -477,6 +481,22 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                         }
                     }
                     if (idle == FULL && pool_next >= pool_end) break;          /* nothing in flight, nothing left to hand out */
+                    /* Every FOUND_PERIOD steps, look whether some other warp has found a surviving attempt of the pool's
+                     * observation below this pool: the rest of the pool is then moot (when few observations are pending,
+                     * all warps of the GPU hold pools of the same ones, and without this look they would each finish
+                     * theirs: measured 2.1x the necessary jump-steps at 1e6 observations). */
+                    if (((++steps) & (FOUND_PERIOD - 1u)) == 0u && pool_next < pool_end) {
+                        unsigned long long f = 0;
+                        if (lane == 0) f = __ldcg(&p.found[item]);
+                        f = __shfl_sync(FULL, f, 0);
+                        const uint32_t fa = (uint32_t)(f >> 8);
+                        if (f != FOUND_NONE && fa < pool_end) {
+                            pool_end = pool_end < fa ? pool_end : fa;
+                            pool_next = pool_next < pool_end ? pool_next : pool_end;
+                            if (active && my_item == item && w.a > fa) active = false;
+                            idle = __ballot_sync(FULL, !active);
+                        }
+                    }
                     if (idle && pool_next < pool_end) {
                         /* idle lanes draw the next attempt indices of the pool (ballot only, no memory traffic) */
                         const uint32_t avail = pool_end - pool_next;
