@@ -234,6 +234,10 @@ class Runner:
         k = min(steps, 32)
         eng2.enqueue(k); eng2.sync()
         tot2, kern_ms = eng2.last_ms()
+        if os.environ.get("PHT_BENCH_VERBOSE"):
+            cc = eng2.counters()
+            sys.stderr.write("rank %d: path kernel %.3f ms/sweep (lane %.2f, tail %.2f ms), %d observations handed to the tail per sweep\n"
+                             % (self.rank, kern_ms, cc["ns_lane"] * 1e-6 / (warmup + k), cc["ns_tail"] * 1e-6 / (warmup + k), cc["deferred"] // (warmup + k)))
         kern_ms = self.reduce(kern_ms)
         eng2.close()
         nloc = max(1, y_loc.shape[0])
