@@ -111,3 +111,31 @@ def test_weak_scaling_shards_share_the_model():
     a = synth.config(3, "MHRS", l=500); b = synth.config(3, "MHRS", l=500, shard=1); c = synth.config(3, "MHRS", l=500, shard=1)
     assert np.array_equal(a.theta, b.theta) and np.array_equal(a.T, b.T)
     assert not np.array_equal(a.y, b.y) and np.array_equal(b.y, c.y)
+
+
+def test_product_path_never_touches_the_checker():
+    """oracle/ is test infrastructure: nothing under phasetype_b200/ or include/ may import, include or link it, and
+    bench.py may only reach it from the CPU-baseline / reference-arm legs."""
+    import ast
+    bad = []
+    for base in ("phasetype_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if os.path.basename(dirpath) in ("build", "__pycache__"):
+                continue
+            for f in files:
+                if not f.endswith((".py", ".c", ".h", ".cu", ".cuh")):
+                    continue
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r'#\s*include\s*["<][^">]*oracle|(from|import)\s+oracle|pyoracle|libphtoracle|libphtref|\bpho_[a-z_]+\s*\(', txt):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    allowed = {"_cpu_worker", "ref_kind", "main"}         # main: only inside the `cpu_baseline` block, checked below
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef):
+            for sub in ast.walk(node):
+                if isinstance(sub, ast.ImportFrom) and sub.module == "oracle":
+                    assert node.name in allowed, node.name
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    main_src = src[src.index("def main():"):]
+    assert main_src.count("from oracle import") == 1 and "if not args.no_cpu:" in main_src.split("from oracle import")[0][-400:]
