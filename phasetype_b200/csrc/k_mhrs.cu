@@ -64,7 +64,9 @@ namespace cg = cooperative_groups;
 #endif
 #define RING 96                     /* per-warp ring of accepted attempts awaiting replay */
 #define RING_TRIGGER 64
-#define TAIL_CH 256u                /* attempts per tail chunk (a pool never crosses a chunk) */
+#ifndef TAIL_CH
+#define TAIL_CH 128u                /* attempts per tail chunk (a pool never crosses a chunk) */
+#endif
 #define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
 #define TAIL_KMAX (1u << 24)
 #ifndef TAIL_GROWTH
@@ -74,7 +76,9 @@ namespace cg = cooperative_groups;
 #define FOUND_PERIOD 8u               /* steps between looks at the pool observation's `found` word (power of two) */
 #endif
 #define POOL_MIN 32u
-#define POOL_MAX 2048u
+#ifndef POOL_MAX
+#define POOL_MAX 256u
+#endif
 #define FOUND_NONE 0xFFFFFFFFFFFFFFFFull
 
 struct Smem {
