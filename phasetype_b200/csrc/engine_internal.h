@@ -68,6 +68,7 @@ struct DevState {
     uint32_t n_items;          /* items appended by the lane phase */
     uint32_t n_pend[2];        /* pending list sizes (double buffered) */
     uint32_t n_done;           /* finished items awaiting replay */
+    uint32_t any_fail;         /* MHRS tail: some pending observation found no surviving attempt in the current round */
     unsigned long long counters[PHT_CNT_COUNT];
 };
 

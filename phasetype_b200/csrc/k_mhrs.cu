@@ -67,7 +67,9 @@ namespace cg = cooperative_groups;
 #ifndef TAIL_CH
 #define TAIL_CH 128u                /* attempts per tail chunk (a pool never crosses a chunk) */
 #endif
-#define TAIL_K0 1024u               /* attempts per pending observation in tail round 0 */
+#ifndef TAIL_K0
+#define TAIL_K0 512u                /* attempts per pending observation in tail round 0 */
+#endif
 #define TAIL_KMAX (1u << 24)
 #ifndef TAIL_GROWTH
 #define TAIL_GROWTH 2u               /* attempts per pending observation grow by this factor per round */
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
         const unsigned long long gsize = (unsigned long long)gridDim.x * MHRS_THREADS;
         const unsigned long long nwarps = gsize / 32ull;
         for (unsigned long long i = gtid; i < n_items; i += gsize) p.pend0[i] = (uint32_t)i;
-        if (gtid == 0) { p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u; }
+        if (gtid == 0) { p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u; p.state->any_fail = 0u; }
         grid.sync();
         uint32_t K = TAIL_K0; int cur = 0; unsigned rounds = 0;
         for (;;) {
@@ -549,6 +551,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                 if (f == FOUND_NONE) {
                     if (it.a > 0xF0000000u - K) { atomicOr(&p.state->error, 8); dropped = true; }   /* survival probability ~ 0 */
                     it.a += K; it.flags &= ~4u;
+                    if (!dropped) atomicOr(&p.state->any_fail, 1u);
                 }
                 else {
                     const uint32_t a = (uint32_t)(f >> 8); const int pre = (int)(f & 0xffull);
@@ -578,8 +581,14 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
             }
             if (gtid == 0) { p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; }
             grid.sync();
+            /* the attempts per observation grow only when some observation needed more than this round offered: with
+             * mhit > 1 every pending observation comes back round after round for its next proposal, and a K that kept
+             * doubling would bury the round in pools to skip */
+            const bool grow = p.state->any_fail != 0u;
+            grid.sync();
+            if (gtid == 0) p.state->any_fail = 0u;
             cur ^= 1; rounds++;
-            K = (K < TAIL_KMAX) ? K * TAIL_GROWTH : K;
+            K = (grow && K < TAIL_KMAX) ? K * TAIL_GROWTH : K;
         }
         if (timekeeper) { const unsigned long long t = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_TAIL], t - t_mark); t_mark = t; }
         /* --- replay the accepted attempt of every tail observation */
