@@ -180,7 +180,7 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     void *bufs[] = { e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items, e->d_pend0, e->d_pend1, e->d_done, e->d_found, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -226,14 +226,12 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     CUE(cudaMalloc(&e->d_cens, ln));
     if (l_local > 0) {
         CUE(cudaMemcpyAsync(e->d_y, y_local, (size_t)l_local * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        uint8_t *hc = nullptr;
-        CUE(cudaMallocHost(&hc, (size_t)l_local));
+        /* (a pageable staging vector: pinning 10 MB per call cost more than the copy it would speed up) */
+        std::vector<uint8_t> hc((size_t)l_local);
         for (long i = 0; i < l_local; i++) hc[i] = cens_local[i] != 0;
-        if (method_of(e->cfg) == PHT_METHOD_ECS) e->h_cens.assign(hc, hc + l_local);
-        cudaError_t ce = cudaMemcpyAsync(e->d_cens, hc, (size_t)l_local, cudaMemcpyHostToDevice, e->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-        cudaFreeHost(hc);
-        CUE(ce);
+        CUE(cudaMemcpyAsync(e->d_cens, hc.data(), (size_t)l_local, cudaMemcpyHostToDevice, e->stream));
+        CUE(cudaStreamSynchronize(e->stream));
+        if (method_of(e->cfg) == PHT_METHOD_ECS) e->h_cens.swap(hc);
     }
 
     /* parameter -> cells CSR in the reference's insertion order (row-major walk of T, src/PHT_MCMC_Aslett.c:210-228) */
@@ -256,10 +254,20 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     CUE(cudaMalloc(&e->d_cell_j, sizeof(int) * cell_j.size())); CUE(cudaMemcpy(e->d_cell_j, cell_j.data(), sizeof(int) * cell_j.size(), cudaMemcpyHostToDevice));
 
     if (method_of(e->cfg) == PHT_METHOD_MHRS) {
-        e->item_cap = (uint32_t)ln;
-        CUE(cudaMalloc(&e->d_items, sizeof(TailItem) * ln)); CUE(cudaMalloc(&e->d_pend0, sizeof(uint32_t) * ln));
-        CUE(cudaMalloc(&e->d_pend1, sizeof(uint32_t) * ln)); CUE(cudaMalloc(&e->d_done, sizeof(uint32_t) * ln));
-        CUE(cudaMalloc(&e->d_found, sizeof(unsigned long long) * ln));
+        /* Tail work lists: one arena with room for a quarter of the shard (at least 2^20 observations, at most all of
+         * them).  In practice ~1 % of the observations plus one per resident lane are handed over; if the lists ever
+         * fill up, lanes simply keep their observation (k_mhrs.cu), so the size is a speed matter, not a limit. */
+        size_t slots = ln / 4 > ((size_t)1 << 20) ? ln / 4 : ((size_t)1 << 20);
+        if (slots > ln) slots = ln;
+        if (const char *ev = getenv("PHT_B200_TAIL_SLOTS")) { const long v = atol(ev); if (v >= 1 && (size_t)v < slots) slots = (size_t)v; }
+        e->item_cap = (uint32_t)slots;
+        unsigned char *arena = nullptr;
+        CUE(cudaMalloc(&arena, slots * (sizeof(TailItem) + sizeof(unsigned long long) + 3 * sizeof(uint32_t))));
+        e->d_items = reinterpret_cast<TailItem *>(arena); arena += slots * sizeof(TailItem);
+        e->d_found = reinterpret_cast<unsigned long long *>(arena); arena += slots * sizeof(unsigned long long);
+        e->d_pend0 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
+        e->d_pend1 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
+        e->d_done = reinterpret_cast<uint32_t *>(arena);
         e->grid_blocks = pht_mhrs_grid_blocks(cfg->device, n);
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }

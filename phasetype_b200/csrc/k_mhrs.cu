@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
     {
         Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
         bool active = false, cens = false, off = false, have_cur = false, cur_off = false;
+        bool keep = false;          /* the tail lists were full when this lane tried to hand its observation over */
         double y = 0.0; uint32_t obs_local = 0, og = 0, tries = 0, cur_a = 0; int cur_pre = 0, kprop = 0;
         unsigned long long chunk_base = 0; unsigned chunk_next = 0, chunk_len = 0;      /* warp-uniform */
         bool exhausted = false, dry = false;      /* this warp found the stream empty / some warp did */
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                     og = p.obs_rank + obs_local * p.obs_world;
                     y = sm.ybuf[warp * OBS_CHUNK + q]; cens = sm.cbuf[warp * OBS_CHUNK + q] != 0;
                     active = true; off = false; have_cur = false; kprop = 0; tries = 0; cur_a = 0; cur_off = false; cur_pre = 0;
+                    keep = false;
                     walk_begin(w, 0u, false, og, p, iter);
                 }
                 const unsigned cnt = __popc(idle);
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                 /* a failed attempt restarts on the next sub-stream right here, unless the lane is due to hand the
                  * observation over: after `cap` attempts, or after END_CAP once the observation stream has run dry
                  * (a lone lane grinding through attempts would hold the whole grid at the barrier) */
-                const bool handover = cap != 0u && (tries >= cap || ((exhausted || dry) && tries >= END_CAP));
+                const bool handover = cap != 0u && !keep && (tries >= cap || ((exhausted || dry) && tries >= END_CAP));
                 const bool restart = failed && !handover;
                 w.a += failed ? 1u : 0u;
                 off = failed ? false : off;
@@ -385,8 +387,11 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(Sw
                             TailItem it; it.obs_local = obs_local; it.a = w.a; it.cur_a = cur_a;
                             it.flags = pack_flags(have_cur, cur_off, false, cur_pre, kprop);
                             p.items[idx] = it; p.found[idx] = FOUND_NONE;
-                        } else atomicOr(&p.state->error, 4);
-                        c_deferred++; active = false;
+                            c_deferred++; active = false;
+                        } else {
+                            /* no room: the lane keeps the observation and goes on with its next attempt */
+                            keep = true; walk_begin(w, w.a, false, og, p, iter);
+                        }
                     } else if (!have_cur) {
                         have_cur = true; cur_a = w.a; cur_off = off; cur_pre = w.j;
                         if (cens || p.mhit == 0) accepted = true;                              /* :70 */

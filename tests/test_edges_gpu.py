@@ -121,3 +121,16 @@ def test_l2_flush_does_not_change_the_chain():
         out.append(eng.run(4))
         eng.close()
     assert np.array_equal(out[0], out[1])
+
+
+def test_full_tail_lists_only_cost_speed(monkeypatch):
+    """With room for 8 handed-over observations only, the lanes that find the lists full keep their observation and go
+    on by themselves: same paths, bit for bit."""
+    monkeypatch.setenv("PHT_B200_TAIL_SLOTS", "8")
+    rng = np.random.default_rng(5)
+    R, s = util.dense_rates(6, rng)
+    y = rng.exponential(1.5, 4000) + 0.01
+    cens = (rng.uniform(size=4000) < 0.2).astype(np.int32)
+    got, want = _paths("MHRS", R, s, y, cens, mhit=2, cap=4)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
