@@ -139,3 +139,21 @@ def test_product_path_never_touches_the_checker():
     src = open(os.path.join(ROOT, "bench.py")).read()
     main_src = src[src.index("def main():"):]
     assert main_src.count("from oracle import") == 1 and "if not args.no_cpu:" in main_src.split("from oracle import")[0][-400:]
+
+
+@pytest.mark.skipif(pb.lib().pht_device_count() > 0, reason="a GPU is present")
+def test_start_row_follows_the_reference_rule_without_a_device():
+    """Row 0 of res is produced by the host routine before any device work: prior mode (nu - 1) / zeta where nu > 1, a
+    prior draw from the keyed parameter stream otherwise (src/PHT_MCMC_Aslett.c:195-207) -- the same numbers as the
+    checker's driver; user-supplied start values are copied through."""
+    from oracle import pyoracle as po
+    os.environ["PHT_B200_SEED"] = "4242"; os.environ["PHT_B200_QUIET"] = "1"
+    T = [0, 2, 2, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0]; Cm = np.ones(16)
+    y = np.array([1.0, 2.0, 0.5]); cens = np.zeros(3, dtype=np.int32)
+    nu = [0.7, 180.0]; zeta = [16.0, 16.0]
+    res = pb.ljma_gibbs(3, 1, 2, 3, 2, nu, zeta, T, Cm, y, cens, [-1.0])
+    want, _ = po.gibbs(4242, 3, 1, 2, 3, nu, zeta, T, Cm, y, cens, [-1.0])
+    assert res[0, 1] == 179.0 / 16.0 and res[0, 0] > 0
+    assert np.array_equal(res[0], want[0])
+    res = pb.ljma_gibbs(3, 1, 2, 3, 2, nu, zeta, T, Cm, y, cens, [0.25, 7.5])
+    assert np.array_equal(res[0], [0.25, 7.5]) and (res[1:] == 0).all()
