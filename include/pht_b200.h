@@ -28,9 +28,11 @@ extern "C" {
  * column-major) is fully overwritten; row 0 is the start value.  Diagnostics go
  * through Rprintf; nothing is signalled (void), as in the reference.
  * Engine knobs that have no slot in the 15 arguments come from the environment:
- *   PHT_B200_SEED   (decimal/hex uint64; default: drawn from unif_rand())
- *   PHT_B200_DEVICE (CUDA ordinal, default 0)
- *   PHT_B200_GPUS   (single-process multi-GPU count, default 1)                */
+ *   PHT_B200_SEED     (decimal/hex uint64; default: drawn from unif_rand())
+ *   PHT_B200_DEVICE   (CUDA ordinal, default 0)
+ *   PHT_B200_GRAPH    (0: launch the sweep's kernels directly instead of replaying a CUDA graph)
+ *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail, default 256)
+ * (multi-GPU runs are one process per GPU on the layer-2 API: pht_engine_create with rank/world + pht_engine_comm_init) */
 void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, double *zeta,
                 int *T, double *C, double *y, int *l, int *censored, double *start,
                 int *silent, double *res);
