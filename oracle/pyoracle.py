@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "libphtoracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libphtref.so")
+REF_LIBM_SO = os.path.join(HERE, "_ref", "libphtref_libm.so")
 REFERENCE_ROOT = "/root/reference"
 
 N_COUNTERS = 16
@@ -34,6 +35,7 @@ def build(target="all"):
     targets = ["oracle"]
     if target in ("all", "ref") and os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
         targets.append("ref")
+        targets.append("ref-libm")
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
 
 
@@ -67,6 +69,7 @@ class _Lib:
 
 _oracle = None
 _ref = None
+_ref_libm = None
 
 
 def oracle():
@@ -117,10 +120,25 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
-def ref():
-    global _ref
+def have_ref_libm():
+    return os.path.exists(REF_LIBM_SO)
+
+
+def ref(libm=False):
+    """libm=True: the reference built with the platform's exp/log and OpenBLAS (`make ref-libm`)."""
+    global _ref, _ref_libm
+    if libm:
+        if _ref_libm is None:
+            _ref_libm = _load_ref(REF_LIBM_SO)
+        return _ref_libm
     if _ref is None:
-        r = _Lib(REF_SO)
+        _ref = _load_ref(REF_SO)
+    return _ref
+
+
+def _load_ref(path):
+    if True:
+        r = _Lib(path)
         L = r.lib
         L.phtref_mhrs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
                                         _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _up]
@@ -132,8 +150,7 @@ def ref():
         L.phtref_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
         L.phtref_gibbs.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                    _ip, _dp, _dp, C.c_int, _ip, _dp, _dp]
-        _ref = r
-    return _ref
+    return r
 
 
 def _out(count, n, want):
@@ -164,7 +181,7 @@ def mhrs_paths(impl, seed, it, y, cens, S, s, mhit=1, obs0=0, stride=1, want=Tru
         rc = oracle().pho_mhrs_paths(seed, it, obs0, stride, count, y, cens, n, S, s, Pfull, mhit, B, N, z, cnt)
         counters = _counters(cnt)
     else:
-        rc = ref().phtref_mhrs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), Pfull, mhit,
+        rc = ref(impl == "ref_libm").phtref_mhrs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), Pfull, mhit,
                                      _ptr(B), _ptr(N), _ptr(z), cnt)
         counters = {"paths": count, "attempts": int(cnt[1]), "jumps": int(cnt[4]), "uniforms": int(cnt[0])}
     if rc != 0:
@@ -210,7 +227,7 @@ def spectral_paths(impl, method, seed, it, y, cens, S, s, obs0=0, stride=1, want
         if impl == "oracle":
             rc = oracle().pho_dcs_paths(seed, it, obs0, stride, count, y, n, S, s, ev, Q, Qi, B, N, z, cnt)
         else:
-            rc = ref().phtref_dcs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), ev.copy(), Q.copy(),
+            rc = ref(impl == "ref_libm").phtref_dcs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), ev.copy(), Q.copy(),
                                         Qi.copy(), _ptr(B), _ptr(N), _ptr(z), cnt)
     elif method == "ECS":
         Qm = Qi.reshape(n, n, order="F")
@@ -223,7 +240,7 @@ def spectral_paths(impl, method, seed, it, y, cens, S, s, obs0=0, stride=1, want
             rc = oracle().pho_ecs_paths(seed, it, obs0, stride, count, y, cens, n, S, s, P, Pfull, ev, Q, Qinv_s, Qinv_1,
                                         B, N, z, cnt)
         else:
-            rc = ref().phtref_ecs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), P.copy(), Pfull.copy(),
+            rc = ref(impl == "ref_libm").phtref_ecs_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), P.copy(), Pfull.copy(),
                                         ev.copy(), Q.copy(), Qinv_s, Qinv_1, _ptr(B), _ptr(N), _ptr(z), cnt)
     else:
         raise ValueError(method)

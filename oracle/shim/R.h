@@ -19,10 +19,12 @@
 #endif
 #define R_INLINE inline
 
+#ifndef PHT_SHIM_LIBM          /* `make ref-libm` keeps the platform's exp/log (mismatch-rate report only) */
 double phtshim_exp(double);
 double phtshim_log(double);
 #define exp phtshim_exp
 #define log phtshim_log
+#endif
 
 void Rprintf(const char *, ...);
 void REprintf(const char *, ...);

@@ -26,8 +26,15 @@
 #include "../../phasetype_b200/csrc/pht_philox.h"
 
 /* ---------------------------------------------------------------- math */
+#ifdef PHT_SHIM_LIBM
+#define SHIM_EXP(x) exp(x)
+#define SHIM_LOG(x) log(x)
+#else
 double phtshim_exp(double x) { return pht_exp(x); }
 double phtshim_log(double x) { return pht_log(x); }
+#define SHIM_EXP(x) pht_exp(x)
+#define SHIM_LOG(x) pht_log(x)
+#endif
 
 /* ---------------------------------------------------------------- RNG state */
 enum { MODE_SEQ = 0, MODE_KEYED = 1, MODE_GIBBS = 2 };
@@ -81,7 +88,7 @@ void R_FlushConsole(void) {
 }
 
 double unif_rand(void) { G.n_unif++; return pht_stream_unif(&G.st); }
-double exp_rand(void) { return -pht_log(unif_rand()); }
+double exp_rand(void) { return -SHIM_LOG(unif_rand()); }
 double norm_rand(void) { return pht_norm_polar(&G.st); }
 
 double runif(double a, double b) {
@@ -95,7 +102,7 @@ double rexp(double scale) {
 double dexp(double x, double scale, int give_log) {
     if (scale <= 0.0) return NAN;
     if (x < 0.0) return give_log ? -INFINITY : 0.0;
-    return give_log ? (-x / scale) - pht_log(scale) : pht_exp(-x / scale) / scale;
+    return give_log ? (-x / scale) - SHIM_LOG(scale) : SHIM_EXP(-x / scale) / scale;
 }
 double rgamma(double shape, double scale) {
     G.n_gamma++;
@@ -144,6 +151,22 @@ void phtshim_release(void) {
 }
 
 /* ---------------------------------------------------------------- BLAS (reference order) */
+#ifdef PHT_SHIM_LIBM
+extern void scipy_dgemv_(const char *, const int *, const int *, const double *, const double *, const int *, const double *,
+                         const int *, const double *, double *, const int *, size_t);
+extern void scipy_dgemm_(const char *, const char *, const int *, const int *, const int *, const double *, const double *,
+                         const int *, const double *, const int *, const double *, double *, const int *, size_t, size_t);
+void phtshim_dgemv(const char *trans, const int *m, const int *n, const double *alpha,
+                   const double *a, const int *lda, const double *x, const int *incx,
+                   const double *beta, double *y, const int *incy) {
+    scipy_dgemv_(trans, m, n, alpha, a, lda, x, incx, beta, y, incy, 1);
+}
+void phtshim_dgemm(const char *transa, const char *transb, const int *m, const int *n, const int *k,
+                   const double *alpha, const double *a, const int *lda, const double *b, const int *ldb,
+                   const double *beta, double *c, const int *ldc) {
+    scipy_dgemm_(transa, transb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, 1, 1);
+}
+#else
 void phtshim_dgemv(const char *trans, const int *m, const int *n, const double *alpha,
                    const double *a, const int *lda, const double *x, const int *incx,
                    const double *beta, double *y, const int *incy) {
@@ -176,6 +199,8 @@ void phtshim_dgemm(const char *transa, const char *transb, const int *m, const i
         }
     }
 }
+
+#endif
 
 /* ---------------------------------------------------------------- LAPACK forwards */
 extern void scipy_dgeevx_(const char *, const char *, const char *, const char *, const int *, double *, const int *,

@@ -80,3 +80,28 @@ def test_sweep_stats_equal_sum_of_paths():
     zf = np.rint(z * 2.0 ** eng.zbits).astype(np.int64).sum(0)
     assert np.array_equal(zfix, zf)
     eng.close()
+
+
+@pytest.mark.parametrize("cid,l,mhit", [(2, 10 ** 6, 1), (3, 10 ** 6, 1)])
+def test_deep_tail_sweep_equals_oracle(cid, l, mhit):
+    """The machinery the small cases never reach: default hand-over cap, a million observations, a dozen or more
+    cooperative tail rounds with attempts per observation growing to 2^20 and beyond (pool clipping by `found`,
+    chunk-major unit numbering, the growth rule).  The packed int64 statistics of the sweep (N | B | z fixed
+    point) must equal the CPU restatement's, which walks every observation sequentially."""
+    import phasetype_b200 as pb
+    from phasetype_b200 import synth
+    wl = synth.config(cid, "MHRS", l=l)
+    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=1, mhit=mhit, seed=0xD33B7A11)
+    eng.set_theta(wl.theta, next_iter=4)
+    c0 = eng.counters()
+    N, B, z = eng.sweep_stats()
+    c1 = eng.counters()
+    zbits = eng.zbits
+    eng.close()
+    No, Bo, zo, co = util.oracle_sweep_stats_all_cores(0xD33B7A11, 4, True, mhit, 1, wl.n, wl.T, wl.C, wl.theta, wl.y,
+                                                       wl.censored, zbits)
+    assert np.array_equal(N, No)
+    assert np.array_equal(B, Bo)
+    assert np.array_equal(z, zo)
+    assert c1["tail_rounds"] - c0["tail_rounds"] >= 10
+    assert c1["paths"] - c0["paths"] == l

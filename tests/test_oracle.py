@@ -188,3 +188,57 @@ def test_sharded_statistics_sum_to_the_whole():
     parts = [po.sweep_stats(9, 1, True, 1, 1, wl.n, wl.T, wl.C, wl.theta, wl.y, wl.censored, rank=r, world=4, zbits=zb) for r in range(4)]
     for k in range(3):
         assert np.array_equal(whole[k], sum(p[k] for p in parts))
+
+
+@pytest.mark.skipif(not po.have_ref_libm(), reason="oracle/_ref/libphtref_libm.so (make ref-libm) not present")
+def test_libm_mismatch_rate_is_reported():
+    """tier 1 is decided against the reference built with the engine's exp/log, plain-loop BLAS and
+    -ffp-contract=off (`make ref`).  This test REPORTS what those three substitutions hide: the same reference sources
+    with the platform's libm, OpenBLAS dgemv/dgemm and R's default -O2 (`make ref-libm`), run on the golden inputs
+    and on a larger sample per method.  Where B and N agree the z totals must agree to 1e-12 relative for MHRS (north_star's
+    tolerance; for the equation-solving samplers the figure is reported per component and bounded at 1e-12 of the path length); the rate at which an integer statistic differs (a flipped comparison somewhere on the path) is
+    written to profiles/r2_libm_mismatch.json, not asserted to be zero."""
+    import json
+    report = {}
+    worst_z = 0.0; worst_path = 0.0
+    cases = [(os.path.basename(p)[:-4], np.load(p)) for p in GOLDEN]
+    rng = np.random.default_rng(2026)
+    for method, n, kind, fc, l in (("MHRS", 8, "dense", 0.2, 20000), ("ECS", 8, "sym", 0.2, 4000), ("DCS", 8, "sym", 0.0, 4000)):
+        R, s = util.dense_rates(n, rng, symmetric=(kind == "sym"))
+        S = _S(R, s)
+        g = dict(method=method, seed=77, it=2, mhit=1, y=rng.exponential(1.2, l) + 0.01, S=S, s=s)
+        g["cens"] = (rng.uniform(size=l) < fc).astype(np.int32)
+        if method != "MHRS":
+            g["evals"], g["Q"], g["Qinv"] = po.eigen("ref", S, n)
+        cases.append(("%s_n%d_l%d" % (method.lower(), n, l), g))
+    for name, g in cases:
+        B0, N0, z0, _ = golden_run("ref", g)
+        B1, N1, z1, _ = golden_run("ref_libm", g)
+        same = (B0 == B1) & (N0 == N1).all(1)
+        rel = np.abs(z1[same] - z0[same]) / np.maximum(np.abs(z0[same]), 1e-300)
+        rel = rel[z0[same] != 0.0]
+        mz = float(rel.max()) if rel.size else 0.0
+        # the same differences against the length of the path they belong to (a sojourn drawn by ARMS or Brent is
+        # the solution of an equation in exp/log values: its own relative error is the solver's conditioning times
+        # the libm difference, and a short sojourn shows it largest)
+        tot = np.abs(z0[same]).sum(1, keepdims=True)
+        mp_ = float((np.abs(z1[same] - z0[same]) / np.maximum(tot, 1e-300)).max()) if same.any() else 0.0
+        if str(g["method"]) == "MHRS":
+            worst_z = max(worst_z, mz)
+        worst_path = max(worst_path, mp_)
+        report[name] = {"paths": int(B0.shape[0]), "paths_with_different_B_or_N": int((~same).sum()),
+                        "mismatch_rate": float((~same).mean()), "max_rel_z_error_where_B_N_agree": mz,
+                        "max_z_error_relative_to_path_length": mp_}
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "profiles", "r2_libm_mismatch.json")
+    try:
+        with open(out, "w") as f:
+            json.dump({"what": "reference C built with platform libm + OpenBLAS + default -O2 (make ref-libm) versus the tier-1 "
+                               "checker build (make ref: pht_math.h exp/log, plain-loop BLAS, -ffp-contract=off), same Philox uniforms",
+                       "cases": report}, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    print(json.dumps(report, indent=1))
+    # MHRS sojourns are sums of scale * (-log u): 1e-12 holds per component.  ECS / DCS sojourns are roots of equations
+    # in exp/log values (ARMS inversion, Brent): per component they agree to ~1e-10, and to 1e-12 of the path length.
+    assert worst_z <= 1e-12
+    assert worst_path <= 1e-12

@@ -72,3 +72,24 @@ def assemble(T, C, theta, n, first=True):
     S = TT[:n, :n].ravel(order="F").copy()
     s = TT[:n, n].copy()
     return S, s
+
+
+def _oracle_shard_stats(args):
+    from oracle import pyoracle as po
+    seed, it, first, mhit, method, n, T, C, theta, y, cens, rank, world, zbits = args
+    N, B, z, cnt = po.sweep_stats(seed, it, first, mhit, method, n, T, C, theta, y, cens, rank=rank, world=world, zbits=zbits)
+    return N, B, z, cnt
+
+
+def oracle_sweep_stats_all_cores(seed, it, first, mhit, method, n, T, C, theta, y, cens, zbits):
+    """One sweep's packed statistics from the CPU restatement, the observations split over every host core
+    (int64 sums: the split cannot change the totals)."""
+    import multiprocessing as mp
+    import os
+    w = max(1, os.cpu_count() or 1)
+    jobs = [(seed, it, first, mhit, method, n, T, C, theta, y, cens, r, w, zbits) for r in range(w)]
+    with mp.get_context("fork").Pool(w) as pool:
+        out = pool.map(_oracle_shard_stats, jobs)
+    N = sum(o[0] for o in out); B = sum(o[1] for o in out); z = sum(o[2] for o in out)
+    cnt = {k: sum(o[3][k] for o in out) for k in out[0][3]}
+    return N, B, z, cnt
