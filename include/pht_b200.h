@@ -80,6 +80,16 @@ void pht_engine_destroy(pht_engine *e);
 int pht_comm_unique_id(void *id128);
 int pht_engine_comm_init(pht_engine *e, const void *id128);
 
+/* MHRS, several GPUs of one box: the deepest part of the rejection tail (observations that need 10^5..10^8
+ * attempts) is searched by all ranks together through peer memory (NVLink): each engine owns an exchange window,
+ * pht_engine_peer_handle writes an opaque PHT_PEER_HANDLE_BYTES handle for it, the launcher gathers the handles of
+ * all ranks (rank order) and every rank calls pht_engine_peer_attach with the concatenation.  Works between
+ * processes (CUDA IPC) and between engines of one process (direct peer access).  Optional: without it the tail
+ * rounds stay local to each rank and the chain is the same, only slower to finish. */
+#define PHT_PEER_HANDLE_BYTES 128
+int pht_engine_peer_handle(pht_engine *e, void *handle);
+int pht_engine_peer_attach(pht_engine *e, const void *handles);
+
 /* parameter vector (length m) the next sweep starts from, and the index that sweep gets */
 int pht_engine_set_theta(pht_engine *e, const double *theta, uint32_t next_iter);
 int pht_engine_get_theta(pht_engine *e, double *theta);
@@ -113,7 +123,8 @@ enum { PHT_CNT_PATHS = 0, PHT_CNT_ATTEMPTS, PHT_CNT_JUMPS, PHT_CNT_DENS_EVALS, P
        PHT_CNT_BRENT_EVALS, PHT_CNT_ARMS_CALLS, PHT_CNT_METROP_REJECTS, PHT_CNT_NONFINITE,
        PHT_CNT_DEFERRED, PHT_CNT_TAIL_ROUNDS, PHT_CNT_ERRORS, PHT_CNT_LAUNCHES,
        PHT_CNT_NS_LANE, PHT_CNT_NS_TAIL, PHT_CNT_NS_REPLAY,   /* device-timer ns spent in the MHRS kernel phases */
-       PHT_CNT_COUNT = 16 };
+       PHT_CNT_NS_GLOBAL,                                      /* ... and in the tail rounds searched by all GPUs together */
+       PHT_CNT_COUNT = 20 };
 int pht_engine_counters(pht_engine *e, unsigned long long *out);
 
 /* measurement helpers ------------------------------------------------------- */

@@ -18,11 +18,13 @@ SYMBOLS = [
     "pht_engine_destroy", "pht_comm_unique_id", "pht_engine_comm_init", "pht_engine_set_theta",
     "pht_engine_get_theta", "pht_engine_run", "pht_engine_enqueue", "pht_engine_sync", "pht_engine_last_ms",
     "pht_engine_sweep_stats", "pht_engine_paths", "pht_engine_set_spectral", "pht_engine_get_model",
-    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush",
+    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush", "pht_engine_peer_handle", "pht_engine_peer_attach",
 ]
+PEER_HANDLE_BYTES = 128
 CNT_NAMES = ["paths", "attempts", "jumps", "dens_evals", "env_updates", "brent_evals", "arms_calls",
-             "metrop_rejects", "nonfinite", "deferred", "tail_rounds", "errors", "launches", "ns_lane", "ns_tail", "ns_replay"]
-N_CNT = 16
+             "metrop_rejects", "nonfinite", "deferred", "tail_rounds", "errors", "launches", "ns_lane", "ns_tail", "ns_replay",
+             "ns_global", "reserved17", "reserved18", "reserved19"]
+N_CNT = 20
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -70,6 +72,8 @@ def lib():
     L.pht_engine_counters.argtypes = [C.c_void_p, _up]
     L.pht_fp64_fma_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.pht_engine_set_l2_flush.argtypes = [C.c_void_p, C.c_ulonglong]
+    L.pht_engine_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.pht_engine_peer_attach.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -122,6 +126,17 @@ class Engine:
     def comm_init(self, id128):
         buf = (C.c_char * 128).from_buffer_copy(bytes(id128))
         _check(lib().pht_engine_comm_init(self._h, buf))
+
+    def peer_handle(self):
+        buf = (C.c_char * PEER_HANDLE_BYTES)()
+        _check(lib().pht_engine_peer_handle(self._h, buf))
+        return bytes(buf.raw)
+
+    def peer_attach(self, handles):
+        """handles: the peer_handle() bytes of every rank, concatenated in rank order."""
+        raw = bytes(handles)
+        buf = (C.c_char * len(raw)).from_buffer_copy(raw)
+        _check(lib().pht_engine_peer_attach(self._h, buf))
 
     def set_theta(self, theta, next_iter=1):
         _check(lib().pht_engine_set_theta(self._h, np.ascontiguousarray(theta, dtype=np.float64), int(next_iter)))

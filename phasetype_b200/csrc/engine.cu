@@ -15,6 +15,7 @@
 #include <cmath>
 #include <vector>
 #include <dlfcn.h>
+#include <unistd.h>
 #include "engine_internal.h"
 
 /* ---------------------------------------------------------------- errors */
@@ -62,6 +63,10 @@ struct pht_engine {
     cudaStream_t stream = nullptr;
     /* device buffers */
     double *d_y = nullptr; uint8_t *d_cens = nullptr;
+    double *d_ys = nullptr; uint8_t *d_cs = nullptr; uint32_t *d_perm = nullptr;   /* MHRS: the same observations by decreasing y */
+    uint32_t *d_glist = nullptr; XchgWindow *d_xw = nullptr;                        /* MHRS global tail */
+    XchgWindow *xpeer[PHT_MAX_WORLD] = {}; std::vector<void *> ipc_opened; bool peers_attached = false;
+    uint32_t k_switch = 1u << 15;
     double *d_model = nullptr; long long *d_stats = nullptr; DevState *d_state = nullptr;
     int *d_T = nullptr; double *d_C = nullptr, *d_nu = nullptr, *d_zeta = nullptr;
     int *d_var_ptr = nullptr, *d_cell_i = nullptr, *d_cell_j = nullptr;
@@ -73,7 +78,7 @@ struct pht_engine {
     double *d_inject = nullptr;        /* host-supplied evals | Q | Qinv (parity hook), else nullptr */
     void *d_flush = nullptr; size_t flush_bytes = 0;   /* L2 flush scratch (measurement aid) */
     ModelLayout L;
-    int grid_blocks = 0;
+    int grid_blocks = 0, tail_blocks = 0;
     /* graph */
     cudaGraphExec_t graph_exec = nullptr; int graph_res_rows = -1; double *graph_res = nullptr;
     unsigned long long graph_launches = 0;      /* kernels one replay of the captured sweep launches */
@@ -109,6 +114,9 @@ static SweepParams sweep_params(pht_engine *e) {
     pht_roundkeys_init(&p.rk, p.k0, p.k1);
     p.items = e->d_items; p.pend0 = e->d_pend0; p.pend1 = e->d_pend1; p.done = e->d_done; p.found = e->d_found;
     p.item_cap = e->item_cap; p.mhrs_cap = e->cfg.mhrs_cap;
+    if (e->d_ys) { p.y = e->d_ys; p.cens = e->d_cs; p.perm = e->d_perm; }      /* production layout: decreasing y */
+    p.glist = e->d_glist; p.k_switch = e->k_switch;
+    if (e->peers_attached) { p.xw = e->d_xw; for (int r = 0; r < e->cfg.world && r < PHT_MAX_WORLD; r++) p.xpeer[r] = e->xpeer[r]; }
     return p;
 }
 static UpdateParams update_params(pht_engine *e, double *res, int res_rows) {
@@ -137,7 +145,7 @@ static int enqueue_paths(pht_engine *e, const SweepParams &p, const uint32_t *id
         else CU(pht_launch_ecs(p, e->grid_blocks, e->d_idx_exact, e->n_exact, e->d_idx_cens, e->n_cens, e->stream));
         e->launches += (lists_given ? (n_exact != 0) + (n_cens != 0) : (e->n_exact != 0) + (e->n_cens != 0)) - 1;
         break;
-    case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->stream)); break;
+    case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->tail_blocks, e->stream)); e->launches++; break;
     case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); break;
     default: return fail("sampling method %d has no kernel in this build", e->cfg.method);
     }
@@ -162,6 +170,7 @@ static int enqueue_sweep(pht_engine *e, double *res, int res_rows, bool time_ker
     if (enqueue_paths(e, p)) return -1;
     if (time_kernel && (e->kev_used & 1)) CU(cudaEventRecord(e->kev[e->kev_used++], e->stream));
     if (e->comm) {
+        CU(pht_launch_pack_error(u, e->stream)); e->launches++;
         int rc = g_nccl.AllReduce(e->d_stats, e->d_stats, (size_t)stats_len(e->cfg.n), NCCL_INT64, NCCL_SUM, e->comm, e->stream);
         if (rc != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
@@ -179,7 +188,8 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
-    void *bufs[] = { e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
+    for (void *q : e->ipc_opened) cudaIpcCloseMemHandle(q);
+    void *bufs[] = { e->d_ys, e->d_cs, e->d_perm, e->d_glist, e->d_xw, e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
                      e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -200,6 +210,9 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     if (l_local < 0 || l_local > 0x7fffffffL) return fail("l_local out of range");
     if ((double)l_local * cfg->world > 4.0e9) return fail("global observation index exceeds 32 bits");
     for (int i = 0; i < n1 * n1; i++) if (cfg->T[i] < 0 || cfg->T[i] > m) return fail("T[%d] = %d outside 0..m", i, cfg->T[i]);
+    /* the absorbing state has no exits: a parameter in row n would make the update read beyond N and z */
+    for (int j = 0; j < n1; j++) if (cfg->T[n + j * n1] != 0) return fail("T[%d, %d] = %d: row n+1 (the absorbing state) must be all zero", n, j, cfg->T[n + j * n1]);
+    if (cfg->world > PHT_MAX_WORLD) return fail("world = %d exceeds %d", cfg->world, PHT_MAX_WORLD);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device available (this library has no CPU path)"); }
@@ -242,9 +255,9 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     { std::vector<int> fill(var_ptr.begin(), var_ptr.end() - 1);
       for (int i = 0; i < n1; i++) for (int j = 0; j < n1; j++) { int v = e->T[i + j * n1]; if (v) { int c = fill[v - 1]++; cell_i[c] = i; cell_j[c] = j; } } }
 
-    CUE(cudaMalloc(&e->d_model, sizeof(double) * e->L.total)); CUE(cudaMemset(e->d_model, 0, sizeof(double) * e->L.total));
-    CUE(cudaMalloc(&e->d_stats, sizeof(long long) * stats_len(n))); CUE(cudaMemset(e->d_stats, 0, sizeof(long long) * stats_len(n)));
-    CUE(cudaMalloc(&e->d_state, sizeof(DevState))); CUE(cudaMemset(e->d_state, 0, sizeof(DevState)));
+    CUE(cudaMalloc(&e->d_model, sizeof(double) * e->L.total)); CUE(cudaMemsetAsync(e->d_model, 0, sizeof(double) * e->L.total, e->stream));
+    CUE(cudaMalloc(&e->d_stats, sizeof(long long) * stats_len(n))); CUE(cudaMemsetAsync(e->d_stats, 0, sizeof(long long) * stats_len(n), e->stream));
+    CUE(cudaMalloc(&e->d_state, sizeof(DevState))); CUE(cudaMemsetAsync(e->d_state, 0, sizeof(DevState), e->stream));
     CUE(cudaMalloc(&e->d_T, sizeof(int) * n1 * n1)); CUE(cudaMemcpy(e->d_T, e->T.data(), sizeof(int) * n1 * n1, cudaMemcpyHostToDevice));
     CUE(cudaMalloc(&e->d_C, sizeof(double) * n1 * n1)); CUE(cudaMemcpy(e->d_C, e->C.data(), sizeof(double) * n1 * n1, cudaMemcpyHostToDevice));
     CUE(cudaMalloc(&e->d_nu, sizeof(double) * m)); CUE(cudaMemcpy(e->d_nu, e->nu.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
@@ -268,7 +281,21 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         e->d_pend0 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
         e->d_pend1 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
         e->d_done = reinterpret_cast<uint32_t *>(arena);
-        e->grid_blocks = pht_mhrs_grid_blocks(cfg->device, n);
+        /* the production layout: observations by decreasing y (k_sort.cu); parity hooks keep using the upload order */
+        if (l_local > 1 && !getenv("PHT_B200_NO_SORT")) {
+            CUE(cudaMalloc(&e->d_ys, ln * sizeof(double))); CUE(cudaMalloc(&e->d_cs, ln)); CUE(cudaMalloc(&e->d_perm, ln * sizeof(uint32_t)));
+            CUE(pht_sort_by_y_desc(e->d_y, e->d_cens, l_local, e->d_ys, e->d_cs, e->d_perm, e->stream));
+        }
+        /* global tail: the canonical list and this rank's exchange window (flags 0, found words NONE) */
+        if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
+        if (cfg->world > 1) {
+            CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * PHT_MAX_WORLD * PHT_GCAP));
+            CUE(cudaMalloc(&e->d_xw, sizeof(XchgWindow)));
+            CUE(cudaMemsetAsync(e->d_xw, 0, sizeof(XchgWindow), e->stream));
+            CUE(cudaMemsetAsync(e->d_xw->gfound, 0xFF, sizeof(e->d_xw->gfound), e->stream));
+            CUE(cudaStreamSynchronize(e->stream));
+        }
+        if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks) != 0) e->grid_blocks = 0;
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
     if (method_of(e->cfg) == PHT_METHOD_ECS) {
@@ -287,7 +314,8 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     }
     /* sweep index 1, start-value assembly (src/PHT_MCMC_Aslett.c:268) */
     DevState st; memset(&st, 0, sizeof(st)); st.iter = 1; st.first_assembly = 1;
-    CUE(cudaMemcpy(e->d_state, &st, sizeof(st), cudaMemcpyHostToDevice));
+    CUE(cudaMemcpyAsync(e->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
+    CUE(cudaStreamSynchronize(e->stream));
 #undef CUE
     *out = e;
     return 0;
@@ -313,6 +341,53 @@ extern "C" int pht_engine_comm_init(pht_engine *e, const void *id128) {
     rc = g_nccl.AllReduce(e->d_stats, e->d_stats, (size_t)stats_len(e->cfg.n), NCCL_INT64, NCCL_SUM, e->comm, e->stream);
     if (rc != 0) return fail("ncclAllReduce (warm-up) failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+/* ---------------------------------------------------------------- peer exchange windows (MHRS global tail) */
+struct PeerHandle { unsigned long long pid; unsigned long long ptr; int device; int valid; cudaIpcMemHandle_t ipc; };
+static_assert(sizeof(PeerHandle) <= PHT_PEER_HANDLE_BYTES, "peer handle does not fit its ABI slot");
+
+extern "C" int pht_engine_peer_handle(pht_engine *e, void *handle) {
+    if (!e || !handle) return fail("null argument");
+    memset(handle, 0, PHT_PEER_HANDLE_BYTES);
+    PeerHandle h; memset(&h, 0, sizeof(h));
+    if (e->d_xw) {
+        CU(cudaSetDevice(e->cfg.device));
+        h.pid = (unsigned long long)getpid(); h.ptr = (unsigned long long)(uintptr_t)e->d_xw; h.device = e->cfg.device; h.valid = 1;
+        CU(cudaIpcGetMemHandle(&h.ipc, e->d_xw));
+    }
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int pht_engine_peer_attach(pht_engine *e, const void *handles) {
+    if (!e || !handles) return fail("null argument");
+    if (e->cfg.world == 1 || !e->d_xw) return 0;           /* nothing to share (single rank, or not an MHRS engine) */
+    CU(cudaSetDevice(e->cfg.device));
+    for (int r = 0; r < e->cfg.world; r++) {
+        PeerHandle h; memcpy(&h, (const char *)handles + (size_t)r * PHT_PEER_HANDLE_BYTES, sizeof(h));
+        if (!h.valid) return fail("rank %d offers no exchange window", r);
+        if (r == e->cfg.rank) { e->xpeer[r] = e->d_xw; continue; }
+        if (h.pid == (unsigned long long)getpid()) {
+            /* same process (one host thread per GPU): the peer's pointer is valid here once peer access is on */
+            if (h.device != e->cfg.device) {
+                int can = 0; CU(cudaDeviceCanAccessPeer(&can, e->cfg.device, h.device));
+                if (!can) return fail("device %d cannot access device %d", e->cfg.device, h.device);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess(%d): %s", h.device, cudaGetErrorString(pe));
+                cudaGetLastError();
+            }
+            e->xpeer[r] = reinterpret_cast<XchgWindow *>((uintptr_t)h.ptr);
+        } else {
+            void *q = nullptr;
+            CU(cudaIpcOpenMemHandle(&q, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+            e->ipc_opened.push_back(q);
+            e->xpeer[r] = reinterpret_cast<XchgWindow *>(q);
+        }
+    }
+    e->peers_attached = true;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }     /* kernel parameters change */
     return 0;
 }
 
@@ -382,12 +457,15 @@ static int check_state(pht_engine *e) {
     DevState st; CU(cudaMemcpy(&st, e->d_state, sizeof(st), cudaMemcpyDeviceToHost));
     if (st.error) {
         int err = st.error;
-        cudaMemset(&e->d_state->error, 0, sizeof(int));
-        return fail("device error word 0x%x (%s%s%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range; " : "",
+        cudaMemsetAsync(&e->d_state->error, 0, sizeof(int), e->stream);
+        cudaStreamSynchronize(e->stream);
+        return fail("device error word 0x%x (%s%s%s%s%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range (lower PHT_B200_ZBITS); " : "",
                     (err & 4) ? "MHRS tail list overflow; " : "",
-                    (err & 8) ? "an observation's survival probability is too small for rejection sampling; " : "",
+                    (err & 8) ? "an observation's survival probability is too small for rejection sampling (more than 4e9 attempts); " : "",
                     (err & 16) ? "S has complex eigenvalues: the spectral samplers (ECS/DCS) are not valid for it; " : "",
-                    (err & 32) ? "spectral decomposition failed; " : "");
+                    (err & 32) ? "spectral decomposition failed; " : "",
+                    (err & 64) ? "a peer GPU did not arrive at a barrier of the global MHRS tail; " : "",
+                    (err & 128) ? "another rank of the run raised its error word; " : "");
     }
     return 0;
 }
@@ -439,7 +517,11 @@ extern "C" int pht_engine_sweep_stats(pht_engine *e, long long *N, long long *B,
     CU(cudaMemcpy(h.data(), e->d_stats, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     if (N) memcpy(N, h.data(), sizeof(long long) * n * n);
     if (B) memcpy(B, h.data() + n * n, sizeof(long long) * n);
-    if (zfix) memcpy(zfix, h.data() + n * n + n, sizeof(long long) * n);
+    if (zfix) for (int i = 0; i < n; i++) {
+        const __int128 tot = ((__int128)h[n * n + 2 * n + i] << 32) + (__int128)(unsigned long long)h[n * n + n + i];
+        if (tot > (__int128)0x7fffffffffffffffLL || tot < -(__int128)0x7fffffffffffffffLL) return fail("sojourn total of state %d overflows the fixed-point range (zbits = %d)", i, e->cfg.zbits);
+        zfix[i] = (long long)tot;
+    }
     return 0;
 }
 
@@ -450,29 +532,35 @@ extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, i
     CU(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n;
     int *dB = nullptr, *dN = nullptr; double *dz = nullptr;
-    CU(cudaMalloc(&dB, sizeof(int) * count)); CU(cudaMalloc(&dN, sizeof(int) * count * n * n)); CU(cudaMalloc(&dz, sizeof(double) * count * n));
-    CU(cudaMemsetAsync(dB, 0, sizeof(int) * count, e->stream)); CU(cudaMemsetAsync(dN, 0, sizeof(int) * count * n * n, e->stream));
-    CU(cudaMemsetAsync(dz, 0, sizeof(double) * count * n, e->stream));
-    UpdateParams u = update_params(e, nullptr, 0);
-    if (enqueue_model(e, u)) { cudaFree(dB); cudaFree(dN); cudaFree(dz); return -1; }
-    SweepParams p = sweep_params(e);
-    p.outB = dB; p.outN = dN; p.outz = dz; p.first = first; p.count = count;
-    int rc;
     uint32_t *t_exact = nullptr, *t_cens = nullptr;
-    if (method_of(e->cfg) == PHT_METHOD_ECS) {
-        std::vector<uint32_t> ie, ic;
-        for (long i = first; i < first + count; i++) (e->h_cens[i] ? ic : ie).push_back((uint32_t)i);
-        CU(cudaMalloc(&t_exact, sizeof(uint32_t) * (ie.size() + 1))); CU(cudaMalloc(&t_cens, sizeof(uint32_t) * (ic.size() + 1)));
-        if (!ie.empty()) CU(cudaMemcpy(t_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice));
-        if (!ic.empty()) CU(cudaMemcpy(t_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
-        rc = enqueue_paths(e, p, t_exact, ie.size(), t_cens, ic.size(), true);
-    } else rc = enqueue_paths(e, p);
-    if (rc == 0) rc = pht_engine_sync(e);
-    if (rc == 0) {
-        CU(cudaMemcpy(B, dB, sizeof(int) * count, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(N, dN, sizeof(int) * count * n * n, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(z, dz, sizeof(double) * count * n, cudaMemcpyDeviceToHost));
+    /* every exit goes through `out`, which releases the temporaries */
+    int rc = -1;
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); goto out; } } while (0)
+    {
+        CUP(cudaMalloc(&dB, sizeof(int) * count)); CUP(cudaMalloc(&dN, sizeof(int) * count * n * n)); CUP(cudaMalloc(&dz, sizeof(double) * count * n));
+        CUP(cudaMemsetAsync(dB, 0, sizeof(int) * count, e->stream)); CUP(cudaMemsetAsync(dN, 0, sizeof(int) * count * n * n, e->stream));
+        CUP(cudaMemsetAsync(dz, 0, sizeof(double) * count * n, e->stream));
+        UpdateParams u = update_params(e, nullptr, 0);
+        if (enqueue_model(e, u)) goto out;
+        SweepParams p = sweep_params(e);
+        p.y = e->d_y; p.cens = e->d_cens; p.perm = nullptr;         /* the window [first, first + count) is in upload order */
+        p.outB = dB; p.outN = dN; p.outz = dz; p.first = first; p.count = count;
+        if (method_of(e->cfg) == PHT_METHOD_ECS) {
+            std::vector<uint32_t> ie, ic;
+            for (long i = first; i < first + count; i++) (e->h_cens[i] ? ic : ie).push_back((uint32_t)i);
+            CUP(cudaMalloc(&t_exact, sizeof(uint32_t) * (ie.size() + 1))); CUP(cudaMalloc(&t_cens, sizeof(uint32_t) * (ic.size() + 1)));
+            if (!ie.empty()) CUP(cudaMemcpy(t_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice));
+            if (!ic.empty()) CUP(cudaMemcpy(t_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
+            if (enqueue_paths(e, p, t_exact, ie.size(), t_cens, ic.size(), true)) goto out;
+        } else if (enqueue_paths(e, p)) goto out;
+        if (pht_engine_sync(e)) goto out;
+        CUP(cudaMemcpy(B, dB, sizeof(int) * count, cudaMemcpyDeviceToHost));
+        CUP(cudaMemcpy(N, dN, sizeof(int) * count * n * n, cudaMemcpyDeviceToHost));
+        CUP(cudaMemcpy(z, dz, sizeof(double) * count * n, cudaMemcpyDeviceToHost));
+        rc = 0;
     }
+#undef CUP
+out:
     cudaFree(dB); cudaFree(dN); cudaFree(dz);
     if (t_exact) cudaFree(t_exact);
     if (t_cens) cudaFree(t_cens);

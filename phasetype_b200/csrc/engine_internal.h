@@ -6,7 +6,7 @@
  *   cens[l_local]   uint8  right-censoring flags (the ABI's int32 is repacked at upload)
  *   model[]         fp64   the per-sweep model block, offsets from ModelLayout (< 70 KB at n = 32);
  *                          rebuilt on the device every sweep, copied to shared memory by the path kernels
- *   stats[]         int64  N (n*n) | B (n) | z fixed point (n): the only data that crosses NVLink
+ *   stats[]         int64  N (n*n) | B (n) | z fixed point in two limbs (2n) | error count: the only data that crosses NVLink
  *   state           DevState: sweep index, work counters, event counters, error word
  *   items/pend/...  MHRS tail work lists (see k_mhrs.cu)
  */
@@ -46,15 +46,46 @@ struct ModelLayout {
     }
 };
 
-/* stats block: int64 [ N: n*n | B: n | zfix: n ] */
-__host__ __device__ inline int stats_len(int n) { return n * n + 2 * n; }
+/* stats block: int64 [ N: n*n | B: n | zlo: n | zhi: n | errors: 1 ].  The fixed-point sojourn total of state i is
+ * zhi[i] 2^32 + zlo[i]: every path adds the low 32 bits of its contribution to zlo and the rest to zhi, so the
+ * accumulated total cannot wrap (each limb stays far inside 64 bits for 2^32 paths) and k_update can tell exactly
+ * whether it still fits the int64 the conjugate update works with.  The last word counts ranks with a raised
+ * error word, so that after the all-reduce every rank stops together. */
+__host__ __device__ inline int stats_len(int n) { return n * n + 3 * n + 1; }
+__device__ __forceinline__ void pht_zfix_add(unsigned long long *zlo, long long *zhi, int i, long long fixed) {
+    atomicAdd(&zlo[i], (unsigned long long)fixed & 0xffffffffull);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&zhi[i]), (unsigned long long)(fixed >> 32));
+}
 
-/* one MHRS observation handed from the lane phase to the cooperative tail */
+/* one MHRS observation handed from the lane phase to the cooperative tail.  It carries everything a search of its
+ * attempts needs (y, flag, global index), so any GPU of the box can run any of its attempts (global tail rounds). */
 struct TailItem {
-    uint32_t obs_local;   /* index into y/cens */
+    double y;
+    uint32_t og;          /* global observation index (Philox counter word 2) */
+    uint32_t pos;         /* position in the owner's y/cens arrays (for the replay of the accepted attempt) */
     uint32_t a;           /* first attempt index of the current search */
     uint32_t cur_a;       /* attempt index of the accepted draw so far */
-    uint32_t flags;       /* bit0 have_cur, bit1 cur_off, bit2 off (for attempt a), bits 8..15 cur_pre, bits 16..31 proposals done */
+    uint32_t flags;       /* bit0 have_cur, bit1 cur_off, bit2 off (for attempt a), bit3 censored, bit4 finished,
+                             bits 8..15 cur_pre, bits 16..31 proposals done */
+    uint32_t owner;       /* rank that holds the observation */
+};
+#define TI_HAVE 1u
+#define TI_CUROFF 2u
+#define TI_OFF 4u
+#define TI_CENS 8u
+#define TI_FIN 16u
+
+/* Peer-exchange window: one per engine, in device memory, mapped into every other rank of the run (direct peer
+ * pointers inside one process, CUDA IPC between processes).  The MHRS kernels of all ranks use it to search the
+ * deepest part of the rejection tail together: peers WRITE into it over NVLink (items, surviving attempts, barrier
+ * flags), its owner only reads it locally. */
+#define PHT_MAX_WORLD 16
+#define PHT_GCAP 2048                     /* observations one rank can contribute to a global tail */
+struct XchgWindow {
+    unsigned long long flags[PHT_MAX_WORLD];                      /* flags[r]: last barrier epoch rank r arrived at */
+    unsigned long long gfound[2][PHT_MAX_WORLD * PHT_GCAP];        /* lowest surviving attempt per item, by round parity */
+    uint32_t gcount[2][PHT_MAX_WORLD];                             /* items contributed by rank r, by sweep parity */
+    TailItem gitems[2][PHT_MAX_WORLD * PHT_GCAP];                  /* the gathered items, by sweep parity */
 };
 
 struct DevState {
@@ -68,13 +99,17 @@ struct DevState {
     uint32_t n_items;          /* items appended by the lane phase */
     uint32_t n_pend[2];        /* pending list sizes (double buffered) */
     uint32_t n_done;           /* finished items awaiting replay */
-    uint32_t any_fail;         /* MHRS tail: some pending observation found no surviving attempt in the current round */
+    uint32_t any_fail[2];      /* MHRS tail, by round parity: some pending observation found no surviving attempt */
+    uint32_t n_gpend;          /* global tail: items not finished yet */
+    uint32_t xdead;            /* a peer barrier timed out: no further waiting */
+    unsigned long long xepoch; /* barrier epochs completed (monotonic over the life of the engine) */
     unsigned long long counters[PHT_CNT_COUNT];
 };
 
 struct SweepParams {
     /* data */
     const double *y; const uint8_t *cens; long l_local; uint32_t obs_rank, obs_world;
+    const uint32_t *perm;      /* position in y/cens -> local observation index; nullptr = identity (y-sorted layout) */
     /* model + state */
     double *model; long long *stats; DevState *state;
     int n, m, mhit, zbits;
@@ -83,6 +118,10 @@ struct SweepParams {
     /* MHRS tail lists */
     TailItem *items; uint32_t *pend0, *pend1, *done; unsigned long long *found; uint32_t item_cap;
     int mhrs_cap;
+    uint32_t *glist;           /* global tail: the gathered items in canonical (rank-major) order */
+    XchgWindow *xw;            /* this rank's exchange window; nullptr = tail rounds stay local */
+    XchgWindow *xpeer[PHT_MAX_WORLD];   /* every rank's window as mapped on this device (xpeer[rank] == xw) */
+    uint32_t k_switch;         /* attempts per observation and round from which the tail goes global */
     /* per-observation recording (parity mode); all NULL in production */
     int *outB, *outN; double *outz; long first, count;
 };
@@ -97,7 +136,8 @@ struct UpdateParams {
 /* kernel launchers (each returns the cudaError of the launch) */
 cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st);
-cudaError_t pht_launch_mhrs(const SweepParams &p, int grid_blocks, cudaStream_t st);
+cudaError_t pht_launch_pack_error(const UpdateParams &p, cudaStream_t st);
+cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, cudaStream_t st);
 cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st);
 int pht_dcs_grid_blocks(int device, int n);
 /* ECS: exact and right-censored observations are separate launches over index lists (nullptr = identity) */
@@ -106,7 +146,8 @@ cudaError_t pht_launch_ecs(const SweepParams &p, int grid_blocks, const uint32_t
 int pht_ecs_grid_blocks(int device, int n);
 /* spectral data of the sweep: inject != nullptr copies host-supplied (evals | Q | Qinv) instead of solving on the device */
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st);
-int pht_mhrs_grid_blocks(int device, int n);
+int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks);
 size_t pht_mhrs_smem_bytes(int n);
+cudaError_t pht_sort_by_y_desc(const double *y, const uint8_t *cens, long l, double *ys, uint8_t *cs, uint32_t *perm, cudaStream_t st);
 
 #endif

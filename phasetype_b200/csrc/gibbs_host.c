@@ -5,14 +5,24 @@
  * meaning :72-103); R reaches it through the unchanged registration table
  * (src/Registrations.c:6-14).  Everything inside the iteration loop (:268-405) runs on the
  * GPU through the engine ABI of include/pht_b200.h; this file only does the once-per-call
- * work: start values (:195-207), seed, upload, sweep batches, result scatter, console text.
- * There is no CPU path: if the engine cannot be created the routine reports through
- * Rprintf and returns with rows 1.. of `res` left as R pre-filled them (zeros).
+ * work: start values (:195-207), seed, sharding, upload, sweep batches, result scatter,
+ * console text.
+ *
+ * Several GPUs: R calls the routine once, in one process (R/phtMCMC2.R:73), so the fan-out
+ * happens here: one engine and one host thread per device, observation i -> device i mod G,
+ * an NCCL communicator over the devices for the per-sweep all-reduce of the statistics, and
+ * the engines' exchange windows attached to one another for the global MHRS tail.  Every
+ * device draws the same parameters from the shared key, so rank 0's rows are the result.
+ *
+ * There is no CPU path: if an engine cannot be created, or the device raises its error word,
+ * the routine reports through Rprintf and fills the rows it could not produce with NA, so
+ * that nothing downstream can mistake them for samples.
  */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <pthread.h>
 #include "../../include/pht_b200.h"
 #include "pht_philox.h"
 
@@ -22,10 +32,98 @@ void GetRNGstate(void);
 void PutRNGstate(void);
 double unif_rand(void);
 
+#define MAX_GPUS 16
+
 static uint64_t env_u64(const char *name, int *found) {
     const char *s = getenv(name);
     *found = (s != NULL && *s != 0);
     return *found ? strtoull(s, NULL, 0) : 0ULL;
+}
+
+/* R's NA_real_: a quiet NaN with payload 1954 (arithmetic.c) */
+static double na_real(void) { const uint64_t u = 0x7FF00000000007A2ULL; double d; memcpy(&d, &u, 8); return d; }
+
+/* what the host threads share */
+typedef struct {
+    int world, IT, M, sweeps, batch, silent;
+    const pht_config *base;
+    const double *y; const int *censored; long l;
+    const double *theta;
+    double *res;
+    unsigned char nccl_id[128];
+    unsigned char handles[MAX_GPUS * PHT_PEER_HANDLE_BYTES];
+    pthread_barrier_t bar;
+    volatile int failed;                 /* some rank could not go on: everybody stops at the next barrier */
+    volatile int done_rows;              /* rows of res produced so far (rank 0) */
+    char err[512];
+    pthread_mutex_t err_lock;
+    int devices[MAX_GPUS];
+} shared_t;
+
+typedef struct { shared_t *sh; int rank; } rank_arg;
+
+static void set_error(shared_t *sh, int rank, const char *msg) {
+    pthread_mutex_lock(&sh->err_lock);
+    if (!sh->failed) snprintf(sh->err, sizeof(sh->err), "GPU %d: %s", sh->devices[rank], msg);
+    sh->failed = 1;
+    pthread_mutex_unlock(&sh->err_lock);
+}
+
+/* One rank = one device.  Every collective step is bracketed by the thread barrier, and a rank that has failed keeps
+ * walking through the barriers without touching its engine, so nobody waits for it in vain. */
+static void *rank_main(void *argp) {
+    rank_arg *ra = (rank_arg *)argp; shared_t *sh = ra->sh; const int rank = ra->rank, world = sh->world;
+    pht_engine *eng = NULL;
+    /* this rank's shard: observations rank, rank + world, ... */
+    const long l_local = sh->l > rank ? (sh->l - rank + world - 1) / world : 0;
+    double *ys = NULL; int *cs = NULL;
+    const double *yl = sh->y; const int *cl = sh->censored;
+    if (world > 1) {
+        ys = (double *)malloc(sizeof(double) * (size_t)(l_local > 0 ? l_local : 1));
+        cs = (int *)malloc(sizeof(int) * (size_t)(l_local > 0 ? l_local : 1));
+        if (!ys || !cs) set_error(sh, rank, "out of memory");
+        else for (long k = 0; k < l_local; k++) { ys[k] = sh->y[rank + k * world]; cs[k] = sh->censored[rank + k * world]; }
+        yl = ys; cl = cs;
+    }
+    pht_config cfg = *sh->base; cfg.rank = rank; cfg.world = world; cfg.device = sh->devices[rank];
+    if (!sh->failed && pht_engine_create(&eng, &cfg, yl, cl, l_local) != 0) set_error(sh, rank, pht_last_error());
+    free(ys); free(cs);
+    if (world > 1) {
+        if (rank == 0 && !sh->failed && pht_comm_unique_id(sh->nccl_id) != 0) set_error(sh, rank, pht_last_error());
+        if (eng && pht_engine_peer_handle(eng, sh->handles + (size_t)rank * PHT_PEER_HANDLE_BYTES) != 0) set_error(sh, rank, pht_last_error());
+        pthread_barrier_wait(&sh->bar);
+        if (!sh->failed && pht_engine_comm_init(eng, sh->nccl_id) != 0) set_error(sh, rank, pht_last_error());
+        if (!sh->failed && pht_engine_peer_attach(eng, sh->handles) != 0) set_error(sh, rank, pht_last_error());
+        pthread_barrier_wait(&sh->bar);
+    }
+    if (!sh->failed && pht_engine_set_theta(eng, sh->theta, 1u) != 0) set_error(sh, rank, pht_last_error());
+    double *rows = NULL;
+    if (rank == 0) {
+        rows = (double *)malloc(sizeof(double) * (size_t)(sh->batch > 0 ? sh->batch : 1) * (size_t)(sh->M > 0 ? sh->M : 1));
+        if (!rows) set_error(sh, rank, "out of memory");
+    }
+    for (int done = 0; done < sh->sweeps; ) {
+        if (world > 1) pthread_barrier_wait(&sh->bar);
+        if (sh->failed) break;
+        const int k = (sh->sweeps - done < sh->batch) ? sh->sweeps - done : sh->batch;
+        /* (a device error raised on one rank reaches every rank through the all-reduced statistics block, so all of
+         * them return from this call, with or without an error of their own) */
+        if (pht_engine_run(eng, k, rows) != 0) { set_error(sh, rank, pht_last_error()); }
+        if (world > 1) pthread_barrier_wait(&sh->bar);
+        if (sh->failed) break;
+        done += k;
+        if (rank == 0) {
+            for (int r = 0; r < k; r++)
+                for (int v = 0; v < sh->M; v++) sh->res[(size_t)(1 + done - k + r) + (size_t)v * sh->IT] = rows[(size_t)r * sh->M + v];
+            sh->done_rows = 1 + done;
+            if (!sh->silent) {
+                Rprintf("\rProcessing iteration %d of %d (%.1lf%%)\r", done + 1, sh->IT, (100.0 * (done + 1)) / sh->IT); R_FlushConsole();
+            }
+        }
+    }
+    free(rows);
+    if (eng) pht_engine_destroy(eng);
+    return NULL;
 }
 
 void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, double *zeta,
@@ -39,6 +137,13 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
     if (!found) {
         const uint64_t hi = (uint64_t)(unif_rand() * 4294967296.0), lo = (uint64_t)(unif_rand() * 4294967296.0);
         seed = (hi << 32) | (lo & 0xffffffffULL);
+    } else if (*start >= 0 && getenv("PHT_B200_SEED_EXACT") == NULL) {
+        /* A fixed key and given start values: a resumed run (R/phtMCMC2.R resume=) would otherwise replay the random
+         * streams of the run it continues.  Mix the start vector into the key (FNV-1a over its bytes). */
+        uint64_t h = 0xcbf29ce484222325ULL;
+        const unsigned char *b = (const unsigned char *)start;
+        for (size_t i = 0; i < sizeof(double) * (size_t)M; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }
+        seed ^= h;
     }
     PutRNGstate();
 
@@ -70,45 +175,65 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
     cfg.n = *n; cfg.m = M; cfg.method = *method; cfg.mhit = *mhit;
     cfg.T = T; cfg.C = C; cfg.nu = nu; cfg.zeta = zeta;
     cfg.seed = seed;
-    cfg.device = (int)env_u64("PHT_B200_DEVICE", &found);
-    cfg.rank = 0; cfg.world = 1;
     cfg.zbits = pht_choose_zbits(sum_y);
+    { int f2; uint64_t z = env_u64("PHT_B200_ZBITS", &f2); if (f2 && z <= 52) cfg.zbits = (int)z; }
     cfg.mhrs_cap = (int)env_u64("PHT_B200_MHRS_CAP", &found);
     cfg.use_graph = 1;
     { int f2; uint64_t g = env_u64("PHT_B200_GRAPH", &f2); if (f2) cfg.use_graph = (int)g; }
 
-    pht_engine *eng = NULL;
-    if (pht_engine_create(&eng, &cfg, y, censored, (long)*l) != 0) {
-        /* mirrors the reference's print-and-continue error style (e.g. :334-337) */
-        Rprintf("CRITICAL ERROR: %s\n\n", pht_last_error());
-        free(theta);
-        return;
-    }
+    /* devices: PHT_B200_GPUS of them starting at PHT_B200_DEVICE; default: every visible device the data can keep
+     * busy (one per 2^19 observations; a few hundred thousand paths are microseconds of one B200) */
+    shared_t sh; memset(&sh, 0, sizeof(sh));
+    const int visible = pht_device_count();
+    const int first_dev = (int)env_u64("PHT_B200_DEVICE", &found);
+    int gpus = (int)env_u64("PHT_B200_GPUS", &found);
+    if (!found || gpus < 1) { gpus = (int)(((long)*l + (1L << 19) - 1) >> 19); if (gpus < 1) gpus = 1; }
+    if (gpus > visible - first_dev) gpus = visible - first_dev;
+    if (gpus > MAX_GPUS) gpus = MAX_GPUS;
+    if (gpus < 1) gpus = 1;               /* no device: engine creation reports it below */
+    for (int r = 0; r < gpus; r++) sh.devices[r] = first_dev + r;
+
     Rprintf("Starting phase-type MCMC sampler ...\n\nBegining processing ..."); R_FlushConsole();
     if (*silent) {
         Rprintf(" silent processing selected, there will be no further feedback until MCMC run complete"); R_FlushConsole();
     }
-
-    int ok = pht_engine_set_theta(eng, theta, 1u) == 0;
-    const int sweeps = IT - 1;
+    sh.world = gpus; sh.IT = IT; sh.M = M; sh.sweeps = IT - 1; sh.silent = *silent;
     /* progress text as the reference prints it (:273), once per batch of sweeps instead of per sweep */
-    int batch = sweeps;
-    if (!*silent) { batch = sweeps / 100; if (batch < 1) batch = 1; }
-    double *rows = (double *)malloc(sizeof(double) * (size_t)(batch > 0 ? batch : 1) * (size_t)(M > 0 ? M : 1));
-    if (!rows) ok = 0;
-    for (int done = 0; ok && done < sweeps; ) {
-        const int k = (sweeps - done < batch) ? sweeps - done : batch;
-        if (pht_engine_run(eng, k, rows) != 0) { ok = 0; break; }
-        for (int r = 0; r < k; r++)
-            for (int v = 0; v < M; v++) res[(size_t)(1 + done + r) + (size_t)v * IT] = rows[(size_t)r * M + v];
-        done += k;
-        if (!*silent) {
-            Rprintf("\rProcessing iteration %d of %d (%.1lf%%)\r", done + 1, IT, (100.0 * (done + 1)) / IT); R_FlushConsole();
+    sh.batch = sh.sweeps;
+    if (!*silent) { sh.batch = sh.sweeps / 100; if (sh.batch < 1) sh.batch = 1; }
+    sh.base = &cfg; sh.y = y; sh.censored = censored; sh.l = (long)*l; sh.theta = theta; sh.res = res;
+    sh.done_rows = 1;
+    pthread_mutex_init(&sh.err_lock, NULL);
+    rank_arg args[MAX_GPUS];
+    if (gpus == 1) {
+        args[0].sh = &sh; args[0].rank = 0;
+        rank_main(&args[0]);
+    } else {
+        pthread_t th[MAX_GPUS];
+        pthread_barrier_init(&sh.bar, NULL, (unsigned)gpus);
+        int started = 0;
+        for (int r = 0; r < gpus; r++) {
+            args[r].sh = &sh; args[r].rank = r;
+            if (pthread_create(&th[r], NULL, rank_main, &args[r]) != 0) break;
+            started++;
         }
+        if (started < gpus) {
+            /* cannot happen short of resource exhaustion; the started threads would wait at the barrier forever */
+            Rprintf("\nCRITICAL ERROR: could not start %d host threads\n", gpus);
+            abort();
+        }
+        for (int r = 0; r < gpus; r++) pthread_join(th[r], NULL);
+        pthread_barrier_destroy(&sh.bar);
     }
-    if (!ok) Rprintf("\nCRITICAL ERROR: %s\n", pht_last_error());
-    free(rows); free(theta);
-    pht_engine_destroy(eng);
+    if (sh.failed) {
+        /* mirrors the reference's print-and-carry-on error style (e.g. :334-337), but the rows that were not produced
+         * are NA, not the zeros R pre-filled */
+        Rprintf("\nCRITICAL ERROR: %s\n", sh.err);
+        const double na = na_real();
+        for (int r = sh.done_rows; r < IT; r++) for (int v = 0; v < M; v++) res[(size_t)r + (size_t)v * IT] = na;
+    }
+    pthread_mutex_destroy(&sh.err_lock);
+    free(theta);
 
     Rprintf("\n\nCompleted MCMC run, returning results ...\n"); R_FlushConsole();
 }

@@ -44,17 +44,17 @@ template <int THREADS>
 struct DcsSmem {
     double *S, *Q, *Qinv, *evals, *s, *pi, *PIQ, *D;
     double *X, *E, *P, *Z;
-    long long *zacc; unsigned int *Nacc, *Bacc, *deg;
+    unsigned long long *zlo; long long *zhi; unsigned int *Nacc, *Bacc, *deg;
     __device__ __forceinline__ void carve(unsigned char *raw, int n) {
         double *d = reinterpret_cast<double *>(raw);
         S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * n; D = d; d += n * n;
         evals = d; d += n; s = d; d += n; pi = d; d += n; PIQ = d; d += n;
         X = d; d += n * THREADS; E = d; d += n * THREADS; P = d; d += n * THREADS; Z = d; d += n * THREADS;
-        zacc = reinterpret_cast<long long *>(d); d += n;
+        zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
         Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n; deg = Bacc + n;
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(4 * n * n + 4 * n + 4 * n * THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
+        return sizeof(double) * (size_t)(4 * n * n + 4 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
     }
 };
 
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     }
     for (int i = tid; i < n; i += THREADS) {
         sm.evals[i] = p.model[ML.evals + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
-        sm.zacc[i] = 0; sm.Bacc[i] = 0u;
+        sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
     }
     __syncthreads();
     /* observation-independent tables: D[j][i] = ev_i - S_jj, the degenerate flags, and pi^T Q in reference-BLAS order */
@@ -297,13 +297,13 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             else { T = y - t; alpha = T; beta = 0.0; kind = K_JUMP; }
         }
         if (flush) {
-            path_flush<THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
+            path_flush<THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
             c_paths++; kind = K_IDLE;
         }
     }
 
     __syncthreads();
-    block_flush<THREADS>(p, n, sm.Nacc, sm.Bacc, sm.zacc);
+    block_flush<THREADS>(p, n, sm.Nacc, sm.Bacc, sm.zlo, sm.zhi);
     unsigned long long w_jumps = c_jumps, w_evals = c_evals, w_paths = c_paths, w_fail = c_fail;
     for (int o = 16; o > 0; o >>= 1) {
         w_jumps += __shfl_down_sync(FULL, w_jumps, o); w_evals += __shfl_down_sync(FULL, w_evals, o);

@@ -37,17 +37,17 @@
 struct EcsSmem {
     double *S, *Q, *P, *Pfull, *evals, *s, *Qinv_s, *Qinv_1, *pi;
     double *PQ, *W, *Z;                 /* per-lane slabs: hoisted p^T Q, scratch weights, sojourn totals */
-    long long *zacc; unsigned int *Nacc, *Bacc;
+    unsigned long long *zlo; long long *zhi; unsigned int *Nacc, *Bacc;
     __device__ __forceinline__ void carve(unsigned char *raw, int n) {
         double *d = reinterpret_cast<double *>(raw);
         S = d; d += n * n; Q = d; d += n * n; P = d; d += n * n; Pfull = d; d += n * (n + 1);
         evals = d; d += n; s = d; d += n; Qinv_s = d; d += n; Qinv_1 = d; d += n; pi = d; d += n;
         PQ = d; d += n * ECS_THREADS; W = d; d += n * ECS_THREADS; Z = d; d += n * ECS_THREADS;
-        zacc = reinterpret_cast<long long *>(d); d += n;
+        zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
         Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n;
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(3 * n * n + n * (n + 1) + 5 * n + 3 * n * ECS_THREADS + n) + sizeof(unsigned int) * (size_t)(n * n + n);
+        return sizeof(double) * (size_t)(3 * n * n + n * (n + 1) + 5 * n + 3 * n * ECS_THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + n);
     }
 };
 
@@ -305,7 +305,7 @@ __device__ __forceinline__ void ecs_load_model(const SweepParams &p, EcsSmem &sm
     for (int i = tid; i < n; i += ECS_THREADS) {
         sm.evals[i] = p.model[ML.evals + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
         sm.Qinv_s[i] = p.model[ML.Qinv_s + i]; sm.Qinv_1[i] = p.model[ML.Qinv_1 + i];
-        sm.zacc[i] = 0; sm.Bacc[i] = 0u;
+        sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
     }
     __syncthreads();
 }
@@ -313,7 +313,7 @@ __device__ __forceinline__ void ecs_load_model(const SweepParams &p, EcsSmem &sm
 __device__ __forceinline__ void ecs_finish(const SweepParams &p, int n, EcsSmem &sm, EcsCounters &c) {
     const unsigned FULL = 0xffffffffu;
     __syncthreads();
-    block_flush<ECS_THREADS>(p, n, sm.Nacc, sm.Bacc, sm.zacc);
+    block_flush<ECS_THREADS>(p, n, sm.Nacc, sm.Bacc, sm.zlo, sm.zhi);
     for (int o = 16; o > 0; o >>= 1) {
         c.jumps += __shfl_down_sync(FULL, c.jumps, o); c.evals += __shfl_down_sync(FULL, c.evals, o);
         c.updates += __shfl_down_sync(FULL, c.updates, o); c.calls += __shfl_down_sync(FULL, c.calls, o);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         if (absorb) {
             count_transition(p, n, sm.Nacc, out_idx, j, j);                             /* :368 */
             sm.Z[j * ECS_THREADS + tid] += y - t;                                       /* :369 */
-            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
+            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
             c.paths++; active = false;
         }
         __syncwarp();
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         if (k == n) {                                                                   /* :379, :390-392 */
             sm.Z[lastj * ECS_THREADS + tid] += t - lastt;
             count_transition(p, n, sm.Nacc, out_idx, lastj, lastj);
-            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zacc, sm.Bacc, B, out_idx);
+            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
             c.paths++; active = false;
         } else {
             sm.Z[lastj * ECS_THREADS + tid] += t - lastt;                               /* :382 */

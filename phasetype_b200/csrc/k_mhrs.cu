@@ -8,41 +8,51 @@
  * `mhit` further draws, and add the accepted path's (B, N, z) to the sweep statistics.
  *
  * How it is organised on the GPU (nothing like the reference's loop nest):
- *   - Every rejection attempt is its own Philox sub-stream (pht_philox.h), so attempts
- *     are independent work items and "the first attempt that survives" is well defined
- *     whatever order they run in.
- *   - SEARCH / REPLAY split: while searching, a lane tracks only (t, state); the 21 of 22
- *     attempts that fail never touch N or z.  The accepted attempt is replayed once from
- *     its (attempt index, offset) with recording on.  No per-attempt zeroing of N2/z2.
- *   - One jump-step (walk_step) is one Philox block: {state uniform of this jump,
- *     exponential uniform of the next}; the attempt's first step uses the same code with
- *     the start distribution as the scan row, and a failed attempt restarts the lane on
- *     the next sub-stream with a handful of selects, so fresh, running and failing lanes
- *     execute one instruction stream.  Only the rare events (a surviving attempt, a
- *     hand-over to the tail) leave it.
- *   - The categorical scan `while (sofar < target) sofar += p[k++]` is answered from
- *     precomputed running sums: a 64-bucket guide table indexed by the top 6 random bits
- *     gives a lower bound of the answer, one or two comparisons finish it (same result as
- *     the sequential scan because the running sums are non-decreasing).
- *   - Lane phase: persistent warps, one observation per lane, refilled from a global
- *     counter in warp-sized chunks (prefetched into shared memory) as lanes finish.
- *     Accepted attempts go to a per-warp ring in shared memory; when the ring holds two
- *     warps' worth, the whole warp replays them together, so the recording code runs
- *     converged instead of on one or two lanes at a time.  A lane gives up after `cap`
- *     attempts (attempt counts are geometric with a heavy tail) and appends
- *     the observation to the tail list.
- *   - Tail phase (same cooperative launch, grid barriers between rounds): the attempts of
- *     every pending observation are searched by all warps of the GPU.  A warp takes a pool
- *     of consecutive attempts of ONE observation from a global counter (pool size shrinks
- *     as the round drains), its lanes draw attempt indices from the pool with a ballot (no
- *     memory traffic), the lowest surviving attempt wins through atomicMin; one thread per
- *     observation then advances its MH state machine.  Attempts per observation double per
- *     round.
- *   - Statistics: N, B in shared-memory integer atomics; z per path in a per-lane shared
- *     slab (bit-identical to the reference's z2), then added as int64 fixed point, so the
- *     sweep totals do not depend on scheduling or on the number of GPUs.
+ *   - Every rejection attempt is its own Philox sub-stream (pht_philox.h), so attempts are
+ *     independent work items and "the first attempt that survives" is well defined whatever
+ *     order, lane or GPU they run on.
+ *   - SEARCH / REPLAY split.  ~21 of 22 attempts fail, and a failed attempt contributes
+ *     nothing but the fact that it failed.  The search therefore runs a FILTER walk: the state
+ *     sequence is exact (the scan `while (sofar < target) sofar += p[k++]` is answered by
+ *     integer thresholds on the 52 random bits -- same decisions as the FP64 comparison), but
+ *     the clock is kept in FP32 with the exponential taken from MUFU.LG2, together with a
+ *     rigorous bound of its error.  "Attempt alive at y?" is decided by the filter when the
+ *     clock is further from y than the bound; the rare attempt that ends inside the band
+ *     (~1e-4 of them) is re-run by the exact FP64 walker.  The decision is therefore always
+ *     the exact one, at a third of the instructions.  The accepted attempt is replayed once
+ *     by the exact walker with recording on: every N, B and z bit comes from FP64 arithmetic
+ *     in the reference's order.
+ *   - One jump-step is one Philox block: {state uniform of this jump, exponential uniform of
+ *     the next sojourn}.  A failed attempt restarts the lane on the next sub-stream with a
+ *     handful of selects, so fresh, running and failing lanes execute one instruction stream.
+ *   - Lane phase: persistent warps, one observation per lane.  Observations are laid out by
+ *     decreasing y (the attempt count is Geometric(survival(y))), so the stream ends with the
+ *     cheapest observations and the drain is short.  Every lane holds one prefetched
+ *     observation; empty slots are refilled eight or more at a time from a global counter.
+ *     A finished observation goes to a per-warp ring with its one or two surviving attempts;
+ *     when the ring holds two warps' worth the whole warp runs the MH accept tests and the
+ *     exact replays together (converged), instead of each lane on its own.
+ *   - A lane gives up after `cap` attempts (attempt counts have a heavy tail) and
+ *     appends the observation to the tail list.
+ *   - Tail phase (same cooperative launch, grid barriers between rounds): the attempts of every
+ *     pending observation are searched by all warps of the GPU.  A warp takes a pool of
+ *     consecutive attempts of ONE observation from a global counter, its lanes draw attempt
+ *     indices from the pool with a ballot, the lowest surviving attempt wins through atomicMin;
+ *     one thread per observation then advances its MH state machine.  Attempts per observation
+ *     double per round.
+ *   - Global tail (several GPUs): an observation that needs 10^5..10^8 attempts is a
+ *     millisecond of a whole GPU, and the sweep ends when the unluckiest rank does.  From
+ *     K = k_switch attempts per round on, the ranks therefore gather their pending observations
+ *     into every rank's exchange window (peer stores over NVLink) and search them TOGETHER:
+ *     attempt block q of observation o belongs to rank (o + q) mod W, a survivor is pushed to
+ *     every rank's `found` word with a system-scope atomicMin, rounds end with a flag barrier in
+ *     peer memory, and every rank advances the (identical) MH state machines redundantly.  The
+ *     owner replays.  No host, no NCCL call inside the sweep kernel.
+ *   - Statistics: N, B in shared-memory integer atomics; z per path in FP64 exactly like the
+ *     reference's z2, then added as int64 fixed point, so the sweep totals do not depend on
+ *     scheduling or on the number of GPUs.
  *
- * Roofline: FP64/issue bound (one log + one Philox block per jump-step, 9 B of HBM per path).
+ * Roofline: issue bound (one Philox block per jump-step; 9..13 B of HBM per path).
  */
 #include <cooperative_groups.h>
 #include "engine_internal.h"
@@ -55,73 +65,89 @@ namespace cg = cooperative_groups;
 #endif
 #define MHRS_WARPS (MHRS_THREADS / 32)
 #ifndef MHRS_MIN_BLOCKS
-#define MHRS_MIN_BLOCKS 3                /* 80 registers: 24 warps per SM */
+#define MHRS_MIN_BLOCKS 4                /* lane kernel: 64 registers, 32 warps per SM */
 #endif
-#define GUIDE 64                    /* buckets of the scan guide table */
-#define OBS_CHUNK 64u               /* observations a warp takes from the global counter at once */
+#ifndef MHRS_TAIL_MIN_BLOCKS
+#define MHRS_TAIL_MIN_BLOCKS 3           /* tail kernel: 80 registers, 24 warps per SM */
+#endif
+/* rare-path helpers (exact walker, replay): inlined, because a call inside the search loops makes ptxas keep the
+ * loop-carried walk state in local memory (measured: 15 LDL/STL per jump-step); -DMHRS_NOINLINE_COLD to compare */
+#ifndef MHRS_NOINLINE_COLD
+#define MHRS_COLD static __device__ __forceinline__
+#else
+#define MHRS_COLD static __device__ __noinline__
+#endif
+#define GUIDE_BITS 8
+#define GUIDE (1 << GUIDE_BITS)     /* buckets of the scan guide table */
 #ifndef END_CAP
-#define END_CAP 8u                   /* attempts a lane still tries once no observations are left */
+#define END_CAP 32u                 /* attempts a lane still tries once no observations are left */
 #endif
-#define RING 96                     /* per-warp ring of accepted attempts awaiting replay */
+#define RING 96                     /* per-warp ring of finished observations awaiting accept test + replay */
 #define RING_TRIGGER 64
+#ifndef PREFETCH_MIN
+#define PREFETCH_MIN 8              /* empty prefetch slots in a warp that trigger a refill */
+#endif
 #ifndef TAIL_CH
-#define TAIL_CH 128u                /* attempts per tail chunk (a pool never crosses a chunk) */
+#define TAIL_CH 256u                /* attempts per tail chunk (a pool never crosses a chunk) */
+#endif
+#ifndef TAIL_BATCH
+#define TAIL_BATCH 8u               /* consecutive attempts a lane takes from a pool at once */
 #endif
 #ifndef TAIL_K0
 #define TAIL_K0 512u                /* attempts per pending observation in tail round 0 */
 #endif
 #define TAIL_KMAX (1u << 24)
 #ifndef TAIL_GROWTH
-#define TAIL_GROWTH 2u               /* attempts per pending observation grow by this factor per round */
+#define TAIL_GROWTH 2u
 #endif
 #ifndef FOUND_PERIOD
-#define FOUND_PERIOD 8u               /* steps between looks at the pool observation's `found` word (power of two) */
+#define FOUND_PERIOD 8u             /* steps between looks at the pool observation's `found` word (power of two) */
 #endif
 #define POOL_MIN 32u
 #ifndef POOL_MAX
 #define POOL_MAX 256u
 #endif
 #define FOUND_NONE 0xFFFFFFFFFFFFFFFFull
+#define T52_NEVER (1ull << 52)
+#define LOWBITS (1u << 20)          /* exponential uniforms below 2^-12 go to the exact walker */
+#define XBAR_TIMEOUT_NS 4000000000ull
 
-struct Smem {
-    double *scale, *cum, *z2;
-    long long *zacc; unsigned int *Nacc, *Bacc;
-    double *ybuf; double *ring_y; uint32_t *ring_obs, *ring_a; unsigned int *ring_n;
-    unsigned char *cbuf, *ring_fl, *guide;
+/* ring record flags */
+#define RF_CENS 1u
+#define RF_PROP 2u                  /* a2/j2 hold an MH proposal whose accept test is still to be made */
+#define RF_OFF 4u                   /* a1 runs one draw into its sub-stream */
+
+template <int NC>
+struct MhrsSmem {
+    static constexpr int R = NC + 1;            /* rows: states 0..n-1, row n = the start distribution */
+    unsigned long long thr[R * R];              /* integer scan thresholds (see build_tables) */
+    double cum[R * R];                          /* running sums: the exact walker's scan */
+    double scale[NC];                           /* 1 / -S_jj */
+    double s[NC];                               /* exit rates (MH accept ratio) */
+    double inv_smax;                            /* 1 / max_j scale[j]: the filter clock's unit */
+    double ring_y[MHRS_WARPS * RING];
+    unsigned long long zlo[NC];                 /* fixed-point sojourn totals, two limbs (engine_internal.h) */
+    long long zhi[NC];
+    unsigned int Nacc[NC * NC];
+    unsigned int Bacc[NC];
+    float A[R + 3];                             /* -ln2 * scale[k] / smax (entry n = 0: absorbed, the clock stands) */
+    uint32_t ring_pos[MHRS_WARPS * RING], ring_og[MHRS_WARPS * RING], ring_a1[MHRS_WARPS * RING],
+             ring_a2[MHRS_WARPS * RING], ring_fl[MHRS_WARPS * RING];
+    unsigned int ring_n[MHRS_WARPS];
+    unsigned int paths_done;                    /* replays finished by this block */
+    /* per-lane state that is touched once or twice per observation lives here, not in registers: the prefetched
+     * next observation and the MH bookkeeping */
+    float pf_yf[MHRS_THREADS]; uint32_t pf_og[MHRS_THREADS], pf_pos[MHRS_THREADS];
+    uint32_t mh_cur_a[MHRS_THREADS], mh_misc[MHRS_THREADS];     /* misc: cur_pre | cur_off << 8 | kprop << 16 */
+    unsigned char guide[R * GUIDE];
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
 }
-
-__host__ __device__ inline size_t mhrs_smem_bytes_of(int n) {
-    size_t o = 0;
-    o += sizeof(double) * (size_t)(n + (n + 1) * (n + 1) + n * MHRS_THREADS + n + MHRS_WARPS * OBS_CHUNK + MHRS_WARPS * RING);
-    o += sizeof(unsigned int) * (size_t)(n * n + n + 2 * MHRS_WARPS * RING + MHRS_WARPS);
-    o += (size_t)(MHRS_WARPS * OBS_CHUNK + MHRS_WARPS * RING + (n + 1) * GUIDE);
-    return (o + 15) & ~(size_t)15;
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
-__device__ __forceinline__ Smem carve(unsigned char *raw, int n) {
-    Smem sm; double *d = reinterpret_cast<double *>(raw);
-    sm.scale = d; d += n;
-    sm.cum = d; d += (n + 1) * (n + 1);
-    sm.z2 = d; d += n * MHRS_THREADS;
-    sm.zacc = reinterpret_cast<long long *>(d); d += n;
-    sm.ybuf = d; d += MHRS_WARPS * OBS_CHUNK;
-    sm.ring_y = d; d += MHRS_WARPS * RING;
-    unsigned int *u = reinterpret_cast<unsigned int *>(d);
-    sm.Nacc = u; u += n * n;
-    sm.Bacc = u; u += n;
-    sm.ring_obs = u; u += MHRS_WARPS * RING;
-    sm.ring_a = u; u += MHRS_WARPS * RING;
-    sm.ring_n = u; u += MHRS_WARPS;
-    unsigned char *c = reinterpret_cast<unsigned char *>(u);
-    sm.cbuf = c; c += MHRS_WARPS * OBS_CHUNK;
-    sm.ring_fl = c; c += MHRS_WARPS * RING;
-    sm.guide = c;
-    return sm;
-}
-size_t pht_mhrs_smem_bytes(int n) { return mhrs_smem_bytes_of(n); }
 
 /* Philox4x32-10 block (b, a, observation, sweep) with the round keys taken from the kernel parameters */
 __device__ __forceinline__ pht_u32x4 philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SweepParams &p) {
@@ -133,7 +159,9 @@ __device__ __forceinline__ pht_u32x4 philox_block(uint32_t c0, uint32_t c1, uint
     return out;
 }
 
-/* the chain of one attempt: sub-stream a, next Philox block b, time t of the pending exit from state j */
+/* ------------------------------------------------------------------------------------------ exact walker
+ * The chain of one attempt in the reference's arithmetic: sub-stream a, next Philox block b, time t of the
+ * pending exit from state j. */
 struct Walk {
     double t, spare;
     uint32_t spare_hi, a, b;
@@ -141,14 +169,14 @@ struct Walk {
     bool odd, fresh;
 };
 /* recording state of a replayed path */
-struct Rec { double lastt; int B; long out_idx; };
+struct Rec { double lastt; int B; long out_idx; double *z2; };
 
 /* position the walk on the first draw of attempt a; off = the MH accept uniform of the previous proposal
  * occupies draw 0 of this sub-stream (src/Simulate_AbsCTMC_eq_Bladt_MHRS.c:79) */
-__device__ __forceinline__ void walk_begin(Walk &w, uint32_t a, bool off, uint32_t obs_global, const SweepParams &p, uint32_t iter) {
-    w.a = a; w.fresh = true; w.b = 0; w.odd = false; w.t = 0.0; w.j = 0;
+__device__ __forceinline__ void walk_begin(Walk &w, uint32_t a, bool off, uint32_t og, const SweepParams &p, uint32_t iter) {
+    w.a = a; w.fresh = true; w.b = 0; w.odd = false; w.t = 0.0; w.j = 0; w.spare = 0.0; w.spare_hi = 0u;
     if (off) {
-        pht_u32x4 r = philox_block(0u, a, obs_global, iter, p);
+        pht_u32x4 r = philox_block(0u, a, og, iter, p);
         w.spare = pht_u01(r.v[2], r.v[3]); w.spare_hi = r.v[3]; w.odd = true; w.b = 1;
     }
 }
@@ -156,12 +184,13 @@ __device__ __forceinline__ void walk_begin(Walk &w, uint32_t a, bool off, uint32
 /* log of a uniform in (0,1): always a positive normal number, so the core of pht_log applies directly */
 __device__ __forceinline__ double log_unit(double x) { return pht_log_core(pht_d2u(x), 0); }
 
-/* One jump-step of a walk; returns true when the attempt ended on this step (w.t, w.j are then the exit time
- * and the state occupied at the end).  No control flow around the expensive parts (Philox, scan, log). */
-template <bool RECORD>
-__device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t obs_global, const SweepParams &p, const Smem &sm,
+/* One jump-step of an exact walk; returns true when the attempt ended on this step (w.t, w.j are then the exit
+ * time and the state occupied at the end). */
+template <bool RECORD, int NC>
+__device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t og, const SweepParams &p, MhrsSmem<NC> &sm,
                                           uint32_t iter, int n, Rec &rec) {
-    pht_u32x4 r = philox_block(w.b, w.a, obs_global, iter, p);
+    constexpr int R = NC + 1;
+    pht_u32x4 r = philox_block(w.b, w.a, og, iter, p);
     w.b++;
     const double f = pht_u01(r.v[0], r.v[1]), g = pht_u01(r.v[2], r.v[3]);
     const double uA = w.odd ? w.spare : f;               /* start state / next state */
@@ -171,17 +200,17 @@ __device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t
     const bool fresh = w.fresh;
     const int row = fresh ? n : w.j;
     const int last = fresh ? n - 1 : n;
-    const double *c = sm.cum + row * (n + 1);
-    /* reference scan `while (sofar < target) sofar += p[k++]` = number of running sums below the target among the
-     * first `last` (the sums are non-decreasing).  The guide entry counts the sums <= bucket floor < uA. */
-    int k = sm.guide[row * GUIDE + (hiA >> 26)];
+    const double *c = sm.cum + row * R;
+    /* reference scan `while (sofar < target) sofar += p[k++]` = number of leading running sums below the target
+     * among the first `last`.  The guide entry counts the sums <= bucket floor < uA. */
+    int k = sm.guide[row * GUIDE + (hiA >> (32 - GUIDE_BITS))];
     while (k < last && c[k] < uA) k++;
     const bool cont = (k < n) && (w.t < y || cens);                /* gt_Bladt_MHRS.c:75,111 */
     const bool ended = !fresh && !cont;
     const bool advance = !fresh && cont;
     if (RECORD) {
         if (advance) {
-            sm.z2[w.j * MHRS_THREADS + threadIdx.x] += w.t - rec.lastt;            /* :112 */
+            rec.z2[w.j] += w.t - rec.lastt;                                        /* :112 */
             if (p.outN != nullptr) p.outN[(size_t)rec.out_idx * n * n + w.j + k * n]++;
             else atomicAdd(&sm.Nacc[w.j + k * n], 1u);                             /* :113 */
         }
@@ -197,451 +226,768 @@ __device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t
     return ended;
 }
 
-/* close a replayed path: gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110 */
-__device__ __forceinline__ void finish_replay(const Walk &w, const Rec &rec, double y, bool cens, const SweepParams &p, const Smem &sm, int n) {
-    const int tid = threadIdx.x;
-    sm.z2[w.j * MHRS_THREADS + tid] += (cens ? w.t : y) - rec.lastt;
-    if (p.outB != nullptr) {
-        p.outB[rec.out_idx] = rec.B;
-        p.outN[rec.out_idx * n * n + w.j + w.j * n]++;
-        for (int i = 0; i < n; i++) { p.outz[rec.out_idx * n + i] = sm.z2[i * MHRS_THREADS + tid]; sm.z2[i * MHRS_THREADS + tid] = 0.0; }
-    } else {
-        atomicAdd(&sm.Nacc[w.j + w.j * n], 1u);
-        atomicAdd(&sm.Bacc[rec.B], 1u);
-        const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
-        for (int i = 0; i < n; i++) {
-            const double v = sm.z2[i * MHRS_THREADS + tid];
-            if (v != 0.0) {
-                if (!(v * zs < 4.0e18)) atomicOr(&p.state->error, 2);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&sm.zacc[i]), (unsigned long long)__double2ll_rn(v * zs));
-                sm.z2[i * MHRS_THREADS + tid] = 0.0;
-            }
-        }
-    }
+/* Run attempt a of observation (y, cens, og) to its end with the exact walker.  Returns true when it survives
+ * (alive at y in a state that can exit, eq_Bladt_MHRS.c:66,74); *jend = the state it is in at the end. */
+/* result word: bit 0 survived, bits 8..15 end state, bits 16..31 jump-steps taken */
+template <int NC>
+MHRS_COLD uint32_t exact_attempt(uint32_t a, bool off, double y, bool cens, uint32_t og, const SweepParams &p,
+                                                      MhrsSmem<NC> &sm, uint32_t iter, int n, uint32_t smask) {
+    Walk w; Rec norec; norec.lastt = 0.0; norec.B = 0; norec.out_idx = 0; norec.z2 = nullptr;
+    walk_begin(w, a, off, og, p, iter);
+    unsigned st = 1;
+    while (!walk_step<false>(w, y, cens, og, p, sm, iter, n, norec)) st++;
+    const bool ok = (w.t >= y) && ((smask >> w.j) & 1u);
+    return (ok ? 1u : 0u) | ((uint32_t)w.j << 8) | ((st > 0xffffu ? 0xffffu : st) << 16);
 }
 
-/* replay one accepted attempt start to end (the lane's z2 slab is all zero on entry and on exit) */
-__device__ __forceinline__ unsigned replay_path(uint32_t obs_local, uint32_t a, bool off, double y, bool cens, const SweepParams &p,
-                                                const Smem &sm, uint32_t iter, int n) {
-    Walk w; Rec rec; rec.lastt = 0.0; rec.B = 0; rec.out_idx = (long)obs_local - p.first;
-    const uint32_t og = p.obs_rank + obs_local * p.obs_world;
-    walk_begin(w, a, off, og, p, iter);
-    unsigned steps = 1;
-    while (!walk_step<true>(w, y, cens, og, p, sm, iter, n, rec)) steps++;
-    finish_replay(w, rec, y, cens, p, sm, n);
+/* Replay one wave of accepted attempts, one per lane (have = this lane holds one), with recording on:
+ * gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110.  The walk loop is warp-uniform (lanes that have finished
+ * wait for the longest path of the wave: paths of one wave belong to neighbours in the y-ordered layout and are of
+ * similar length), so that the bookkeeping after it -- the path's z per state rounded to fixed point, reduced over the
+ * warp with shuffles, one shared atomic per state -- runs converged instead of lane by lane. */
+template <int NC>
+__device__ __forceinline__ unsigned replay_wave(bool have, uint32_t pos, uint32_t og, uint32_t a, bool off, double y, bool cens,
+                                                const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n) {
+    const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
+    double z2[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) z2[i] = 0.0;
+    Walk w; Rec rec; rec.lastt = 0.0; rec.B = 0; rec.z2 = z2; rec.out_idx = 0;
+    if (have) {
+        rec.out_idx = (long)(p.perm ? p.perm[pos] : pos) - p.first;
+        walk_begin(w, a, off, og, p, iter);
+    } else { w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true; }
+    unsigned steps = 0;
+    bool act = have;
+    while (__any_sync(FULL, act)) {
+        if (act) { steps++; if (walk_step<true>(w, y, cens, og, p, sm, iter, n, rec)) act = false; }
+    }
+    if (have) z2[w.j] += (cens ? w.t : y) - rec.lastt;
+    if (p.outB != nullptr) {
+        if (have) {
+            p.outB[rec.out_idx] = rec.B;
+            p.outN[rec.out_idx * n * n + w.j + w.j * n]++;
+#pragma unroll 1
+            for (int i = 0; i < n; i++) p.outz[rec.out_idx * n + i] = z2[i];
+        }
+    } else {
+        if (have) { atomicAdd(&sm.Nacc[w.j + w.j * n], 1u); atomicAdd(&sm.Bacc[rec.B], 1u); }
+        const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
+        bool bad = false;
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            const double v = have ? z2[i] : 0.0;
+            bad = bad || !(v * zs < 4.0e18);
+            const long long fx = __double2ll_rn(v * zs);
+            unsigned long long lo = (unsigned long long)fx & 0xffffffffull; long long hi = fx >> 32;
+            for (int d = 16; d > 0; d >>= 1) { lo += __shfl_xor_sync(FULL, lo, d); hi += __shfl_xor_sync(FULL, hi, d); }
+            if (lane == 0 && (lo | (unsigned long long)hi)) {
+                atomicAdd(&sm.zlo[i], lo); atomicAdd(reinterpret_cast<unsigned long long *>(&sm.zhi[i]), (unsigned long long)hi);
+            }
+        }
+        if (bad) atomicOr(&p.state->error, 2);
+    }
     return steps;
 }
 
-/* the whole warp replays the accepted attempts waiting in its ring */
-__device__ __forceinline__ void replay_session(const SweepParams &p, const Smem &sm, uint32_t iter, int n, int warp,
-                                               unsigned &c_jumps, unsigned &c_paths) {
-    const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
+/* the whole warp works through the finished observations waiting in its ring: MH accept test where a proposal is
+ * pending (eq_Bladt_MHRS.c:79-82), then the exact replay of the accepted attempt */
+template <int NC>
+MHRS_COLD unsigned replay_session(const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n, int warp) {
+    const int lane = threadIdx.x & 31;
+    unsigned c_jumps = 0;
     __syncwarp();
     const unsigned count = sm.ring_n[warp];
-    unsigned next = 0;
-    Walk w; Rec rec; double y = 0.0; bool cens = false, active = false; uint32_t og = 0;
-    rec.lastt = 0.0; rec.B = 0; rec.out_idx = 0;
-    for (;;) {
-        unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && next < count) {
-            const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-            if (!active && next + rank < count) {
-                const unsigned e = warp * RING + next + rank;
-                const uint32_t ol = sm.ring_obs[e]; const unsigned fl = sm.ring_fl[e];
-                y = sm.ring_y[e]; cens = fl & 1u; og = p.obs_rank + ol * p.obs_world;
-                rec.lastt = 0.0; rec.B = 0; rec.out_idx = (long)ol - p.first;
-                walk_begin(w, sm.ring_a[e], (fl & 2u) != 0u, og, p, iter);
-                active = true;
-            }
-            const unsigned cnt = __popc(idle);
-            next = next + cnt < count ? next + cnt : count;
-            idle = __ballot_sync(FULL, !active);
+    for (unsigned e0 = 0; e0 < count; e0 += 32u) {
+        const unsigned e = e0 + lane;
+        const bool have = e < count;
+        const unsigned q = warp * RING + (have ? e : 0u);
+        const uint32_t fl = sm.ring_fl[q], og = sm.ring_og[q];
+        uint32_t a = sm.ring_a1[q];
+        if (have && (fl & RF_PROP)) {
+            const uint32_t a2 = sm.ring_a2[q];
+            pht_u32x4 r = philox_block(0u, a2 + 1u, og, iter, p);
+            const double U = pht_u01(r.v[0], r.v[1]);
+            if (U < sm.s[(fl >> 16) & 0xffu] / sm.s[(fl >> 8) & 0xffu]) a = a2;
         }
-        if (idle == FULL) break;
         __syncwarp();
-        if (active) {
-            const bool ended = walk_step<true>(w, y, cens, og, p, sm, iter, n, rec);
-            c_jumps++;
-            if (ended) { finish_replay(w, rec, y, cens, p, sm, n); c_paths++; active = false; }
-        }
+        c_jumps += replay_wave(have, sm.ring_pos[q], og, a, (fl & RF_OFF) != 0u, sm.ring_y[q], (fl & RF_CENS) != 0u, p, sm, iter, n);
     }
     __syncwarp();
-    if (lane == 0) sm.ring_n[warp] = 0u;
+    if (lane == 0) { atomicAdd(&sm.paths_done, count); sm.ring_n[warp] = 0u; }
     __syncwarp();
+    return c_jumps;
 }
 
-__device__ __forceinline__ uint32_t pack_flags(bool have_cur, bool cur_off, bool off, int cur_pre, int kprop) {
-    return (have_cur ? 1u : 0u) | (cur_off ? 2u : 0u) | (off ? 4u : 0u) | ((uint32_t)(cur_pre & 0xff) << 8) | ((uint32_t)kprop << 16);
+/* replay of the tail's finished observations: waves over the done list, all warps of the grid */
+template <int NC>
+MHRS_COLD unsigned replay_done_list(const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n,
+                                                         uint32_t n_done, uint32_t gwarp, uint32_t nwarps) {
+    const int lane = threadIdx.x & 31;
+    unsigned c_jumps = 0;
+    for (uint32_t base = gwarp * 32u; base < n_done; base += nwarps * 32u) {
+        const bool have = base + lane < n_done;
+        TailItem it; it.y = 0.0; it.og = 0u; it.pos = 0u; it.a = 0u; it.cur_a = 0u; it.flags = 0u; it.owner = 0u;
+        if (have) it = p.items[p.done[base + lane]];
+        c_jumps += replay_wave(have, it.pos, it.og, it.cur_a, (it.flags & TI_CUROFF) != 0u, it.y, (it.flags & TI_CENS) != 0u, p, sm, iter, n);
+        if (lane == 0) atomicAdd(&sm.paths_done, (n_done - base < 32u) ? n_done - base : 32u);
+    }
+    return c_jumps;
 }
 
-__global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_sweep(SweepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cg::grid_group grid = cg::this_grid();
-    const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned FULL = 0xffffffffu;
-    const ModelLayout ML = ModelLayout::make(n, p.m);
-    Smem sm = carve(smem_raw, n);
-    const uint32_t iter = p.state->iter;
+/* ------------------------------------------------------------------------------------------ filter walk
+ * What a search needs to know of its observation: y in FP32 in units of the largest mean sojourn (smax = max_j
+ * scale[j]; the filter clock runs in those units so that its error constants are pure numbers), the part of the
+ * per-step error bound that depends on y, the Philox word, and the censoring flag. */
+struct ObsF { float yn, c0y; uint32_t og; bool cens; };
+__device__ __forceinline__ void obs_set(ObsF &o, float yn, uint32_t og, bool cens) {
+    o.yn = yn; o.c0y = __fmaf_rn(1.2e-7f, yn, 4.5e-7f); o.og = og; o.cens = cens;
+}
+/* the filter walk of one attempt: FP32 clock t with error bound dacc, sub-stream a, next block b, scan row */
+struct Fast { float t, dacc; uint32_t a, b; int row; };
 
-    for (int i = tid; i < n; i += MHRS_THREADS) { sm.scale[i] = p.model[ML.scale + i]; sm.zacc[i] = 0; sm.Bacc[i] = 0u; }
-    for (int i = tid; i < (n + 1) * (n + 1); i += MHRS_THREADS) sm.cum[i] = p.model[ML.cum + i];
+__device__ __forceinline__ void fast_begin(Fast &f, uint32_t a, int n) { f.t = 0.0f; f.dacc = 0.0f; f.a = a; f.b = 0u; f.row = n; }
+
+/* One jump-step of the filter walk.
+ * The next state is exact: with x the 52 random bits of the state uniform u = (x + 0.5) 2^-52, `cum[k] < u` <=>
+ * x >= thr[k] (build_tables), and rows end with a NEVER entry so the scan needs no bound check.
+ * The clock advances by (scale[k] / smax) * -ln(u) in FP32, with u taken from the top 32 bits w of the exponential
+ * uniform: w -> FP32 (I2F), exponent and mantissa split, lg2.approx of the mantissa in [1, 2) (documented absolute
+ * error 2^-22 there), L = (exponent - 32) + lg2(mantissa), t = fma(L, A[k], t) with A[k] = -ln2 scale[k] / smax.
+ * Error of one step, in clock units (scale[k] / smax <= 1):
+ *     truncation of u to w           relative 1/w <= 2^-(exponent)          -> |d ln u| <= 2^-e     (`trunc`)
+ *     I2F rounding                   relative 2^-24                         -> 6.0e-8
+ *     lg2.approx of the mantissa     absolute 2^-22 in log2                 -> 1.65e-7
+ *     rounding of L, of A[k]         relative 2^-24 each, times ln2 |L|     -> 8.3e-8 |L|
+ *     rounding of the FMA            relative 2^-24 of t_new <= y + ln2 |L| -> 6.0e-8 y + 4.1e-8 |L|
+ * (a clock beyond 2y is in no danger: its relative error stays below 1e-3 for the 4096 steps a walk may take here.)
+ * The bound accumulated per step is TWICE that sum: 2 * 2^-e + (4.5e-7 + 1.2e-7 y) + 2.5e-7 |L|.  Uniforms with
+ * w < 4096 and walks of 4096 steps make the bound infinite, i.e. leave the decision to the exact walker.
+ * Outcome of the step: fail (the attempt is dead for certain), surv (alive at y for certain, in state kout), amb (the
+ * clock is inside the error band at the moment of the test: ask the exact walker), none of them (the walk goes on). */
+template <int NC>
+__device__ __forceinline__ void fast_step(Fast &f, const ObsF &o, const SweepParams &p, const MhrsSmem<NC> &sm, uint32_t iter, int n,
+                                          bool &fail, bool &surv, bool &amb, int &kout) {
+    constexpr int R = NC + 1;
+    const pht_u32x4 r = philox_block(f.b, f.a, o.og, iter, p);
+    f.b++;
+    const unsigned long long x = (((unsigned long long)r.v[1] << 32) | r.v[0]) >> 12;
+    int k = sm.guide[f.row * GUIDE + (r.v[1] >> (32 - GUIDE_BITS))];
+    const unsigned long long *th = sm.thr + f.row * R;
+    while (x >= th[k]) k++;
+    const uint32_t w = r.v[3];
+    const uint32_t wb = __float_as_uint(__uint2float_rn(w));
+    const uint32_t eb = wb >> 23;                                                     /* 127 + exponent of w */
+    const float lg2m = lg2_approx(__uint_as_float((wb & 0x007fffffu) | 0x3f800000u));
+    const float L = (__uint_as_float(0x4b400000u + eb) - 12583071.0f) + lg2m;        /* (eb - 159) + lg2m: log2 of u */
+    f.t = __fmaf_rn(L, sm.A[k], f.t);
+    const float trunc = __uint_as_float((254u - eb) << 23);                           /* 2^-(exponent of w) >= 1 / w */
+    const float step_err = __fmaf_rn(trunc, 2.0f, __fmaf_rn(fabsf(L), 2.5e-7f, o.c0y));
+    const bool flagged = (w < 4096u) || (f.b >> 12) != 0u;
+    f.dacc = flagged ? __int_as_float(0x7f800000) : f.dacc + step_err;
+    const bool absd = (k == n);
+    const float diff = f.t - o.yn;
+    const bool over = diff > f.dacc, under = -diff > f.dacc;      /* alive at y for certain / dead at y for certain */
+    const bool test = o.cens == absd;                            /* the step at which `alive at y` is decided */
+    surv = test && over;
+    amb = test && !over && !under;
+    fail = absd && (!o.cens || under);
+    kout = absd ? f.row : k;             /* the state occupied at the end: absorption happens FROM the previous state */
+    f.row = k;
+}
+
+/* Scan tables of the sweep's model.  thr[row][k] = the smallest x in [0, 2^52] whose uniform (x + 0.5) 2^-52
+ * exceeds cum[row][k] (NEVER = 2^52 when none does, also for NaN sums, and for every k beyond the row's last
+ * category).  guide[row][b] = number of leading sums <= b / GUIDE: every uniform of bucket b is above them. */
+template <int NC>
+__device__ __forceinline__ void build_tables(const SweepParams &p, MhrsSmem<NC> &sm, int n, const ModelLayout &ML) {
+    constexpr int R = NC + 1;
+    const int tid = threadIdx.x;
+    double smax = 0.0;
+    for (int i = 0; i < n; i++) { const double sc = p.model[ML.scale + i]; smax = (sc > smax) ? sc : smax; }
+    const double inv_smax = 1.0 / smax;          /* smax = 0 or NaN: the clock is NaN, every decision goes to the exact walker */
+    for (int i = tid; i < n; i += MHRS_THREADS) {
+        const double sc = p.model[ML.scale + i];
+        sm.scale[i] = sc; sm.s[i] = p.model[ML.s + i]; sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
+        sm.A[i] = (float)((-0.69314718055994530942 * sc) * inv_smax);
+    }
+    if (tid == 0) { sm.A[n] = 0.0f; sm.inv_smax = inv_smax; }
     for (int i = tid; i < n * n; i += MHRS_THREADS) sm.Nacc[i] = 0u;
-    for (int i = 0; i < n; i++) sm.z2[i * MHRS_THREADS + tid] = 0.0;
+    for (int e = tid; e < R * R; e += MHRS_THREADS) {
+        const int row = e / R, k = e % R;
+        unsigned long long t52 = T52_NEVER; double c = 0.0;
+        if (row <= n && k <= n) {
+            c = p.model[ML.cum + row * (n + 1) + k];
+            const int last = (row == n) ? n - 1 : n;
+            if (k < last && c < 1.0) {                   /* NaN compares false: NEVER */
+                if (!(c > 0.0)) t52 = 0ull;
+                else {
+                    /* floor(c 2^52) is exact; the answer is that or the next integer */
+                    const unsigned long long xf = (unsigned long long)(c * 4503599627370496.0);
+                    const double u = pht_u2d(0x3ff0000000000000ULL | xf) - 0.99999999999999988898;
+                    t52 = (u > c) ? xf : xf + 1ull;
+                }
+            }
+        }
+        sm.thr[e] = t52; sm.cum[e] = c;
+    }
     if (tid < MHRS_WARPS) sm.ring_n[tid] = 0u;
-    /* states that can exit: bit j of smask (the accept tests of eq_Bladt_MHRS.c:66,74 need s[j] != 0) */
-    uint32_t smask = 0u;
-    for (int i = 0; i < n; i++) smask |= (p.model[ML.s + i] != 0.0) ? (1u << i) : 0u;
+    if (tid == 0) sm.paths_done = 0u;
     __syncthreads();
-    /* guide[row][b] = #{ i < last(row) : cum[row][i] <= b / GUIDE }: every uniform of bucket b is > b / GUIDE */
     for (int e = tid; e < (n + 1) * GUIDE; e += MHRS_THREADS) {
         const int row = e / GUIDE, b = e % GUIDE, last = (row == n) ? n - 1 : n;
         const double floor_u = (double)b * (1.0 / GUIDE);
         int k = 0;
-        while (k < last && sm.cum[row * (n + 1) + k] <= floor_u) k++;
+        while (k < last && sm.cum[row * R + k] <= floor_u) k++;
         sm.guide[e] = (unsigned char)k;
     }
     __syncthreads();
+}
 
-    unsigned c_attempts = 0, c_jumps = 0, c_paths = 0, c_deferred = 0;      /* per thread and sweep: far below 2^32 */
-    const unsigned long long t_start = gtimer();
-    const bool per_obs = p.outB != nullptr;
-    const unsigned long long obs_begin = per_obs ? (unsigned long long)p.first : 0ull;
-    const unsigned long long obs_end = per_obs ? (unsigned long long)(p.first + p.count) : (unsigned long long)p.l_local;
-    const uint32_t cap = (uint32_t)p.mhrs_cap;
-    const double *s_model = p.model + ML.s;
-    Rec norec; norec.lastt = 0.0; norec.B = 0; norec.out_idx = 0;
+__device__ __forceinline__ uint32_t pack_flags(bool have_cur, bool cur_off, bool off, bool cens, int cur_pre, uint32_t kprop) {
+    return (have_cur ? TI_HAVE : 0u) | (cur_off ? TI_CUROFF : 0u) | (off ? TI_OFF : 0u) | (cens ? TI_CENS : 0u) |
+           ((uint32_t)(cur_pre & 0xff) << 8) | (kprop << 16);
+}
 
-    /* ---------------------------------------------------------------- lane phase */
-    {
-        Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
-        bool active = false, cens = false, off = false, have_cur = false, cur_off = false;
-        bool keep = false;          /* the tail lists were full when this lane tried to hand its observation over */
-        double y = 0.0; uint32_t obs_local = 0, og = 0, tries = 0, cur_a = 0; int cur_pre = 0, kprop = 0;
-        unsigned long long chunk_base = 0; unsigned chunk_next = 0, chunk_len = 0;      /* warp-uniform */
-        bool exhausted = false, dry = false;      /* this warp found the stream empty / some warp did */
-        unsigned it_count = 0;
-        for (;;) {
-            /* every 64 steps, look whether the observation stream has run dry elsewhere: a warp whose lanes are all
-             * busy would otherwise never notice and grind on to `cap` while the rest of the grid waits */
-            if (((++it_count) & 63u) == 0u && !dry) {
-                unsigned long long nx = 0;
-                if (lane == 0) nx = __ldcg(&p.state->next_obs);
-                dry = obs_begin + __shfl_sync(FULL, nx, 0) >= obs_end;
-            }
-            unsigned idle = __ballot_sync(FULL, !active);
-            if (idle && !exhausted) {
-                if (chunk_next == chunk_len) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = obs_begin + atomicAdd(&p.state->next_obs, (unsigned long long)OBS_CHUNK);
-                    base = __shfl_sync(FULL, base, 0);
-                    chunk_base = base < obs_end ? base : obs_end;
-                    const unsigned long long end = base + OBS_CHUNK < obs_end ? base + OBS_CHUNK : obs_end;
-                    chunk_len = (unsigned)(end > chunk_base ? end - chunk_base : 0ull); chunk_next = 0;
-                    if (chunk_len == 0u) exhausted = true;
-                    /* prefetch the chunk's observations (coalesced) into this warp's staging buffer */
-                    __syncwarp();
-                    for (unsigned q = lane; q < chunk_len; q += 32u) {
-                        sm.ybuf[warp * OBS_CHUNK + q] = p.y[chunk_base + q];
-                        sm.cbuf[warp * OBS_CHUNK + q] = p.cens[chunk_base + q];
-                    }
-                    __syncwarp();
-                }
-                const unsigned avail = chunk_len - chunk_next;
-                const unsigned rank = __popc(idle & ((1u << lane) - 1u));
-                if (!active && rank < avail) {
-                    const unsigned q = chunk_next + rank;
-                    obs_local = (uint32_t)(chunk_base + q);
-                    og = p.obs_rank + obs_local * p.obs_world;
-                    y = sm.ybuf[warp * OBS_CHUNK + q]; cens = sm.cbuf[warp * OBS_CHUNK + q] != 0;
-                    active = true; off = false; have_cur = false; kprop = 0; tries = 0; cur_a = 0; cur_off = false; cur_pre = 0;
-                    keep = false;
-                    walk_begin(w, 0u, false, og, p, iter);
-                }
-                const unsigned cnt = __popc(idle);
-                chunk_next += cnt < avail ? cnt : avail;
-                idle = __ballot_sync(FULL, !active);
-            }
-            if (idle == FULL) { if (exhausted) break; else continue; }
-            __syncwarp();                   /* lanes that have just taken an observation step together with the rest */
-            if (active) {
-                const bool ended = walk_step<false>(w, y, cens, og, p, sm, iter, n, norec);
-                c_jumps++;
-                /* an ended attempt survives when it reached y in a state that can exit (eq_Bladt_MHRS.c:66,74) */
-                const bool ok = (w.t >= y) && ((smask >> w.j) & 1u);
-                const bool failed = ended && !ok;
-                c_attempts += ended ? 1u : 0u;
-                tries += failed ? 1u : 0u;
-                /* a failed attempt restarts on the next sub-stream right here, unless the lane is due to hand the
-                 * observation over: after `cap` attempts, or after END_CAP once the observation stream has run dry
-                 * (a lone lane grinding through attempts would hold the whole grid at the barrier) */
-                const bool handover = cap != 0u && !keep && (tries >= cap || ((exhausted || dry) && tries >= END_CAP));
-                const bool restart = failed && !handover;
-                w.a += failed ? 1u : 0u;
-                off = failed ? false : off;
-                w.fresh = restart; w.b = restart ? 0u : w.b; w.odd = restart ? false : w.odd;
-                if (ended && !restart) {
-                    bool accepted = false;
-                    if (!ok) {
-                        const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
-                        if (idx < p.item_cap) {
-                            TailItem it; it.obs_local = obs_local; it.a = w.a; it.cur_a = cur_a;
-                            it.flags = pack_flags(have_cur, cur_off, false, cur_pre, kprop);
-                            p.items[idx] = it; p.found[idx] = FOUND_NONE;
-                            c_deferred++; active = false;
-                        } else {
-                            /* no room: the lane keeps the observation and goes on with its next attempt */
-                            keep = true; walk_begin(w, w.a, false, og, p, iter);
-                        }
-                    } else if (!have_cur) {
-                        have_cur = true; cur_a = w.a; cur_off = off; cur_pre = w.j;
-                        if (cens || p.mhit == 0) accepted = true;                              /* :70 */
-                        else { off = false; walk_begin(w, w.a + 1u, false, og, p, iter); }
-                    } else {
-                        /* a valid proposal: accept test with draw 0 of the next sub-stream (:79-82) */
-                        pht_u32x4 r = philox_block(0u, w.a + 1u, og, iter, p);
-                        const double U = pht_u01(r.v[0], r.v[1]);
-                        if (U < s_model[w.j] / s_model[cur_pre]) { cur_a = w.a; cur_off = off; cur_pre = w.j; }
-                        kprop++;
-                        if (kprop >= p.mhit) accepted = true;
-                        else {
-                            /* next proposal: sub-stream a+1 from draw 1 (the spare half of the block just computed) */
-                            off = true; w.a++; w.fresh = true; w.b = 1; w.odd = true; w.t = 0.0;
-                            w.spare = pht_u01(r.v[2], r.v[3]); w.spare_hi = r.v[3];
-                        }
-                    }
-                    if (accepted) {
-                        const unsigned e = warp * RING + atomicAdd(&sm.ring_n[warp], 1u);
-                        sm.ring_y[e] = y; sm.ring_obs[e] = obs_local; sm.ring_a[e] = cur_a;
-                        sm.ring_fl[e] = (unsigned char)((cens ? 1u : 0u) | (cur_off ? 2u : 0u));
-                        active = false;
-                    }
-                }
-            }
-            __syncwarp();
-            if (sm.ring_n[warp] >= RING_TRIGGER) replay_session(p, sm, iter, n, warp, c_jumps, c_paths);
-        }
-        replay_session(p, sm, iter, n, warp, c_jumps, c_paths);
-    }
-
-    /* ---------------------------------------------------------------- tail phase */
-    const bool timekeeper = (blockIdx.x == 0 && tid == 0);
+/* barrier over the ranks of the run through the exchange windows: every thread's peer stores are fenced, the grid
+ * meets, rank flags are exchanged, the grid meets again.  Gives up (error word 64) when a peer does not arrive. */
+__device__ __forceinline__ void peer_barrier(cg::grid_group &grid, const SweepParams &p, unsigned long long epoch) {
+    __threadfence_system();
     grid.sync();
-    unsigned long long t_mark = 0;
-    if (timekeeper) { t_mark = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_LANE], t_mark - t_start); }
-    const uint32_t n_items = p.state->n_items < p.item_cap ? p.state->n_items : p.item_cap;
-    if (n_items != 0u) {
-        const unsigned long long gtid = (unsigned long long)blockIdx.x * MHRS_THREADS + tid;
-        const unsigned long long gsize = (unsigned long long)gridDim.x * MHRS_THREADS;
-        const unsigned long long nwarps = gsize / 32ull;
-        for (unsigned long long i = gtid; i < n_items; i += gsize) p.pend0[i] = (uint32_t)i;
-        if (gtid == 0) { p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u; p.state->any_fail = 0u; }
-        grid.sync();
-        uint32_t K = TAIL_K0; int cur = 0; unsigned rounds = 0;
-        for (;;) {
-            const uint32_t P = p.state->n_pend[cur];
-            if (P == 0u) break;
-            const uint32_t *pend = cur ? p.pend1 : p.pend0;
-            uint32_t *pend_next = cur ? p.pend0 : p.pend1;
-            /* The round's work is K attempts for each of the P pending observations, numbered as units in chunk-major
-             * order: unit u belongs to chunk u / TAIL_CH; chunk c covers attempts [ (c / P) TAIL_CH, +TAIL_CH ) beyond
-             * the start attempt of observation pend[c % P].  So the first chunk of every observation is handed out
-             * before any second chunk, and later chunks are mostly skipped once an earlier one has survived. */
-            const unsigned long long total_units = (unsigned long long)P * K;
-            /* --- search: each warp works through pools of consecutive attempts of one observation; a lane keeps the
-             * observation of the pool it drew its attempt from, so the warp moves on to the next pool while slower lanes
-             * are still finishing attempts of the previous one */
-            {
-                Walk w; w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
-                bool active = false;
-                uint32_t my_item = 0, my_og = 0; double my_y = 0.0; bool my_cens = false;
-                unsigned steps = 0;
-                /* warp-uniform: the units this warp holds, and the pool being handed out */
-                unsigned long long u_next = 0, u_end = 0, last_base = 0;
-                bool out_of_units = false;
-                uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; double y = 0.0; bool cens = false, first_off = false;
-                for (;;) {
-                    unsigned idle = __ballot_sync(FULL, !active);
-                    if (idle && pool_next >= pool_end && !out_of_units) {
-                        /* take the next pool (skipping pools that an earlier survivor made moot) */
-                        bool have = false;
-                        while (!have) {
-                            if (u_next >= u_end) {
-                                const unsigned long long remaining = total_units > last_base ? total_units - last_base : 0ull;
-                                unsigned long long want = remaining / (2ull * nwarps);
-                                want = want < POOL_MIN ? POOL_MIN : (want > POOL_MAX ? POOL_MAX : want);
-                                unsigned long long base = 0;
-                                if (lane == 0) base = atomicAdd(&p.state->unit_counter, want);
-                                base = __shfl_sync(FULL, base, 0);
-                                last_base = base;
-                                if (base >= total_units) { out_of_units = true; break; }
-                                u_next = base; u_end = base + want < total_units ? base + want : total_units;
-                            }
-                            const unsigned long long chunk = u_next / TAIL_CH;
-                            const unsigned long long chunk_end_u = (chunk + 1ull) * TAIL_CH;
-                            const unsigned long long stop = u_end < chunk_end_u ? u_end : chunk_end_u;
-                            item = pend[chunk % P];
-                            const TailItem it = p.items[item];
-                            a_first = it.a; first_off = (it.flags & 4u) != 0u;
-                            pool_next = it.a + (uint32_t)(chunk / P) * TAIL_CH + (uint32_t)(u_next - chunk * TAIL_CH);
-                            pool_end = pool_next + (uint32_t)(stop - u_next);
-                            u_next = stop;
-                            if ((__ldcg(&p.found[item]) >> 8) >= (unsigned long long)pool_next) {
-                                have = true;
-                                y = p.y[it.obs_local]; cens = p.cens[it.obs_local] != 0; og = p.obs_rank + it.obs_local * p.obs_world;
-                            } else pool_end = pool_next;
-                        }
-                    }
-                    if (idle == FULL && pool_next >= pool_end) break;          /* nothing in flight, nothing left to hand out */
-                    /* Every FOUND_PERIOD steps, look whether some other warp has found a surviving attempt of the pool's
-                     * observation below this pool: the rest of the pool is then moot (when few observations are pending,
-                     * all warps of the GPU hold pools of the same ones, and without this look they would each finish
-                     * theirs: measured 2.1x the necessary jump-steps at 1e6 observations). */
-                    if (((++steps) & (FOUND_PERIOD - 1u)) == 0u && pool_next < pool_end) {
-                        unsigned long long f = 0;
-                        if (lane == 0) f = __ldcg(&p.found[item]);
-                        f = __shfl_sync(FULL, f, 0);
-                        const uint32_t fa = (uint32_t)(f >> 8);
-                        if (f != FOUND_NONE && fa < pool_end) {
-                            pool_end = pool_end < fa ? pool_end : fa;
-                            pool_next = pool_next < pool_end ? pool_next : pool_end;
-                            if (active && my_item == item && w.a > fa) active = false;
-                            idle = __ballot_sync(FULL, !active);
-                        }
-                    }
-                    if (idle && pool_next < pool_end) {
-                        /* idle lanes draw the next attempt indices of the pool (ballot only, no memory traffic) */
-                        const uint32_t avail = pool_end - pool_next;
-                        const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-                        if (!active && rank < avail) {
-                            const uint32_t a = pool_next + rank;
-                            my_item = item; my_y = y; my_cens = cens; my_og = og;
-                            walk_begin(w, a, first_off && a == a_first, og, p, iter);
-                            active = true;
-                        }
-                        const uint32_t cnt = __popc(idle);
-                        pool_next += cnt < avail ? cnt : avail;
-                    }
-                    bool survived = false;
-                    __syncwarp();           /* lanes that have just drawn an attempt step together with the rest */
-                    if (active) {
-                        const bool ended = walk_step<false>(w, my_y, my_cens, my_og, p, sm, iter, n, norec);
-                        c_jumps++;
-                        c_attempts += ended ? 1u : 0u;
-                        survived = ended && (w.t >= my_y) && ((smask >> w.j) & 1u);
-                        active = !ended;
-                    }
-                    const unsigned smk = __ballot_sync(FULL, survived);
-                    if (smk) {
-                        /* every survivor competes for "lowest surviving attempt" of its observation; the first one in
-                         * the warp also calls off the later attempts of the same observation that are in flight here */
-                        if (survived) atomicMin(&p.found[my_item], ((unsigned long long)w.a << 8) | (unsigned long long)w.j);
-                        const int src = __ffs(smk) - 1;
-                        const uint32_t s_item = __shfl_sync(FULL, my_item, src), s_a = __shfl_sync(FULL, w.a, src);
-                        if (active && my_item == s_item && w.a > s_a) active = false;
-                        if (s_item == item && pool_next < pool_end) {
-                            pool_end = pool_end < s_a ? pool_end : s_a;
-                            pool_next = pool_next < pool_end ? pool_next : pool_end;
-                        }
-                    }
-                }
+    if (blockIdx.x == 0) {
+        const int t = threadIdx.x;
+        if (t < (int)p.obs_world && p.state->xdead == 0u) {
+            volatile unsigned long long *mine = &p.xpeer[t]->flags[p.obs_rank];
+            __threadfence_system();
+            *mine = epoch;
+            __threadfence_system();
+            volatile unsigned long long *theirs = &p.xw->flags[t];
+            const unsigned long long t0 = gtimer();
+            while (*theirs < epoch) {
+                if (gtimer() - t0 > XBAR_TIMEOUT_NS) { p.state->xdead = 1u; atomicOr(&p.state->error, 64); break; }
             }
-            grid.sync();
-            /* --- advance each pending observation's MH state machine (eq_Bladt_MHRS.c:65-101) */
-            for (unsigned long long i = gtid; i < P; i += gsize) {
-                const uint32_t item = pend[i];
-                TailItem it = p.items[item];
-                const unsigned long long f = p.found[item];
-                bool done = false;
-                bool dropped = false;
-                if (f == FOUND_NONE) {
-                    if (it.a > 0xF0000000u - K) { atomicOr(&p.state->error, 8); dropped = true; }   /* survival probability ~ 0 */
-                    it.a += K; it.flags &= ~4u;
-                    if (!dropped) atomicOr(&p.state->any_fail, 1u);
-                }
-                else {
-                    const uint32_t a = (uint32_t)(f >> 8); const int pre = (int)(f & 0xffull);
-                    const bool off = (a == it.a) && (it.flags & 4u);
-                    const bool cens = p.cens[it.obs_local] != 0;
-                    bool have_cur = it.flags & 1u; bool cur_off = it.flags & 2u;
-                    int cur_pre = (int)((it.flags >> 8) & 0xffu); uint32_t kprop = it.flags >> 16;
-                    bool next_off = false;
-                    if (!have_cur) {
-                        have_cur = true; it.cur_a = a; cur_off = off; cur_pre = pre;
-                        done = cens || p.mhit == 0;
-                    } else {
-                        const uint32_t og = p.obs_rank + it.obs_local * p.obs_world;
-                        pht_u32x4 r = philox_block(0u, a + 1u, og, iter, p);
-                        const double U = pht_u01(r.v[0], r.v[1]);
-                        if (U < s_model[pre] / s_model[cur_pre]) { it.cur_a = a; cur_off = off; cur_pre = pre; }
-                        kprop++; done = (int)kprop >= p.mhit; next_off = true;
-                    }
-                    it.a = a + 1u;
-                    it.flags = pack_flags(have_cur, cur_off, next_off, cur_pre, (int)kprop);
-                    p.found[item] = FOUND_NONE;
-                }
-                p.items[item] = it;
-                if (dropped) continue;
-                if (done) p.done[atomicAdd(&p.state->n_done, 1u)] = item;
-                else pend_next[atomicAdd(&p.state->n_pend[cur ^ 1], 1u)] = item;
-            }
-            if (gtid == 0) { p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; }
-            grid.sync();
-            /* the attempts per observation grow only when some observation needed more than this round offered: with
-             * mhit > 1 every pending observation comes back round after round for its next proposal, and a K that kept
-             * doubling would bury the round in pools to skip */
-            const bool grow = p.state->any_fail != 0u;
-            grid.sync();
-            if (gtid == 0) p.state->any_fail = 0u;
-            cur ^= 1; rounds++;
-            K = (grow && K < TAIL_KMAX) ? K * TAIL_GROWTH : K;
+            __threadfence_system();
         }
-        if (timekeeper) { const unsigned long long t = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_TAIL], t - t_mark); t_mark = t; }
-        /* --- replay the accepted attempt of every tail observation */
-        {
-            const uint32_t n_done = p.state->n_done;
-            for (unsigned long long i = gtid; i < n_done; i += gsize) {
-                const TailItem it = p.items[p.done[i]];
-                c_jumps += replay_path(it.obs_local, it.cur_a, (it.flags & 2u) != 0u, p.y[it.obs_local], p.cens[it.obs_local] != 0, p, sm, iter, n);
-                c_paths++;
-            }
-        }
-        if (gtid == 0) atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
-        if (timekeeper) atomicAdd(&p.state->counters[PHT_CNT_NS_REPLAY], gtimer() - t_mark);
     }
+    grid.sync();
+}
 
-    /* ---------------------------------------------------------------- block -> global statistics */
+/* ------------------------------------------------------------------------------------------ tail search
+ * One round: K attempts for each of the P pending observations.  Units are numbered chunk-major: local chunk c
+ * covers attempt block q = c / Pl of the observation in column i = c % Pl, so every observation's first chunk is
+ * handed out before any second chunk, and later chunks are mostly skipped once an earlier one has survived.
+ * Local rounds: Pl = P, column i is pend[i].  Global rounds (W ranks): Pl = ceil(P / W), column i of block q is
+ * observation i W + (rank - q) mod W, i.e. block q of observation o is searched by rank (o + q) mod W. */
+struct TailView {
+    TailItem *items; const uint32_t *pend; unsigned long long *found; uint32_t P, K;
+    bool global; uint32_t parity;
+};
+
+template <int NC>
+__device__ __forceinline__ void tail_search(const TailView &tv, const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n,
+                                            uint32_t smask, uint32_t nwarps,
+                                            unsigned &c_jumps, unsigned &c_attempts) {
+    const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
+    const uint32_t W = tv.global ? p.obs_world : 1u;
+    const uint32_t Pl = (tv.P + W - 1u) / W;
+    const unsigned long long total_units = (unsigned long long)Pl * tv.K;
+    /* per lane: the batch [f.a, a_end) of consecutive attempts of observation my_item it is working through */
+    Fast f; fast_begin(f, 0u, n);
+    ObsF mo; obs_set(mo, 0.0f, 0u, false);
+    const double inv_smax = sm.inv_smax;
+    double my_y = 0.0; uint32_t my_item = 0xFFFFFFFFu, a_end = 0u; bool active = false;
+    unsigned steps = 0;
+    /* warp-uniform: the units this warp holds, and the pool being handed out */
+    unsigned long long u_next = 0, u_end = 0, last_base = 0;
+    bool out_of_units = false, finished = false;
+    uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; double y = 0.0; float yf = 0.0f; bool cens = false, first_off = false;
+    while (!finished) {
+        /* ---- the search loop proper: no calls in here (the exact walker is asked from outside, see below) */
+        bool want_exact = false, exact_off = false, survived = false; int kend = 0;
+        for (;;) {
+            unsigned idle = __ballot_sync(FULL, !active);
+            if (idle) {
+                if (pool_next >= pool_end && !out_of_units) {
+                    /* take the next pool (skipping pools that an earlier survivor made moot) */
+                    bool have = false;
+                    while (!have) {
+                        if (u_next >= u_end) {
+                            const unsigned long long remaining = total_units > last_base ? total_units - last_base : 0ull;
+                            unsigned long long want = remaining / (2ull * (unsigned long long)nwarps);
+                            want = want < POOL_MIN ? POOL_MIN : (want > POOL_MAX ? POOL_MAX : want);
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(&p.state->unit_counter, want);
+                            base = __shfl_sync(FULL, base, 0);
+                            last_base = base;
+                            if (base >= total_units) { out_of_units = true; break; }
+                            u_next = base; u_end = base + want < total_units ? base + want : total_units;
+                        }
+                        const unsigned long long chunk = u_next / TAIL_CH;
+                        const unsigned long long chunk_end_u = (chunk + 1ull) * TAIL_CH;
+                        const unsigned long long stop = u_end < chunk_end_u ? u_end : chunk_end_u;
+                        const uint32_t q = (uint32_t)(chunk / Pl), col = (uint32_t)(chunk % Pl);
+                        const uint32_t o = tv.global ? col * W + (p.obs_rank + W - q % W) % W : col;
+                        const uint32_t within = (uint32_t)(u_next - chunk * TAIL_CH), len = (uint32_t)(stop - u_next);
+                        u_next = stop;
+                        if (o >= tv.P) continue;
+                        item = tv.pend[o];
+                        const TailItem it = tv.items[item];
+                        if (it.flags & TI_FIN) continue;
+                        a_first = it.a; first_off = (it.flags & TI_OFF) != 0u;
+                        pool_next = it.a + q * TAIL_CH + within;
+                        pool_end = pool_next + len;
+                        if ((__ldcg(&tv.found[item]) >> 8) >= (unsigned long long)pool_next) {
+                            have = true;
+                            y = it.y; yf = (float)(y * inv_smax); cens = (it.flags & TI_CENS) != 0u; og = it.og;
+                        } else pool_end = pool_next;
+                    }
+                }
+                if (idle == FULL && pool_next >= pool_end) { finished = true; break; }      /* nothing in flight, nothing left to hand out */
+                if (pool_next < pool_end) {
+                    /* idle lanes take a batch of consecutive attempts each (ballot only, no memory traffic): a small pool
+                     * is spread over them, a large one is handed out TAIL_BATCH attempts at a time */
+                    const uint32_t avail = pool_end - pool_next, nidle = __popc(idle);
+                    uint32_t bsz = (avail + nidle - 1u) / nidle; bsz = bsz > TAIL_BATCH ? TAIL_BATCH : bsz;
+                    const uint32_t a0 = pool_next + (uint32_t)__popc(idle & ((1u << lane) - 1u)) * bsz;
+                    if (!active && a0 < pool_end) {
+                        a_end = a0 + bsz < pool_end ? a0 + bsz : pool_end;
+                        my_item = item; my_y = y; obs_set(mo, yf, og, cens);
+                        fast_begin(f, a0, n);
+                        /* the attempt that starts one draw into its sub-stream (after an MH accept test) is the exact walker's */
+                        if (first_off && a0 == a_first) { want_exact = true; exact_off = true; } else active = true;
+                    }
+                    const uint32_t take = nidle * bsz;
+                    pool_next += take < avail ? take : avail;
+                }
+            }
+            /* Every FOUND_PERIOD steps, look whether someone (another warp, another GPU) has found a surviving attempt
+             * of the pool's observation: everything above it is moot. */
+            if (((++steps) & (FOUND_PERIOD - 1u)) == 0u) {
+                unsigned long long fw = 0;
+                if (lane == 0) fw = __ldcg(&tv.found[item]);
+                fw = __shfl_sync(FULL, fw, 0);
+                if (fw != FOUND_NONE) {
+                    const uint32_t fa = (uint32_t)(fw >> 8);
+                    if (pool_next < pool_end && fa < pool_end) { pool_end = pool_end < fa ? pool_end : fa; pool_next = pool_next < pool_end ? pool_next : pool_end; }
+                    if (my_item == item) { a_end = a_end < fa ? a_end : fa; if (f.a > fa) active = false; }
+                }
+            }
+            __syncwarp();           /* lanes that have just drawn a batch step together with the rest */
+            if (active) {
+                bool fail, surv, amb; int k;
+                fast_step(f, mo, p, sm, iter, n, fail, surv, amb, k);
+                c_jumps++;
+                if (surv && !((smask >> k) & 1u)) { surv = false; fail = true; }     /* alive at y in a state that cannot exit: failed */
+                if (fail) {
+                    c_attempts++;
+                    const uint32_t na = f.a + 1u;
+                    if (na < a_end) fast_begin(f, na, n); else active = false;
+                } else if (surv) { c_attempts++; survived = true; kend = k; active = false; }
+                else if (amb) { want_exact = true; active = false; }
+            }
+            if (__any_sync(FULL, survived || want_exact)) break;
+        }
+        if (finished) break;
+        /* ---- attempts the filter could not decide (or that start off the block boundary): the exact walker */
+        if (want_exact) {
+            const uint32_t res = exact_attempt(f.a, exact_off, my_y, mo.cens, mo.og, p, sm, iter, n, smask);
+            c_jumps += res >> 16; c_attempts++;
+            survived = res & 1u; kend = (int)((res >> 8) & 0xffu);
+            if (!survived) {
+                const uint32_t na = f.a + 1u;
+                if (na < a_end) { fast_begin(f, na, n); active = true; }
+            }
+        }
+        /* ---- every survivor competes for "lowest surviving attempt" of its observation (on every rank in a global
+         * round); the first one in the warp also calls off the later attempts of the same observation in flight here */
+        const unsigned smk = __ballot_sync(FULL, survived);
+        if (survived) {
+            const unsigned long long word = ((unsigned long long)f.a << 8) | (unsigned long long)kend;
+            atomicMin(&tv.found[my_item], word);
+            if (tv.global) {
+                for (uint32_t r = 0; r < p.obs_world; r++)
+                    if (r != p.obs_rank) atomicMin_system(&p.xpeer[r]->gfound[tv.parity][my_item], word);
+                __threadfence_system();
+            }
+        }
+        if (smk) {
+            const int src = __ffs(smk) - 1;
+            const uint32_t s_item = __shfl_sync(FULL, my_item, src), s_a = __shfl_sync(FULL, f.a, src);
+            if (my_item == s_item) { a_end = a_end < s_a ? a_end : s_a; if (active && f.a > s_a) active = false; }
+            if (s_item == item && pool_next < pool_end) {
+                pool_end = pool_end < s_a ? pool_end : s_a;
+                pool_next = pool_next < pool_end ? pool_next : pool_end;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+/* advance one pending observation's MH state machine after a round (eq_Bladt_MHRS.c:65-101); returns 0 = still
+ * pending, 1 = finished (accepted attempt known), 2 = dropped */
+MHRS_COLD int tail_advance(TailItem &it, unsigned long long fword, uint32_t K, const SweepParams &p,
+                                            const double *s_model, uint32_t iter, bool &failed) {
+    failed = false;
+    if (fword == FOUND_NONE) {
+        failed = true;
+        if (it.a > 0xF0000000u - K) return 2;              /* survival probability ~ 0: see DESIGN.md */
+        it.a += K; it.flags &= ~TI_OFF;
+        return 0;
+    }
+    const uint32_t a = (uint32_t)(fword >> 8); const int pre = (int)(fword & 0xffull);
+    const bool off = (a == it.a) && (it.flags & TI_OFF);
+    const bool cens = (it.flags & TI_CENS) != 0u;
+    bool have_cur = it.flags & TI_HAVE; bool cur_off = it.flags & TI_CUROFF;
+    int cur_pre = (int)((it.flags >> 8) & 0xffu); uint32_t kprop = it.flags >> 16;
+    bool next_off = false, done;
+    if (!have_cur) {
+        have_cur = true; it.cur_a = a; cur_off = off; cur_pre = pre;
+        done = cens || p.mhit == 0;
+    } else {
+        pht_u32x4 r = philox_block(0u, a + 1u, it.og, iter, p);
+        const double U = pht_u01(r.v[0], r.v[1]);
+        if (U < s_model[pre] / s_model[cur_pre]) { it.cur_a = a; cur_off = off; cur_pre = pre; }
+        kprop++; done = (int)kprop >= p.mhit; next_off = true;
+    }
+    it.a = a + 1u;
+    it.flags = pack_flags(have_cur, cur_off, next_off, cens, cur_pre, kprop);
+    return done ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------------------------------ lane phase
+ * Persistent warps, one observation per lane, in layout order from a global counter. */
+#define LF_RUN 1u        /* the lane holds an observation and walks */
+#define LF_HAVE 2u       /* a first surviving attempt is known (mh_cur_a / mh_misc) */
+#define LF_CENS 4u
+#define LF_NVALID 8u     /* the prefetch slot holds an observation */
+#define LF_NCENS 16u
+template <int NC>
+__device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n, uint32_t smask,
+                                           uint32_t obs_begin, uint32_t obs_end, uint32_t cap,
+                                           unsigned &c_jumps, unsigned &c_attempts) {
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Fast f; fast_begin(f, 0u, n);
+    ObsF o; obs_set(o, 0.0f, 0u, false);
+    const double inv_smax = sm.inv_smax;
+    uint32_t pos = 0, a_lim = cap, fl = 0u;
+    bool dry = false;                     /* warp-uniform: the observation stream has run out */
+    for (;;) {
+        /* ---- refill the prefetch slots, eight or more at a time */
+        const unsigned empty = __ballot_sync(FULL, !(fl & LF_NVALID));
+        if (!dry && __popc(empty) >= PREFETCH_MIN) {
+            const unsigned cnt = __popc(empty);
+            unsigned long long base = 0;
+            if (lane == 0) base = (unsigned long long)obs_begin + atomicAdd(&p.state->next_obs, (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            const unsigned long long left = base < obs_end ? (unsigned long long)obs_end - base : 0ull;
+            const unsigned avail = left < cnt ? (unsigned)left : cnt;
+            if (avail < cnt) dry = true;
+            const unsigned rank = __popc(empty & ((1u << lane) - 1u));
+            if (!(fl & LF_NVALID) && rank < avail) {
+                const unsigned long long q = base + rank;
+                sm.pf_pos[tid] = (uint32_t)q; sm.pf_yf[tid] = (float)(p.y[q] * inv_smax);
+                sm.pf_og[tid] = p.obs_rank + (p.perm ? p.perm[q] : (uint32_t)q) * p.obs_world;
+                fl |= LF_NVALID | (p.cens[q] != 0 ? LF_NCENS : 0u);
+            }
+        }
+        if (!(fl & LF_RUN) && (fl & LF_NVALID)) {
+            obs_set(o, sm.pf_yf[tid], sm.pf_og[tid], (fl & LF_NCENS) != 0u); pos = sm.pf_pos[tid];
+            fl = LF_RUN | (o.cens ? LF_CENS : 0u);
+            sm.mh_cur_a[tid] = 0u; sm.mh_misc[tid] = 0u; a_lim = cap;
+            fast_begin(f, 0u, n);
+        }
+        if (__ballot_sync(FULL, fl & LF_RUN) == 0u) { if (dry) break; else continue; }
+        if (dry && a_lim != 0xFFFFFFFFu && a_lim > END_CAP) a_lim = END_CAP;      /* a lone lane must not hold the grid */
+        __syncwarp();
+        /* ---- the search loop proper: steps until some lane has something to report.  No calls, nothing but the
+         * filter walk, in here; a failed attempt restarts on the next sub-stream on the spot. */
+        bool surv = false, amb = false, hand = false; int k = 0;
+        const bool run = (fl & LF_RUN) != 0u;
+        do {
+            if (run) {
+                bool fail;
+                fast_step(f, o, p, sm, iter, n, fail, surv, amb, k);
+                c_jumps++;
+                if (fail) { fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
+            }
+        } while (!__any_sync(FULL, surv || amb || hand));
+        /* ---- events, a few lanes at a time */
+        if (amb) {
+            const uint32_t res = exact_attempt(f.a, false, p.y[pos], o.cens, o.og, p, sm, iter, n, ~0u);
+            surv = res & 1u; k = (int)((res >> 8) & 0xffu); c_jumps += res >> 16;
+            if (!surv) { fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
+#ifdef MHRS_DEBUG_COUNTERS
+            atomicAdd(&p.state->counters[18], 1ull);
+#endif
+        }
+        /* survived to y in a state that cannot exit: a failed attempt (eq_Bladt_MHRS.c:66,74) */
+        if (surv && !((smask >> k) & 1u)) { surv = false; fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
+        bool this_off = false;
+        while (surv) {
+            c_attempts++;
+            bool complete = false; uint32_t rfl = 0u, ra1 = 0u, ra2 = 0u;
+            uint32_t cur_a = sm.mh_cur_a[tid], misc = sm.mh_misc[tid];
+            int cur_pre = (int)(misc & 0xffu); bool cur_off = (misc >> 8) & 1u; uint32_t kprop = misc >> 16;
+            if (!(fl & LF_HAVE)) {
+                fl |= LF_HAVE; cur_a = f.a; cur_off = this_off; cur_pre = k;
+                if (o.cens || p.mhit == 0) { complete = true; ra1 = cur_a; rfl = cur_off ? RF_OFF : 0u; }        /* :70 */
+            } else if (p.mhit == 1) {
+                /* the one proposal: its accept test is left to the replay session (whole warp at once) */
+                complete = true; ra1 = cur_a; ra2 = f.a;
+                rfl = RF_PROP | ((uint32_t)cur_pre << 8) | ((uint32_t)k << 16);
+            } else {
+                /* a valid proposal: accept test with draw 0 of the next sub-stream (:79-82) */
+                pht_u32x4 r = philox_block(0u, f.a + 1u, o.og, iter, p);
+                const double U = pht_u01(r.v[0], r.v[1]);
+                if (U < sm.s[k] / sm.s[cur_pre]) { cur_a = f.a; cur_off = this_off; cur_pre = k; }
+                kprop++;
+                if ((int)kprop >= p.mhit) { complete = true; ra1 = cur_a; rfl = cur_off ? RF_OFF : 0u; }
+            }
+            sm.mh_cur_a[tid] = cur_a; sm.mh_misc[tid] = (uint32_t)cur_pre | (cur_off ? 0x100u : 0u) | (kprop << 16);
+            if (complete) {
+                const unsigned e = warp * RING + atomicAdd(&sm.ring_n[warp], 1u);
+                sm.ring_y[e] = p.y[pos]; sm.ring_pos[e] = pos; sm.ring_og[e] = o.og; sm.ring_a1[e] = ra1; sm.ring_a2[e] = ra2;
+                sm.ring_fl[e] = rfl | (o.cens ? RF_CENS : 0u);
+                fl &= ~LF_RUN; surv = false;
+            } else if (kprop == 0u) {
+                /* first survivor of an exact observation: go on to the proposal search */
+                fast_begin(f, f.a + 1u, n); surv = false;
+            } else {
+                /* next proposal: sub-stream a+1 from draw 1 (draw 0 was the accept uniform) */
+                const uint32_t a = f.a + 1u;
+                const uint32_t res = exact_attempt(a, true, p.y[pos], o.cens, o.og, p, sm, iter, n, smask);
+                surv = res & 1u; k = (int)((res >> 8) & 0xffu); c_jumps += res >> 16;
+                this_off = true;
+                if (!surv) c_attempts++;
+                fast_begin(f, surv ? a : a + 1u, n);
+            }
+        }
+        if (hand && (fl & LF_RUN)) {
+            const uint32_t idx = atomicAdd(&p.state->n_items, 1u);
+            if (idx < p.item_cap) {
+                const uint32_t misc = sm.mh_misc[tid];
+                TailItem it; it.y = p.y[pos]; it.og = o.og; it.pos = pos; it.a = f.a; it.cur_a = sm.mh_cur_a[tid];
+                it.flags = pack_flags((fl & LF_HAVE) != 0u, (misc >> 8) & 1u, false, o.cens, (int)(misc & 0xffu), misc >> 16);
+                it.owner = p.obs_rank;
+                p.items[idx] = it; p.found[idx] = FOUND_NONE;
+                atomicAdd(&p.state->counters[PHT_CNT_DEFERRED], 1ull);
+#ifdef MHRS_DEBUG_COUNTERS
+                if (dry) atomicAdd(&p.state->counters[19], 1ull);
+#endif
+                fl &= ~LF_RUN;
+            } else a_lim = 0xFFFFFFFFu;          /* no room: the lane keeps the observation */
+        }
+        __syncwarp();
+        if (sm.ring_n[warp] >= RING_TRIGGER) c_jumps += replay_session(p, sm, iter, n, warp);
+    }
+    c_jumps += replay_session(p, sm, iter, n, warp);
+}
+
+/* block accumulators and per-thread event counts -> global memory */
+template <int NC>
+__device__ __forceinline__ void flush_block(const SweepParams &p, MhrsSmem<NC> &sm, int n, bool per_obs, unsigned c_attempts, unsigned c_jumps) {
+    const unsigned FULL = 0xffffffffu; const int tid = threadIdx.x;
     __syncthreads();
     if (!per_obs) {
         unsigned long long *gN = reinterpret_cast<unsigned long long *>(p.stats);
         for (int i = tid; i < n * n; i += MHRS_THREADS) if (sm.Nacc[i]) atomicAdd(&gN[i], (unsigned long long)sm.Nacc[i]);
         for (int i = tid; i < n; i += MHRS_THREADS) {
             if (sm.Bacc[i]) atomicAdd(&gN[n * n + i], (unsigned long long)sm.Bacc[i]);
-            if (sm.zacc[i]) atomicAdd(&gN[n * n + n + i], (unsigned long long)sm.zacc[i]);
+            if (sm.zlo[i]) atomicAdd(&gN[n * n + n + i], sm.zlo[i]);
+            if (sm.zhi[i]) atomicAdd(&gN[n * n + 2 * n + i], (unsigned long long)sm.zhi[i]);
         }
     }
-    unsigned long long w_attempts = c_attempts, w_jumps = c_jumps, w_paths = c_paths, w_deferred = c_deferred;
-    for (int o = 16; o > 0; o >>= 1) {
-        w_attempts += __shfl_down_sync(FULL, w_attempts, o); w_jumps += __shfl_down_sync(FULL, w_jumps, o);
-        w_paths += __shfl_down_sync(FULL, w_paths, o); w_deferred += __shfl_down_sync(FULL, w_deferred, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&p.state->counters[PHT_CNT_ATTEMPTS], w_attempts); atomicAdd(&p.state->counters[PHT_CNT_JUMPS], w_jumps);
-        atomicAdd(&p.state->counters[PHT_CNT_PATHS], w_paths); atomicAdd(&p.state->counters[PHT_CNT_DEFERRED], w_deferred);
-    }
+    unsigned long long w_attempts = c_attempts, w_jumps = c_jumps;
+    for (int o = 16; o > 0; o >>= 1) { w_attempts += __shfl_down_sync(FULL, w_attempts, o); w_jumps += __shfl_down_sync(FULL, w_jumps, o); }
+    if ((tid & 31) == 0) { atomicAdd(&p.state->counters[PHT_CNT_ATTEMPTS], w_attempts); atomicAdd(&p.state->counters[PHT_CNT_JUMPS], w_jumps); }
+    if (tid == 0 && sm.paths_done) atomicAdd(&p.state->counters[PHT_CNT_PATHS], (unsigned long long)sm.paths_done);
 }
 
-int pht_mhrs_grid_blocks(int device, int n) {
-    int per_sm = 0, sms = 0;
-    const size_t smem = pht_mhrs_smem_bytes(n);
-    if (cudaFuncSetAttribute(k_mhrs_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mhrs_sweep, MHRS_THREADS, smem) != cudaSuccess) return -1;
+/* states that can exit: bit j of smask (the accept tests of eq_Bladt_MHRS.c:66,74 need s[j] != 0) */
+template <int NC>
+__device__ __forceinline__ void model_scalars(const MhrsSmem<NC> &sm, int n, uint32_t &smask) {
+    smask = 0u;
+    for (int i = 0; i < n; i++) smask |= (sm.s[i] != 0.0) ? (1u << i) : 0u;
+}
+
+/* Kernel 1 of the MHRS sweep: the lane phase (an ordinary launch; its own register budget). */
+template <int NC>
+__global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_lanes(const __grid_constant__ SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MhrsSmem<NC> &sm = *reinterpret_cast<MhrsSmem<NC> *>(smem_raw);
+    const int n = p.n;
+    const uint32_t iter = p.state->iter;
+    const unsigned long long t0 = (blockIdx.x == 0 && threadIdx.x == 0) ? gtimer() : 0ull;
+    build_tables(p, sm, n, ModelLayout::make(n, p.m));
+    uint32_t smask;
+    model_scalars(sm, n, smask);
+    const bool per_obs = p.outB != nullptr;
+    const uint32_t obs_begin = per_obs ? (uint32_t)p.first : 0u;
+    const uint32_t obs_end = per_obs ? (uint32_t)(p.first + p.count) : (uint32_t)p.l_local;
+    const uint32_t cap = p.mhrs_cap > 0 ? (uint32_t)p.mhrs_cap : 256u;
+    unsigned c_attempts = 0, c_jumps = 0;      /* per thread and sweep: far below 2^32 */
+    lane_phase(p, sm, iter, n, smask, obs_begin, obs_end, cap, c_jumps, c_attempts);
+#ifdef MHRS_DEBUG_COUNTERS
+    atomicAdd(&p.state->counters[17], (unsigned long long)c_attempts);
+#endif
+    flush_block(p, sm, n, per_obs, c_attempts, c_jumps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.state->counters[PHT_CNT_NS_LANE], gtimer() - t0);
+}
+
+/* Kernel 2: the tail (cooperative launch: grid barriers between rounds; peer barriers in global rounds). */
+template <int NC>
+__global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tail(const __grid_constant__ SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    MhrsSmem<NC> &sm = *reinterpret_cast<MhrsSmem<NC> *>(smem_raw);
+    const int n = p.n, tid = threadIdx.x;
+    const uint32_t iter = p.state->iter;
+    const bool per_obs = p.outB != nullptr;
+    const bool multi = p.xw != nullptr && p.obs_world > 1u && !per_obs;
+    const uint32_t n_items = p.state->n_items < p.item_cap ? p.state->n_items : p.item_cap;
+    if (n_items == 0u && !multi) return;                  /* every observation finished in its lane */
+    const bool timekeeper = (blockIdx.x == 0 && tid == 0);
+    unsigned long long t_mark = timekeeper ? gtimer() : 0ull;
+    build_tables(p, sm, n, ModelLayout::make(n, p.m));
+    uint32_t smask;
+    model_scalars(sm, n, smask);
+    const double *s_model = p.model + ModelLayout::make(n, p.m).s;
+    unsigned c_attempts = 0, c_jumps = 0;
+    const uint32_t gtid = blockIdx.x * MHRS_THREADS + tid, gsize = gridDim.x * MHRS_THREADS, nwarps = gsize / 32u;
+
+    for (uint32_t i = gtid; i < n_items; i += gsize) p.pend0[i] = i;
+    if (gtid == 0) {
+        p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u;
+        p.state->any_fail[0] = 0u; p.state->any_fail[1] = 0u;
+    }
+    grid.sync();
+    /* One loop for both kinds of round.  LOCAL: this rank's pending observations, lists double-buffered and
+     * compacted every round.  GLOBAL (several GPUs, from K = k_switch on): the observations still pending on any
+     * rank, gathered once into every rank's exchange window in a canonical order that never changes (finished
+     * items are flagged and skipped), searched by all ranks, advanced by every rank redundantly. */
+    /* round 0 offers every pending observation as many attempts as its lane has already spent on it */
+    uint32_t K = TAIL_K0; while (K < (uint32_t)p.mhrs_cap && K < TAIL_KMAX) K *= 2u;
+    uint32_t rounds = 0u, g0 = 0u, Pg = 0u; int cur = 0; bool global = false;
+    const uint32_t W = p.obs_world, me = p.obs_rank, sp = iter & 1u;
+    unsigned long long epoch = multi ? p.state->xepoch : 0ull;
+    for (;;) {
+        const uint32_t *pend = cur ? p.pend1 : p.pend0;
+        uint32_t *pend_next = cur ? p.pend0 : p.pend1;
+        if (!global) {
+            const uint32_t P = p.state->n_pend[cur];
+            const bool leave = P == 0u || (multi && K >= p.k_switch && P <= PHT_GCAP);
+            if (leave && !multi) break;
+            if (leave) {
+                /* ---- gather: my pending items into every rank's window (mine included), then the canonical list */
+                if (timekeeper) { const unsigned long long t = gtimer(); atomicAdd(&p.state->counters[PHT_CNT_NS_TAIL], t - t_mark); t_mark = t; }
+                for (uint32_t r = 0; r < W; r++) {
+                    XchgWindow *dst = p.xpeer[r];
+                    for (uint32_t i = gtid; i < P; i += gsize) dst->gitems[sp][me * PHT_GCAP + i] = p.items[pend[i]];
+                    if (gtid == 0) dst->gcount[sp][me] = P;
+                }
+                peer_barrier(grid, p, ++epoch);
+                for (uint32_t r = 0; r < W; r++) {
+                    const uint32_t c = p.xw->gcount[sp][r] <= PHT_GCAP ? p.xw->gcount[sp][r] : PHT_GCAP;
+                    for (uint32_t i = gtid; i < c; i += gsize) p.glist[Pg + i] = r * PHT_GCAP + i;
+                    Pg += c;
+                }
+                if (gtid == 0) { p.state->n_gpend = Pg; p.state->unit_counter = 0ull; p.state->any_fail[0] = 0u; p.state->any_fail[1] = 0u; }
+                grid.sync();
+                global = true; g0 = rounds;
+                K = p.k_switch > TAIL_K0 ? p.k_switch : TAIL_K0;
+                continue;
+            }
+        } else if (p.state->n_gpend == 0u || p.state->xdead != 0u) break;
+        const uint32_t par = (rounds - g0) & 1u;
+        TailView tv;
+        if (!global) { tv.items = p.items; tv.pend = pend; tv.found = p.found; tv.P = p.state->n_pend[cur]; }
+        else { tv.items = p.xw->gitems[sp]; tv.pend = p.glist; tv.found = p.xw->gfound[par]; tv.P = Pg; }
+        tv.K = K; tv.global = global; tv.parity = par;
+        tail_search(tv, p, sm, iter, n, smask, nwarps, c_jumps, c_attempts);
+        if (global) peer_barrier(grid, p, ++epoch); else grid.sync();
+        /* ---- advance each pending observation's MH state machine (eq_Bladt_MHRS.c:65-101); in a global round every
+         * rank advances every item: same inputs, same outcome */
+        for (uint32_t i = gtid; i < tv.P; i += gsize) {
+            const uint32_t item = tv.pend[i];
+            TailItem it = tv.items[item];
+            if (it.flags & TI_FIN) continue;
+            bool failed;
+            const int st = tail_advance(it, tv.found[item], K, p, s_model, iter, failed);
+            tv.found[item] = FOUND_NONE;
+            if (st != 0 && global) it.flags |= TI_FIN;
+            tv.items[item] = it;
+            const bool mine = !global || it.owner == me;
+            if (st == 2 && mine) { atomicAdd(&p.state->counters[PHT_CNT_ERRORS], 1ull); atomicOr(&p.state->error, 8); }
+            if (failed && st == 0) atomicOr(&p.state->any_fail[par], 1u);
+            if (global) {
+                if (st != 0) atomicSub(&p.state->n_gpend, 1u);
+                if (st == 1 && mine) {
+                    /* back into my own list for the replay */
+                    const uint32_t back = pend[item - me * PHT_GCAP];
+                    p.items[back] = it;
+                    p.done[atomicAdd(&p.state->n_done, 1u)] = back;
+                }
+            } else if (st == 1) p.done[atomicAdd(&p.state->n_done, 1u)] = item;
+            else if (st == 0) pend_next[atomicAdd(&p.state->n_pend[cur ^ 1], 1u)] = item;
+        }
+        if (gtid == 0) { if (!global) p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; p.state->any_fail[par ^ 1u] = 0u; }
+        grid.sync();
+        /* the attempts per observation grow only when some observation needed more than this round offered: with
+         * mhit > 1 every pending observation comes back round after round for its next proposal, and a K that kept
+         * doubling would bury the round in pools to skip */
+        const bool grow = p.state->any_fail[par] != 0u;
+        if (!global) cur ^= 1;
+        rounds++;
+        K = (grow && K < TAIL_KMAX) ? K * TAIL_GROWTH : K;
+    }
+    if (multi && gtid == 0) { p.state->xepoch = epoch; p.state->n_pend[cur] = 0u; }
+    if (timekeeper) {
+        const unsigned long long t = gtimer();
+        atomicAdd(&p.state->counters[global ? PHT_CNT_NS_GLOBAL : PHT_CNT_NS_TAIL], t - t_mark); t_mark = t;
+    }
+    /* ---- replay the accepted attempt of every tail observation this rank owns */
+    grid.sync();
+    {
+        c_jumps += replay_done_list(p, sm, iter, n, p.state->n_done, gtid / 32u, nwarps);
+    }
+    if (gtid == 0) atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
+    if (timekeeper) atomicAdd(&p.state->counters[PHT_CNT_NS_REPLAY], gtimer() - t_mark);
+    flush_block(p, sm, n, per_obs, c_attempts, c_jumps);
+}
+
+/* ------------------------------------------------------------------------------------------ host side */
+template <int NC>
+static int grid_blocks_of(int device, int *lane_blocks, int *tail_blocks) {
+    int a = 0, b = 0, sms = 0;
+    const size_t smem = sizeof(MhrsSmem<NC>);
+    if (cudaFuncSetAttribute(k_mhrs_lanes<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_mhrs_tail<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_mhrs_lanes<NC>, MHRS_THREADS, smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_mhrs_tail<NC>, MHRS_THREADS, smem) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-    return per_sm * sms;
+    *lane_blocks = a * sms; *tail_blocks = b * sms;
+    return (a > 0 && b > 0) ? 0 : -1;
+}
+/* grid sizes: every SM full of resident blocks of each kernel (persistent warps; the tail launch is cooperative) */
+int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks) {
+    if (n <= 8) return grid_blocks_of<8>(device, lane_blocks, tail_blocks);
+    if (n <= 16) return grid_blocks_of<16>(device, lane_blocks, tail_blocks);
+    return grid_blocks_of<32>(device, lane_blocks, tail_blocks);
+}
+size_t pht_mhrs_smem_bytes(int n) {
+    return n <= 8 ? sizeof(MhrsSmem<8>) : (n <= 16 ? sizeof(MhrsSmem<16>) : sizeof(MhrsSmem<32>));
 }
 
-cudaError_t pht_launch_mhrs(const SweepParams &p, int grid_blocks, cudaStream_t st) {
+cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, cudaStream_t st) {
     SweepParams q = p;
     void *args[] = { &q };
-    return cudaLaunchCooperativeKernel((const void *)k_mhrs_sweep, dim3(grid_blocks), dim3(MHRS_THREADS), args,
-                                       pht_mhrs_smem_bytes(p.n), st);
+    const size_t smem = pht_mhrs_smem_bytes(p.n);
+    if (p.n <= 8) k_mhrs_lanes<8><<<lane_blocks, MHRS_THREADS, smem, st>>>(q);
+    else if (p.n <= 16) k_mhrs_lanes<16><<<lane_blocks, MHRS_THREADS, smem, st>>>(q);
+    else k_mhrs_lanes<32><<<lane_blocks, MHRS_THREADS, smem, st>>>(q);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const void *fn = p.n <= 8 ? (const void *)k_mhrs_tail<8> : (p.n <= 16 ? (const void *)k_mhrs_tail<16> : (const void *)k_mhrs_tail<32>);
+    return cudaLaunchCooperativeKernel(fn, dim3(tail_blocks), dim3(MHRS_THREADS), args, smem, st);
 }

@@ -86,15 +86,20 @@ __global__ void __launch_bounds__(128) k_update(UpdateParams p) {
     const ModelLayout L = ModelLayout::make(n, m);
     const uint32_t iter = p.state->iter;
     const uint32_t row = p.state->res_row;
-    const long long *Nacc = p.stats, *zfix = p.stats + n * n + n;
+    const long long *Nacc = p.stats, *zlo = p.stats + n * n + n, *zhi = p.stats + n * n + 2 * n;
     const double zscale = pht_u2d((uint64_t)(1023 - p.zbits) << 52);      /* 2^-zbits */
+    /* some rank raised its error word this sweep: every rank learns it here and stops at the next synchronisation */
+    if (threadIdx.x == 0 && p.stats[stats_len(n) - 1] != 0 && p.state->error == 0) atomicOr(&p.state->error, 128);
     for (int v = threadIdx.x; v < m; v += blockDim.x) {
         long long Nsum = 0; double zsum = 0.0;
         /* the reference walks prepend lists, i.e. cells in reverse insertion order (:340-355) */
         for (int c = p.var_ptr[v + 1] - 1; c >= p.var_ptr[v]; c--) {
             const int i = p.cell_i[c], j = p.cell_j[c];
             Nsum += (j == n) ? Nacc[i + i * n] : Nacc[i + j * n];
-            const double zi = (double)zfix[i] * zscale;
+            /* the two limbs of the fixed-point total; it must fit the int64 it is converted from (else: error word 2) */
+            const __int128 tot = ((__int128)zhi[i] << 32) + (__int128)(unsigned long long)zlo[i];
+            if (tot > (__int128)0x7fffffffffffffffLL || tot < -(__int128)0x7fffffffffffffffLL) atomicOr(&p.state->error, 2);
+            const double zi = (double)(long long)tot * zscale;
             zsum += zi / p.C[i + j * n1];
         }
         pht_stream st; st.k0 = p.k0; st.k1 = p.k1;
@@ -170,5 +175,15 @@ cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st) {
 }
 cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st) {
     k_update<<<1, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+/* before the all-reduce of a multi-GPU sweep: the last word of the statistics block says whether this rank's error
+ * word is raised, so the sum tells every rank (k_update) */
+__global__ void k_pack_error(long long *stats, int len, const DevState *state) {
+    if (threadIdx.x == 0) stats[len - 1] = state->error != 0 ? 1 : 0;
+}
+cudaError_t pht_launch_pack_error(const UpdateParams &p, cudaStream_t st) {
+    k_pack_error<<<1, 32, 0, st>>>(p.stats, stats_len(p.n), p.state);
     return cudaGetLastError();
 }

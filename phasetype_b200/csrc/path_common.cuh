@@ -73,7 +73,7 @@ __device__ __forceinline__ int slab_scan(const double *slab, int n, double targe
 
 /* add one finished path to the statistics (production) or write it out (parity mode) */
 template <int THREADS>
-__device__ __forceinline__ void path_flush(const SweepParams &p, int n, const double *zslab, long long *zacc,
+__device__ __forceinline__ void path_flush(const SweepParams &p, int n, const double *zslab, unsigned long long *zlo, long long *zhi,
                                            unsigned int *Bacc, int B, long out_idx) {
     const int tid = threadIdx.x;
     if (p.outB != nullptr) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void path_flush(const SweepParams &p, int n, const do
             const double v = zslab[i * THREADS + tid];
             if (v != 0.0) {
                 if (!(v * zs < 4.0e18) || !(v * zs > -4.0e18)) atomicOr(&p.state->error, 2);
-                atomicAdd(reinterpret_cast<unsigned long long *>(&zacc[i]), (unsigned long long)__double2ll_rn(v * zs));
+                pht_zfix_add(zlo, zhi, i, __double2ll_rn(v * zs));
             }
         }
     }
@@ -102,13 +102,14 @@ __device__ __forceinline__ void count_transition(const SweepParams &p, int n, un
 /* block accumulators -> global statistics block */
 template <int THREADS>
 __device__ __forceinline__ void block_flush(const SweepParams &p, int n, const unsigned int *Nacc, const unsigned int *Bacc,
-                                            const long long *zacc) {
+                                            const unsigned long long *zlo, const long long *zhi) {
     if (p.outB != nullptr) return;
     unsigned long long *g = reinterpret_cast<unsigned long long *>(p.stats);
     for (int i = threadIdx.x; i < n * n; i += THREADS) if (Nacc[i]) atomicAdd(&g[i], (unsigned long long)Nacc[i]);
     for (int i = threadIdx.x; i < n; i += THREADS) {
         if (Bacc[i]) atomicAdd(&g[n * n + i], (unsigned long long)Bacc[i]);
-        if (zacc[i]) atomicAdd(&g[n * n + n + i], (unsigned long long)zacc[i]);
+        if (zlo[i]) atomicAdd(&g[n * n + n + i], zlo[i]);
+        if (zhi[i]) atomicAdd(&g[n * n + 2 * n + i], (unsigned long long)zhi[i]);
     }
 }
 
