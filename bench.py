@@ -8,12 +8,13 @@ latent-path draw per observation + the conjugate parameter update.  Metric: path
   python bench.py [--gpus N] [--steps K] [--warmup W] [--method MHRS|ECS|DCS] [--config 3] [--obs L]
   python bench.py --impl reference ...      # the reference's own C on the host cores
 
-Headline (N = 1): BASELINE.json configs[2] = 8-phase general PHT, 10^7 observations, 20 % right-censored, method
-MHRS (the one sampler the reference's phtMCMC() uses); ECS and DCS on the same shape are measured in the same run and
-reported under "other_methods".  N > 1: one process per GPU (torchrun); every rank holds 10^7 observations of its own
-(weak scaling, observation i of the global set -> rank i mod N) and the one exchange per sweep is the NCCL all-reduce
-of the statistics block inside the captured sweep; a strong-scaling run (the same 10^7 observations sharded N ways)
-is timed too and reported under "strong".
+Headline: BASELINE.json configs[2] = 8-phase general PHT, 10^7 observations, 20 % right-censored, method MHRS (the
+one sampler the reference's phtMCMC() uses); ECS and DCS on the same shape are measured in the same run and reported
+under "other_methods".  N > 1: one process per GPU (torchrun) and the SAME 10^7 observations sharded over the N ranks
+(observation i -> rank i mod N; "scaling": "strong", as BASELINE's config says).  Per sweep the ranks exchange the
+statistics block (NCCL all-reduce inside the captured sweep) and search the deepest part of the MHRS rejection tail
+together through peer memory.  The run also checks that every rank's chain is identical and equal to the one-GPU chain
+of the same data ("chain_parity"), and times the weak-scaling variant (10^7 observations per GPU) under "weak".
 
 The JSON line carries `roofline` (FP64-issue bound kernel: see DESIGN.md section 5), `cpu_baseline`, `e2e`, `clocks`,
 `gpu_launches`.  Only the cpu_baseline / --impl reference legs touch oracle/ (the work model's event counts come from
@@ -174,10 +175,37 @@ class Runner:
             torch.cuda.set_device(local_rank)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             self.torch = torch; self.dist = dist
+            # host-side waits that must not occupy the GPUs (rank 0 drives all devices in the end-to-end leg)
+            self.cpu_group = dist.new_group(backend="gloo")
 
     def barrier(self):
         if self.world > 1:
             self.torch.cuda.synchronize(); self.dist.barrier(); self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
+
+    def chain_parity(self, wl, method, y_loc, c_loc, sum_y, sweeps=3):
+        """Every rank's chain must be the same numbers, and the same as the chain ONE GPU draws from the whole data set
+        (integer statistics, keyed Philox streams: the number of GPUs must not show in the results)."""
+        torch, dist = self.torch, self.dist
+        e = self.make_engine(wl, method, y_loc, c_loc, sum_y, True, False)
+        rows = e.run(sweeps); e.close()
+        mine = torch.from_numpy(rows.copy()).cuda()
+        allr = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allr, mine); torch.cuda.synchronize()
+        same = all(bool(torch.equal(a, allr[0])) for a in allr)
+        ok = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if self.rank == 0:
+            import phasetype_b200 as pb
+            one = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=METHOD_CODE[method], mhit=self.a.mhit, seed=SEED,
+                            device=self.local_rank, rank=0, world=1, use_graph=True, sum_y_global=sum_y)
+            one.set_theta(wl.theta, next_iter=1)
+            ref = one.run(sweeps); one.close()
+            ok[0] = 1 if (same and np.array_equal(ref, rows)) else 0
+        dist.broadcast(ok, 0)
+        return bool(ok.item())
 
     def reduce(self, x, op="max"):
         if self.world == 1:
@@ -203,6 +231,13 @@ class Runner:
                 buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
             dist.broadcast(buf, 0)
             e.comm_init(bytes(buf.cpu().numpy().tobytes()))
+            if not os.environ.get("PHT_BENCH_NO_PEERS"):
+                # the engines' exchange windows (global MHRS tail): every rank opens every other rank's through CUDA IPC
+                from phasetype_b200._lib import PEER_HANDLE_BYTES
+                mine = torch.frombuffer(bytearray(e.peer_handle()), dtype=torch.uint8).cuda()
+                allh = [torch.zeros(PEER_HANDLE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
+                dist.all_gather(allh, mine); torch.cuda.synchronize()
+                e.peer_attach(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
         if flush:
             e.set_l2_flush(FLUSH_BYTES)
         e.set_theta(wl.theta, next_iter=1)
@@ -236,8 +271,9 @@ class Runner:
         tot2, kern_ms = eng2.last_ms()
         if os.environ.get("PHT_BENCH_VERBOSE"):
             cc = eng2.counters()
-            sys.stderr.write("rank %d: path kernel %.3f ms/sweep (lane %.2f, tail %.2f ms), %d observations handed to the tail per sweep\n"
-                             % (self.rank, kern_ms, cc["ns_lane"] * 1e-6 / (warmup + k), cc["ns_tail"] * 1e-6 / (warmup + k), cc["deferred"] // (warmup + k)))
+            sys.stderr.write("rank %d: path kernels %.3f ms/sweep (lanes %.2f, local tail %.2f, global tail %.2f, tail replay %.2f ms), %d observations handed to the tail, %.1f tail rounds per sweep\n"
+                             % (self.rank, kern_ms, cc["ns_lane"] * 1e-6 / (warmup + k), cc["ns_tail"] * 1e-6 / (warmup + k), cc["ns_global"] * 1e-6 / (warmup + k),
+                                cc["ns_replay"] * 1e-6 / (warmup + k), cc["deferred"] // (warmup + k), cc["tail_rounds"] / float(warmup + k)))
         kern_ms = self.reduce(kern_ms)
         eng2.close()
         nloc = max(1, y_loc.shape[0])
@@ -253,7 +289,7 @@ class Runner:
         W = work_per_path(method, wl.n, ev)
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
-        kernel = {"MHRS": "k_mhrs_sweep", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
+        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
         cap = ncu_capture(method, l_local)
         issue = None
         mhz = (res.get("clocks") or {}).get("sm_mhz") or getattr(self, "sm_mhz", None)
@@ -265,6 +301,7 @@ class Runner:
                      "active_lanes_per_instruction": cap.get("active_lanes_per_instruction"), "source": cap.get("source")}
         return {"bound": "fp64_issue", "achieved": achieved / 1e9, "peak": fma_rate / 1e9, "unit": "G FP64-instr-equiv/s",
                 "frac": achieved / fma_rate, "traffic": cap.get("dram_bytes_per_launch"), "issue": issue,
+                "traffic_and_issue": "from_capture: read from the committed ncu capture %s, not measured in this run" % cap.get("source") if cap else None,
                 "peak_source": "measured in this run: dependent FP64 FMA chains on all SMs (pht_fp64_fma_rate); burst figure",
                 "kernel": kernel, "kernel_ms": res["kern_ms"], "kernel_share_of_step": res["share"],
                 "work_per_path": W, "events_per_path": ev,
@@ -287,7 +324,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the ECS / DCS side measurements at N = 1")
-    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling side measurement at N > 1")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling side measurement at N > 1")
+    ap.add_argument("--no-parity", action="store_true", help="skip the chain-parity check at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -306,7 +344,7 @@ def main():
         pps, ms = cpu_sweeps(wl, args.method, args.mhit, sample, cores, args.steps, args.warmup, kind)
         line = {"impl": "reference", "metric": "path_draws_per_sec", "value": pps, "unit": "paths/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "gibbs_iters_per_sec_extrapolated": pps / full_l,
                 "config": {"workload": wl.name, "method": args.method, "mhit": args.mhit, "phases": wl.n,
                            "observations": full_l, "sample_per_step": sample},
@@ -321,11 +359,15 @@ def main():
     import phasetype_b200 as pb
     R = Runner(args, rank, world, local_rank)
     method = args.method
-    # weak scaling: rank r owns an independent data set of the same model (global observation r + k * world)
-    wl = synth.config(args.config, method, l=full_l, shard=(rank if world > 1 else None))
-    y_loc = np.ascontiguousarray(wl.y); c_loc = np.ascontiguousarray(wl.censored)
-    l_local = int(y_loc.shape[0]); l_global = l_local * world
-    sum_y = R.reduce(float(y_loc.sum()), "max") * world * 1.0000001 if world > 1 else float(y_loc.sum())
+    # the config's own data set, the same on every rank; rank r works on observations r, r + N, ...
+    wl = synth.config(args.config, method, l=full_l)
+    if world > 1:
+        ys, cs = wl.shard(rank, world)
+        y_loc = np.ascontiguousarray(ys); c_loc = np.ascontiguousarray(cs)
+    else:
+        y_loc = np.ascontiguousarray(wl.y); c_loc = np.ascontiguousarray(wl.censored)
+    l_local = int(y_loc.shape[0]); l_global = wl.l
+    sum_y = float(wl.y.sum())
 
     res = R.timed(wl, method, y_loc, c_loc, sum_y, args.steps, args.warmup, clocks=True)
     R.sm_mhz = (res.get("clocks") or {}).get("sm_mhz")
@@ -336,11 +378,11 @@ def main():
         fma_rate = pb.fp64_fma_rate(local_rank)
         line = {"metric": "path_draws_per_sec", "value": value, "unit": "paths/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["total_ms"] / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "gibbs_iters_per_sec": args.steps / (res["total_ms"] * 1e-3),
                 "config": {"workload": wl.name, "method": method, "mhit": args.mhit, "phases": wl.n, "parameters": wl.m,
                            "observations": l_global, "observations_per_gpu": l_local,
-                           "sharding": "observation i of the global set -> rank i mod %d; one NCCL all-reduce of n^2+2n int64 per sweep" % world
+                           "sharding": "observation i of the %d -> rank i mod %d; per sweep one NCCL all-reduce of n^2+3n+1 int64 and the global MHRS tail over peer memory" % (l_global, world)
                            if world > 1 else "single GPU",
                            "l2": "flushed: a %d MiB memset on the sweep stream before every sweep, inside the timed region" % (FLUSH_BYTES >> 20)},
                 "gpu_launches": res["launches"], "wall_ms_per_step": 1e3 * res["wall"] / args.steps,
@@ -348,25 +390,35 @@ def main():
                 "clocks": res["clocks"]}
         line["roofline"] = R.roofline(wl, method, res, l_local, fma_rate)
 
-    # ---- strong scaling beside it (N > 1): the config's own 10^7 observations sharded N ways
-    if world > 1 and not args.no_strong:
-        wls = synth.config(args.config, method, l=full_l)
-        ys, cs = wls.shard(rank, world)
-        rs = R.timed(wls, method, np.ascontiguousarray(ys), np.ascontiguousarray(cs), float(wls.y.sum()), args.steps, args.warmup)
+    # ---- N > 1: the chain must not depend on the number of GPUs
+    if world > 1 and not args.no_parity:
+        ok = R.chain_parity(wl, method, y_loc, c_loc, sum_y)
         if rank == 0:
-            line["strong"] = {"observations": full_l, "value": full_l * args.steps / (rs["total_ms"] * 1e-3), "unit": "paths/s",
-                              "ms_per_step": rs["total_ms"] / args.steps, "kernel_ms": rs["kern_ms"]}
-        del wls
+            line["chain_parity"] = ok
+        if not ok:
+            sys.stderr.write("rank %d: CHAIN PARITY FAILED: the %d-GPU chain differs between ranks or from the 1-GPU chain\n" % (rank, world))
 
-    # ---- end to end through the drop-in routine with host buffers (upload, sweeps, download)
+    # ---- weak scaling beside it (N > 1): every rank its own 10^7 observations of the same model
+    if world > 1 and not args.no_weak:
+        wlw = synth.config(args.config, method, l=full_l, shard=rank)
+        sum_w = R.reduce(float(wlw.y.sum()), "max") * world * 1.0000001
+        rw = R.timed(wlw, method, np.ascontiguousarray(wlw.y), np.ascontiguousarray(wlw.censored), sum_w, args.steps, args.warmup)
+        if rank == 0:
+            line["weak"] = {"observations": full_l * world, "value": full_l * world * args.steps / (rw["total_ms"] * 1e-3), "unit": "paths/s",
+                            "ms_per_step": rw["total_ms"] / args.steps, "kernel_ms": rw["kern_ms"]}
+        del wlw
+
+    # ---- end to end through the drop-in routine with host buffers (upload, communicator set-up, sweeps, download)
     e2e = None
     if not args.no_e2e:
         R.barrier()
         code = METHOD_CODE[method]
-        t0 = time.perf_counter()
-        if world == 1:
+        dt = 0.0
+        if rank == 0:
+            # ONE call of LJMA_Gibbs, as R makes it: the routine itself fans out over the N devices (host threads, NCCL
+            # communicator, peer windows); the other ranks of this launch keep their GPUs idle meanwhile
             os.environ["PHT_B200_SEED"] = str(SEED); os.environ["PHT_B200_QUIET"] = "1"
-            os.environ["PHT_B200_DEVICE"] = str(local_rank)
+            os.environ["PHT_B200_DEVICE"] = str(local_rank if world == 1 else 0); os.environ["PHT_B200_GPUS"] = str(world)
             dts = []
             for _ in range(3):          # the call allocates and frees ~0.5 GB of device and pinned memory: take the median of three
                 t0 = time.perf_counter()
@@ -375,19 +427,11 @@ def main():
                 dts.append(time.perf_counter() - t0)
                 assert np.isfinite(out).all() and (out[1:] > 0).all()
             dt = float(np.median(dts))
-        else:
-            # one process per GPU: upload of the shard and the sweeps are timed, the one-off NCCL communicator set-up is not
-            e3 = R.make_engine(wl, method, y_loc, c_loc, sum_y, True, False)
-            R.barrier()
-            t1 = time.perf_counter()
-            out = e3.run(args.steps)
-            dt = R.last_create_s + (time.perf_counter() - t1)
-            e3.close()
-        dt = R.reduce(dt)
-        e2e = {"value": l_global * args.steps / dt, "unit": "paths/s", "h2d_bytes_per_step": int(12 * l_global / args.steps),
-               "d2h_bytes_per_step": int(8 * wl.m), "seconds": dt, "runs": 3 if world == 1 else 1,
-               "note": ("LJMA_Gibbs(it=%d) on host vectors: engine creation, upload of y/censored (once per call, amortised over the sweeps), %d sweeps, download of res"
-                        % (args.steps + 1, args.steps)) if world == 1 else "per rank: engine creation with upload of the host shard + %d sweeps + result download (NCCL communicator set-up excluded)" % args.steps}
+        R.host_barrier()
+        e2e = {"value": l_global * args.steps / dt if dt > 0 else None, "unit": "paths/s", "h2d_bytes_per_step": int(12 * l_global / args.steps),
+               "d2h_bytes_per_step": int(8 * wl.m), "seconds": dt, "runs": 3,
+               "note": "one LJMA_Gibbs(it=%d) call on host vectors driving %d GPU(s): engine creation, upload of y/censored (once per call, amortised over "
+                       "the sweeps), %s%d sweeps, download of res" % (args.steps + 1, world, "NCCL communicator and peer-window set-up, " if world > 1 else "", args.steps)}
     if rank == 0:
         line["e2e"] = e2e
         # ---- the other two samplers on the same shape (N = 1 only; fewer sweeps)

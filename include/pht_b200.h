@@ -124,8 +124,14 @@ enum { PHT_CNT_PATHS = 0, PHT_CNT_ATTEMPTS, PHT_CNT_JUMPS, PHT_CNT_DENS_EVALS, P
        PHT_CNT_DEFERRED, PHT_CNT_TAIL_ROUNDS, PHT_CNT_ERRORS, PHT_CNT_LAUNCHES,
        PHT_CNT_NS_LANE, PHT_CNT_NS_TAIL, PHT_CNT_NS_REPLAY,   /* device-timer ns spent in the MHRS kernel phases */
        PHT_CNT_NS_GLOBAL,                                      /* ... and in the tail rounds searched by all GPUs together */
+       PHT_CNT_NS_XWAIT,                                       /* part of NS_GLOBAL spent in barriers between the GPUs */
+       PHT_CNT_GLOBAL_ROUNDS, PHT_CNT_GLOBAL_ITEMS,            /* global tail: rounds run, observations gathered */
        PHT_CNT_COUNT = 20 };
 int pht_engine_counters(pht_engine *e, unsigned long long *out);
+/* MHRS tail, per round number (accumulated since creation): ns searching, ns at the barrier after the search, ns
+ * advancing, sum of pending observations, sum of attempts offered per observation; out: PHT_ROUND_TRACE x 5 words */
+#define PHT_ROUND_TRACE 48
+int pht_engine_round_trace(pht_engine *e, unsigned long long *out);
 
 /* measurement helpers ------------------------------------------------------- */
 /* dependent-chain FP64 FMA microbenchmark: achieved FMA instructions per second (all SMs) */

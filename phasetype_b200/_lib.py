@@ -18,12 +18,12 @@ SYMBOLS = [
     "pht_engine_destroy", "pht_comm_unique_id", "pht_engine_comm_init", "pht_engine_set_theta",
     "pht_engine_get_theta", "pht_engine_run", "pht_engine_enqueue", "pht_engine_sync", "pht_engine_last_ms",
     "pht_engine_sweep_stats", "pht_engine_paths", "pht_engine_set_spectral", "pht_engine_get_model",
-    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush", "pht_engine_peer_handle", "pht_engine_peer_attach",
+    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush", "pht_engine_peer_handle", "pht_engine_peer_attach", "pht_engine_round_trace",
 ]
 PEER_HANDLE_BYTES = 128
 CNT_NAMES = ["paths", "attempts", "jumps", "dens_evals", "env_updates", "brent_evals", "arms_calls",
              "metrop_rejects", "nonfinite", "deferred", "tail_rounds", "errors", "launches", "ns_lane", "ns_tail", "ns_replay",
-             "ns_global", "reserved17", "reserved18", "reserved19"]
+             "ns_global", "ns_xwait", "global_rounds", "global_items"]
 N_CNT = 20
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -72,6 +72,7 @@ def lib():
     L.pht_engine_counters.argtypes = [C.c_void_p, _up]
     L.pht_fp64_fma_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.pht_engine_set_l2_flush.argtypes = [C.c_void_p, C.c_ulonglong]
+    L.pht_engine_round_trace.argtypes = [C.c_void_p, _up]
     L.pht_engine_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.pht_engine_peer_attach.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
@@ -192,6 +193,12 @@ class Engine:
         _check(lib().pht_engine_get_model(self._h, *[out[k].ctypes.data for k in
                                                      ("S", "s", "P", "Pfull", "evals", "Q", "Qinv")]))
         return out
+
+    def round_trace(self):
+        """(48, 5) array: per tail round number, ns search / ns barrier / ns advance / sum of pending / sum of K."""
+        t = np.zeros(48 * 5, dtype=np.uint64)
+        _check(lib().pht_engine_round_trace(self._h, t))
+        return t.reshape(48, 5)
 
     def counters(self):
         c = np.zeros(N_CNT, dtype=np.uint64)

@@ -289,7 +289,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         /* global tail: the canonical list and this rank's exchange window (flags 0, found words NONE) */
         if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
         if (cfg->world > 1) {
-            CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * PHT_MAX_WORLD * PHT_GCAP));
+            CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
             CUE(cudaMalloc(&e->d_xw, sizeof(XchgWindow)));
             CUE(cudaMemsetAsync(e->d_xw, 0, sizeof(XchgWindow), e->stream));
             CUE(cudaMemsetAsync(e->d_xw->gfound, 0xFF, sizeof(e->d_xw->gfound), e->stream));
@@ -599,6 +599,17 @@ extern "C" int pht_engine_get_model(pht_engine *e, double *S, double *s, double 
     if (evals) memcpy(evals, &h[e->L.evals], sizeof(double) * n);
     if (Q) memcpy(Q, &h[e->L.Q], sizeof(double) * n * n);
     if (Qinv) memcpy(Qinv, &h[e->L.Qinv], sizeof(double) * n * n);
+    return 0;
+}
+
+extern "C" int pht_engine_round_trace(pht_engine *e, unsigned long long *out) {
+    if (!e || !out) return fail("null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    DevState *st = new DevState; cudaError_t ce = cudaMemcpy(st, e->d_state, sizeof(*st), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) memcpy(out, st->round_trace, sizeof(st->round_trace));
+    delete st;
+    CU(ce);
     return 0;
 }
 

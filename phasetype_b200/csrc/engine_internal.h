@@ -104,6 +104,9 @@ struct DevState {
     uint32_t xdead;            /* a peer barrier timed out: no further waiting */
     unsigned long long xepoch; /* barrier epochs completed (monotonic over the life of the engine) */
     unsigned long long counters[PHT_CNT_COUNT];
+    /* measurement aid: per tail round (index = round number, accumulated over sweeps) the device-timer ns block 0 spent
+     * searching / waiting at the barrier after the search / advancing, and the sum of pending items and of K */
+    unsigned long long round_trace[PHT_ROUND_TRACE][5];
 };
 
 struct SweepParams {

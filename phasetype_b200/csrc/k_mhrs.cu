@@ -91,14 +91,23 @@ namespace cg = cooperative_groups;
 #define TAIL_CH 256u                /* attempts per tail chunk (a pool never crosses a chunk) */
 #endif
 #ifndef TAIL_BATCH
-#define TAIL_BATCH 8u               /* consecutive attempts a lane takes from a pool at once */
+#define TAIL_BATCH 1u               /* consecutive attempts a lane takes from a pool at once (measured: 1 beats 2, 4, 8) */
+#endif
+#ifndef TAIL_LATE_P
+#define TAIL_LATE_P 1024u           /* from this few pending observations on, K grows by TAIL_LATE_GROWTH per round */
+#endif
+#ifndef TAIL_LATE_GROWTH
+#define TAIL_LATE_GROWTH 4u
+#endif
+#ifndef DRAIN_LANES
+#define DRAIN_LANES 32              /* END_CAP applies once this few lanes of the warp still hold an observation (32 = at once; 8 measured slower) */
 #endif
 #ifndef TAIL_K0
-#define TAIL_K0 512u                /* attempts per pending observation in tail round 0 */
+#define TAIL_K0 512u                /* attempts per pending observation in tail round 0 (a multiple of TAIL_CH) */
 #endif
 #define TAIL_KMAX (1u << 24)
 #ifndef TAIL_GROWTH
-#define TAIL_GROWTH 2u
+#define TAIL_GROWTH 2u              /* K grows by this factor per round */
 #endif
 #ifndef FOUND_PERIOD
 #define FOUND_PERIOD 8u             /* steps between looks at the pool observation's `found` word (power of two) */
@@ -135,6 +144,7 @@ struct MhrsSmem {
              ring_a2[MHRS_WARPS * RING], ring_fl[MHRS_WARPS * RING];
     unsigned int ring_n[MHRS_WARPS];
     unsigned int paths_done;                    /* replays finished by this block */
+    unsigned int scan[MHRS_WARPS + 1];          /* block-level compaction of the global list */
     /* per-lane state that is touched once or twice per observation lives here, not in registers: the prefetched
      * next observation and the MH bookkeeping */
     float pf_yf[MHRS_THREADS]; uint32_t pf_og[MHRS_THREADS], pf_pos[MHRS_THREADS];
@@ -452,6 +462,7 @@ __device__ __forceinline__ uint32_t pack_flags(bool have_cur, bool cur_off, bool
 /* barrier over the ranks of the run through the exchange windows: every thread's peer stores are fenced, the grid
  * meets, rank flags are exchanged, the grid meets again.  Gives up (error word 64) when a peer does not arrive. */
 __device__ __forceinline__ void peer_barrier(cg::grid_group &grid, const SweepParams &p, unsigned long long epoch) {
+    const unsigned long long t_in = (blockIdx.x == 0 && threadIdx.x == 0) ? gtimer() : 0ull;
     __threadfence_system();
     grid.sync();
     if (blockIdx.x == 0) {
@@ -470,6 +481,7 @@ __device__ __forceinline__ void peer_barrier(cg::grid_group &grid, const SweepPa
         }
     }
     grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.state->counters[PHT_CNT_NS_XWAIT], gtimer() - t_in);
 }
 
 /* ------------------------------------------------------------------------------------------ tail search
@@ -498,7 +510,7 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
     double my_y = 0.0; uint32_t my_item = 0xFFFFFFFFu, a_end = 0u; bool active = false;
     unsigned steps = 0;
     /* warp-uniform: the units this warp holds, and the pool being handed out */
-    unsigned long long u_next = 0, u_end = 0, last_base = 0;
+    unsigned long long u_next = 0, u_end = 0, last_base = 0, remaining = total_units;
     bool out_of_units = false, finished = false;
     uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; double y = 0.0; float yf = 0.0f; bool cens = false, first_off = false;
     while (!finished) {
@@ -512,7 +524,7 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                     bool have = false;
                     while (!have) {
                         if (u_next >= u_end) {
-                            const unsigned long long remaining = total_units > last_base ? total_units - last_base : 0ull;
+                            remaining = total_units > last_base ? total_units - last_base : 0ull;
                             unsigned long long want = remaining / (2ull * (unsigned long long)nwarps);
                             want = want < POOL_MIN ? POOL_MIN : (want > POOL_MAX ? POOL_MAX : want);
                             unsigned long long base = 0;
@@ -547,7 +559,11 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                     /* idle lanes take a batch of consecutive attempts each (ballot only, no memory traffic): a small pool
                      * is spread over them, a large one is handed out TAIL_BATCH attempts at a time */
                     const uint32_t avail = pool_end - pool_next, nidle = __popc(idle);
-                    uint32_t bsz = (avail + nidle - 1u) / nidle; bsz = bsz > TAIL_BATCH ? TAIL_BATCH : bsz;
+                    /* (towards the end of the round the batches shrink to single attempts, so the round does not end on
+                     * one lane working through a long batch while the grid waits) */
+                    const unsigned long long fair = remaining / (64ull * (unsigned long long)nwarps);
+                    const uint32_t bmax = fair >= TAIL_BATCH ? TAIL_BATCH : (fair < 1ull ? 1u : (uint32_t)fair);
+                    uint32_t bsz = (avail + nidle - 1u) / nidle; bsz = bsz > bmax ? bmax : bsz;
                     const uint32_t a0 = pool_next + (uint32_t)__popc(idle & ((1u << lane) - 1u)) * bsz;
                     if (!active && a0 < pool_end) {
                         a_end = a0 + bsz < pool_end ? a0 + bsz : pool_end;
@@ -697,8 +713,11 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
             sm.mh_cur_a[tid] = 0u; sm.mh_misc[tid] = 0u; a_lim = cap;
             fast_begin(f, 0u, n);
         }
-        if (__ballot_sync(FULL, fl & LF_RUN) == 0u) { if (dry) break; else continue; }
-        if (dry && a_lim != 0xFFFFFFFFu && a_lim > END_CAP) a_lim = END_CAP;      /* a lone lane must not hold the grid */
+        const unsigned running = __ballot_sync(FULL, fl & LF_RUN);
+        if (running == 0u) { if (dry) break; else continue; }
+        /* a few last lanes must not hold the grid: once the stream is dry and the warp is mostly idle, the rest goes
+         * to the tail after END_CAP attempts */
+        if (dry && __popc(running) <= DRAIN_LANES && a_lim != 0xFFFFFFFFu && a_lim > END_CAP) a_lim = END_CAP;
         __syncwarp();
         /* ---- the search loop proper: steps until some lane has something to report.  No calls, nothing but the
          * filter walk, in here; a failed attempt restarts on the next sub-stream on the spot. */
@@ -717,9 +736,6 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
             const uint32_t res = exact_attempt(f.a, false, p.y[pos], o.cens, o.og, p, sm, iter, n, ~0u);
             surv = res & 1u; k = (int)((res >> 8) & 0xffu); c_jumps += res >> 16;
             if (!surv) { fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
-#ifdef MHRS_DEBUG_COUNTERS
-            atomicAdd(&p.state->counters[18], 1ull);
-#endif
         }
         /* survived to y in a state that cannot exit: a failed attempt (eq_Bladt_MHRS.c:66,74) */
         if (surv && !((smask >> k) & 1u)) { surv = false; fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
@@ -772,9 +788,6 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
                 it.owner = p.obs_rank;
                 p.items[idx] = it; p.found[idx] = FOUND_NONE;
                 atomicAdd(&p.state->counters[PHT_CNT_DEFERRED], 1ull);
-#ifdef MHRS_DEBUG_COUNTERS
-                if (dry) atomicAdd(&p.state->counters[19], 1ull);
-#endif
                 fl &= ~LF_RUN;
             } else a_lim = 0xFFFFFFFFu;          /* no room: the lane keeps the observation */
         }
@@ -828,9 +841,6 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_lanes(co
     const uint32_t cap = p.mhrs_cap > 0 ? (uint32_t)p.mhrs_cap : 256u;
     unsigned c_attempts = 0, c_jumps = 0;      /* per thread and sweep: far below 2^32 */
     lane_phase(p, sm, iter, n, smask, obs_begin, obs_end, cap, c_jumps, c_attempts);
-#ifdef MHRS_DEBUG_COUNTERS
-    atomicAdd(&p.state->counters[17], (unsigned long long)c_attempts);
-#endif
     flush_block(p, sm, n, per_obs, c_attempts, c_jumps);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.state->counters[PHT_CNT_NS_LANE], gtimer() - t0);
 }
@@ -868,7 +878,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
      * items are flagged and skipped), searched by all ranks, advanced by every rank redundantly. */
     /* round 0 offers every pending observation as many attempts as its lane has already spent on it */
     uint32_t K = TAIL_K0; while (K < (uint32_t)p.mhrs_cap && K < TAIL_KMAX) K *= 2u;
-    uint32_t rounds = 0u, g0 = 0u, Pg = 0u; int cur = 0; bool global = false;
+    uint32_t rounds = 0u, g0 = 0u, Pg = 0u; int cur = 0, gl_cur = 0; bool global = false;
     const uint32_t W = p.obs_world, me = p.obs_rank, sp = iter & 1u;
     unsigned long long epoch = multi ? p.state->xepoch : 0ull;
     for (;;) {
@@ -892,20 +902,26 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
                     for (uint32_t i = gtid; i < c; i += gsize) p.glist[Pg + i] = r * PHT_GCAP + i;
                     Pg += c;
                 }
-                if (gtid == 0) { p.state->n_gpend = Pg; p.state->unit_counter = 0ull; p.state->any_fail[0] = 0u; p.state->any_fail[1] = 0u; }
+                if (gtid == 0) {
+                    p.state->n_gpend = Pg; p.state->unit_counter = 0ull; p.state->any_fail[0] = 0u; p.state->any_fail[1] = 0u;
+                    atomicAdd(&p.state->counters[PHT_CNT_GLOBAL_ITEMS], (unsigned long long)Pg);
+                }
                 grid.sync();
                 global = true; g0 = rounds;
                 K = p.k_switch > TAIL_K0 ? p.k_switch : TAIL_K0;
                 continue;
             }
-        } else if (p.state->n_gpend == 0u || p.state->xdead != 0u) break;
+        } else if (Pg == 0u || p.state->xdead != 0u) break;
         const uint32_t par = (rounds - g0) & 1u;
         TailView tv;
         if (!global) { tv.items = p.items; tv.pend = pend; tv.found = p.found; tv.P = p.state->n_pend[cur]; }
-        else { tv.items = p.xw->gitems[sp]; tv.pend = p.glist; tv.found = p.xw->gfound[par]; tv.P = Pg; }
+        else { tv.items = p.xw->gitems[sp]; tv.pend = gl_cur ? p.glist + PHT_MAX_WORLD * PHT_GCAP : p.glist; tv.found = p.xw->gfound[par]; tv.P = Pg; }
         tv.K = K; tv.global = global; tv.parity = par;
+        const unsigned long long tr0 = timekeeper ? gtimer() : 0ull;
         tail_search(tv, p, sm, iter, n, smask, nwarps, c_jumps, c_attempts);
+        const unsigned long long tr1 = timekeeper ? gtimer() : 0ull;
         if (global) peer_barrier(grid, p, ++epoch); else grid.sync();
+        const unsigned long long tr2 = timekeeper ? gtimer() : 0ull;
         /* ---- advance each pending observation's MH state machine (eq_Bladt_MHRS.c:65-101); in a global round every
          * rank advances every item: same inputs, same outcome */
         for (uint32_t i = gtid; i < tv.P; i += gsize) {
@@ -921,7 +937,6 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
             if (st == 2 && mine) { atomicAdd(&p.state->counters[PHT_CNT_ERRORS], 1ull); atomicOr(&p.state->error, 8); }
             if (failed && st == 0) atomicOr(&p.state->any_fail[par], 1u);
             if (global) {
-                if (st != 0) atomicSub(&p.state->n_gpend, 1u);
                 if (st == 1 && mine) {
                     /* back into my own list for the replay */
                     const uint32_t back = pend[item - me * PHT_GCAP];
@@ -933,13 +948,42 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
         }
         if (gtid == 0) { if (!global) p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; p.state->any_fail[par ^ 1u] = 0u; }
         grid.sync();
+        if (global) {
+            /* the canonical list without the finished items, in the same order on every rank (one block, ballot scan) */
+            uint32_t *next_list = (gl_cur ? p.glist : p.glist + PHT_MAX_WORLD * PHT_GCAP);
+            if (blockIdx.x == 0) {
+                const int lane = tid & 31, warp = tid >> 5;
+                uint32_t outn = 0u;
+                for (uint32_t tile = 0; tile < Pg; tile += MHRS_THREADS) {
+                    const uint32_t i = tile + tid;
+                    uint32_t item = 0u; bool keep = false;
+                    if (i < Pg) { item = tv.pend[i]; keep = !(tv.items[item].flags & TI_FIN); }
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (lane == 0) sm.scan[warp] = __popc(bal);
+                    __syncthreads();
+                    uint32_t off = 0u, tot = 0u;
+                    for (int w2 = 0; w2 < MHRS_WARPS; w2++) { const uint32_t c = sm.scan[w2]; off += (w2 < warp) ? c : 0u; tot += c; }
+                    if (keep) next_list[outn + off + __popc(bal & ((1u << lane) - 1u))] = item;
+                    outn += tot;
+                    __syncthreads();
+                }
+                if (tid == 0) p.state->n_gpend = outn;
+            }
+            grid.sync();
+            Pg = p.state->n_gpend; gl_cur ^= 1;
+        }
         /* the attempts per observation grow only when some observation needed more than this round offered: with
          * mhit > 1 every pending observation comes back round after round for its next proposal, and a K that kept
          * doubling would bury the round in pools to skip */
         const bool grow = p.state->any_fail[par] != 0u;
+        if (timekeeper && rounds < PHT_ROUND_TRACE) {
+            unsigned long long *tr = p.state->round_trace[rounds];
+            tr[0] += tr1 - tr0; tr[1] += tr2 - tr1; tr[2] += gtimer() - tr2; tr[3] += tv.P; tr[4] += K;
+        }
         if (!global) cur ^= 1;
         rounds++;
-        K = (grow && K < TAIL_KMAX) ? K * TAIL_GROWTH : K;
+        if (grow && K < TAIL_KMAX) K *= ((global ? Pg : p.state->n_pend[cur]) <= TAIL_LATE_P) ? TAIL_LATE_GROWTH : TAIL_GROWTH;
+        if (K > TAIL_KMAX) K = TAIL_KMAX;
     }
     if (multi && gtid == 0) { p.state->xepoch = epoch; p.state->n_pend[cur] = 0u; }
     if (timekeeper) {
@@ -951,7 +995,10 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
     {
         c_jumps += replay_done_list(p, sm, iter, n, p.state->n_done, gtid / 32u, nwarps);
     }
-    if (gtid == 0) atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
+    if (gtid == 0) {
+        atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
+        if (global) atomicAdd(&p.state->counters[PHT_CNT_GLOBAL_ROUNDS], (unsigned long long)(rounds - g0));
+    }
     if (timekeeper) atomicAdd(&p.state->counters[PHT_CNT_NS_REPLAY], gtimer() - t_mark);
     flush_block(p, sm, n, per_obs, c_attempts, c_jumps);
 }

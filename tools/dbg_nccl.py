@@ -17,7 +17,7 @@ from phasetype_b200._lib import PEER_HANDLE_BYTES
 L = int(float(os.environ.get("DBG_L", "200000")))
 wl = synth.config(3, "MHRS", l=L)
 y, c = wl.shard(rank, world)
-for graph in (False, True):
+for graph in ((True,) if os.environ.get("DBG_FAST") else (False, True)):
     e = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, np.ascontiguousarray(y), np.ascontiguousarray(c), method=1, seed=5, device=lr,
                   rank=rank, world=world, use_graph=graph, sum_y_global=float(wl.y.sum()))
     say("engine", graph)
@@ -37,9 +37,9 @@ for graph in (False, True):
     e.set_theta(wl.theta, 1)
     t0 = time.time(); out = e.run(3); dt = time.time() - t0
     cn = e.counters()
-    say("run done", dt, out[-1][:3], {k: cn[k] for k in ("tail_rounds", "deferred", "ns_lane", "ns_tail", "ns_global", "ns_replay")})
+    say("run done", dt, out[-1][:3], {k: cn[k] for k in ("tail_rounds", "deferred", "attempts", "jumps", "ns_lane", "ns_tail", "ns_global", "ns_xwait", "global_rounds", "global_items", "ns_replay")})
     e.close()
-if rank == 0:
+if rank == 0 and not os.environ.get("DBG_FAST"):
     from oracle import pyoracle as po
     want, _ = po.gibbs(5, 4, 1, 1, wl.n, wl.nu, wl.zeta, wl.T, wl.C, wl.y, wl.censored, wl.theta)
     say("chain equals single-process oracle:", bool(np.array_equal(out, want[1:])))

@@ -15,3 +15,8 @@ eng.set_theta(wl.theta, 1)
 t = time.time(); out = eng.run(sweeps); dt = time.time() - t
 tot, k = eng.last_ms()
 print("sweeps", sweeps, "total_ms", tot, "kernel_ms", k, "wall", dt, eng.counters())
+if os.environ.get("TRACE"):
+    tr = eng.round_trace()
+    for r in range(48):
+        if tr[r, 4]:
+            print("round %2d: search %8.1f us  barrier %7.1f us  advance %7.1f us  P %9.1f  K %10.0f" % (r, tr[r, 0] / 1e3 / sweeps, tr[r, 1] / 1e3 / sweeps, tr[r, 2] / 1e3 / sweeps, tr[r, 3] / sweeps, tr[r, 4] / sweeps))
