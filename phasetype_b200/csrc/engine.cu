@@ -462,7 +462,7 @@ static int check_state(pht_engine *e) {
         return fail("device error word 0x%x (%s%s%s%s%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range (lower PHT_B200_ZBITS); " : "",
                     (err & 4) ? "MHRS tail list overflow; " : "",
                     (err & 8) ? "an observation's survival probability is too small for rejection sampling (more than 4e9 attempts); " : "",
-                    (err & 16) ? "S has complex eigenvalues: the spectral samplers (ECS/DCS) are not valid for it; " : "",
+                    (err & 16) ? "S has complex eigenvalues: the DCS sampler is not valid for it (ECS and MHRS are); " : "",
                     (err & 32) ? "spectral decomposition failed; " : "",
                     (err & 64) ? "a peer GPU did not arrive at a barrier of the global MHRS tail; " : "",
                     (err & 128) ? "another rank of the run raised its error word; " : "");

@@ -23,7 +23,7 @@
 /* offsets in doubles inside the model block */
 struct ModelLayout {
     int n, m;
-    int S, s, scale, P, Pfull, cum, pi, evals, Q, Qinv, Qinv_s, Qinv_1, TT, theta, total;
+    int S, s, scale, P, Pfull, cum, pi, evals, Q, Qinv, Qinv_s, Qinv_1, TT, theta, evals_im, total;
     __host__ __device__ static ModelLayout make(int n, int m) {
         ModelLayout L; int o = 0;
         L.n = n; L.m = m;
@@ -41,6 +41,7 @@ struct ModelLayout {
         L.Qinv_1 = o; o += n;
         L.TT = o; o += (n + 1) * (n + 1);
         L.theta = o; o += m;
+        L.evals_im = o; o += n;              /* +b, -b on the two entries of a complex pair a +- ib, else 0 (pht_eigen.h) */
         L.total = o;
         return L;
     }

@@ -66,6 +66,9 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     const ModelLayout ML = ModelLayout::make(n, p.m);
     DcsSmem<THREADS> sm; sm.carve(smem_raw, n);
     const uint32_t iter = p.state->iter;
+    /* complex pairs in the spectrum: this sampler's formulas (the reference's) are not valid; ECS has block formulas */
+    { bool cplx = false; for (int i = 0; i < n; i++) cplx = cplx || (p.model[ML.evals_im + i] != 0.0);
+      if (cplx) { if (tid == 0 && blockIdx.x == 0) atomicOr(&p.state->error, 16); return; } }
     for (int i = tid; i < n * n; i += THREADS) {
         sm.S[i] = p.model[ML.S + i]; sm.Q[i] = p.model[ML.Q + i]; sm.Qinv[i] = p.model[ML.Qinv + i]; sm.Nacc[i] = 0u;
     }

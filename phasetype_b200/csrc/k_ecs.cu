@@ -35,23 +35,57 @@
 #define A_NIL (-1)
 
 struct EcsSmem {
-    double *S, *Q, *P, *Pfull, *evals, *s, *Qinv_s, *Qinv_1, *pi;
+    double *S, *Q, *P, *Pfull, *evals, *evi, *s, *Qinv_s, *Qinv_1, *pi;
+    int *cplx;                          /* the spectrum has complex pairs: block formulas (spec_* below) instead of the reference's */
     double *PQ, *W, *Z;                 /* per-lane slabs: hoisted p^T Q, scratch weights, sojourn totals */
     unsigned long long *zlo; long long *zhi; unsigned int *Nacc, *Bacc;
     __device__ __forceinline__ void carve(unsigned char *raw, int n) {
         double *d = reinterpret_cast<double *>(raw);
         S = d; d += n * n; Q = d; d += n * n; P = d; d += n * n; Pfull = d; d += n * (n + 1);
-        evals = d; d += n; s = d; d += n; Qinv_s = d; d += n; Qinv_1 = d; d += n; pi = d; d += n;
+        evals = d; d += n; evi = d; d += n; s = d; d += n; Qinv_s = d; d += n; Qinv_1 = d; d += n; pi = d; d += n;
         PQ = d; d += n * ECS_THREADS; W = d; d += n * ECS_THREADS; Z = d; d += n * ECS_THREADS;
         zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
-        Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n;
+        Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n; cplx = reinterpret_cast<int *>(Bacc + n);
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(3 * n * n + n * (n + 1) + 5 * n + 3 * n * ECS_THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + n);
+        return sizeof(double) * (size_t)(3 * n * n + n * (n + 1) + 6 * n + 3 * n * ECS_THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + n + 2);
     }
 };
 
 struct EcsCounters { unsigned long long jumps, evals, updates, calls, rejects, nonfinite, paths; };
+
+/* ---- spectra with complex pairs (pht_eigen.h: real block form S = Q B Q^-1).  The reference takes the real parts
+ * and carries on (src/utility.c:116-121), i.e. is silently wrong there; these two helpers are what its formulas
+ * become when exp(x Lambda) is block diagonal: a pair a +- ib in positions (i, i+1) contributes
+ * e^{ax} [[cos bx, sin bx], [-sin bx, cos bx]].  Checked against the analytic conditional expectations (tier 2). */
+/* u^T exp(x B) v */
+static __device__ __noinline__ double spec_bilinear(const double *u, int su, const double *v, const double *ev, const double *evi, int n, double x) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const double b = evi[i], ex = pht_exp(ev[i] * x);
+        if (b > 0.0 && i + 1 < n) {
+            double sn, cs; sincos(b * x, &sn, &cs);
+            const double u1 = u[i * su], u2 = u[(i + 1) * su], v1 = v[i], v2 = v[i + 1];
+            acc += ex * (cs * (u1 * v1 + u2 * v2) + sn * (u1 * v2 - u2 * v1));
+            i++;
+        } else acc += (u[i * su] * ex) * v[i];
+    }
+    return acc;
+}
+/* out = exp(x B) v, out with stride so */
+static __device__ __noinline__ void spec_apply(double *out, int so, const double *v, const double *ev, const double *evi, int n, double x) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) {
+        const double b = evi[i], ex = pht_exp(ev[i] * x);
+        if (b > 0.0 && i + 1 < n) {
+            double sn, cs; sincos(b * x, &sn, &cs);
+            const double v1 = v[i], v2 = v[i + 1];
+            out[i * so] = ex * (cs * v1 + sn * v2); out[(i + 1) * so] = ex * (cs * v2 - sn * v1);
+            i++;
+        } else out[i * so] = ex * v[i];
+    }
+}
 
 /* log-density closures.  The evaluation itself is ONE out-of-line function per sampler: ARMS calls its density from
  * five places, and five inlined copies of an n-term exp loop made the kernels' loop bodies larger than the
@@ -82,12 +116,22 @@ static __device__ __noinline__ double ecs_dens_gt(const double *pq, const double
 struct DensExact {
     double y_t, Sjj;
     __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
+        if (*sm.cplx) return pht_log(spec_bilinear(sm.PQ + threadIdx.x, ECS_THREADS, sm.Qinv_s, sm.evals, sm.evi, n, y_t - d)) + Sjj * d;
         return ecs_dens_exact(sm.PQ + threadIdx.x, sm.evals, sm.Qinv_s, n, y_t, Sjj, d);
     }
 };
 struct DensGt {
     double rem, scale;
     __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
+        if (*sm.cplx) {
+            const double x1 = rem - d;
+            const double r1 = x1 > 0 ? spec_bilinear(sm.PQ + threadIdx.x, ECS_THREADS, sm.Qinv_1, sm.evals, sm.evi, n, x1) : 1.0;
+            double dens;
+            if (scale <= 0.0) dens = pht_u2d(0x7ff8000000000000ULL);
+            else if (d < 0.0) dens = -pht_u2d(0x7ff0000000000000ULL);
+            else dens = (-d / scale) - pht_log(scale);
+            return pht_log(r1) + dens;
+        }
         return ecs_dens_gt(sm.PQ + threadIdx.x, sm.evals, sm.Qinv_1, n, rem, scale, d);
     }
 };
@@ -303,10 +347,11 @@ __device__ __forceinline__ void ecs_load_model(const SweepParams &p, EcsSmem &sm
     }
     for (int i = tid; i < n * (n + 1); i += ECS_THREADS) sm.Pfull[i] = p.model[ML.Pfull + i];
     for (int i = tid; i < n; i += ECS_THREADS) {
-        sm.evals[i] = p.model[ML.evals + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
+        sm.evals[i] = p.model[ML.evals + i]; sm.evi[i] = p.model[ML.evals_im + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
         sm.Qinv_s[i] = p.model[ML.Qinv_s + i]; sm.Qinv_1[i] = p.model[ML.Qinv_1 + i];
         sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
     }
+    if (tid == 0) { int c = 0; for (int i = 0; i < n; i++) c |= (p.model[ML.evals_im + i] != 0.0); *sm.cplx = c; }
     __syncthreads();
 }
 
@@ -407,8 +452,11 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         if (step && sm.s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
             const double num = (Sjj * y_t) + pht_log(sm.s[j]);
             double den = 0.0;
+            if (*sm.cplx) den = spec_bilinear(sm.Q + j, n, sm.Qinv_s, sm.evals, sm.evi, n, y_t);
+            else {
 #pragma unroll 1
-            for (int i = 0; i < n; i++) den += sm.Q[j + i * n] * pht_exp(sm.evals[i] * y_t) * sm.Qinv_s[i];
+                for (int i = 0; i < n; i++) den += sm.Q[j + i * n] * pht_exp(sm.evals[i] * y_t) * sm.Qinv_s[i];
+            }
             absorb = rng.next(p, iter) < pht_exp(num - pht_log(den));
         }
         if (absorb) {
@@ -438,9 +486,10 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         const double rem = y_t - d;
 #pragma unroll 1
         for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] = 0.0;
+        if (*sm.cplx) spec_apply(sm.PQ + tid, ECS_THREADS, sm.Qinv_s, sm.evals, sm.evi, n, rem);      /* PQ is free now: exp(rem B) Q^-1 s */
 #pragma unroll 1
         for (int col = 0; col < n; col++) {
-            const double tv = 1.0 * (pht_exp(sm.evals[col] * rem) * sm.Qinv_s[col]);
+            const double tv = *sm.cplx ? sm.PQ[col * ECS_THREADS + tid] : 1.0 * (pht_exp(sm.evals[col] * rem) * sm.Qinv_s[col]);
 #pragma unroll 1
             for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] += tv * sm.Q[r + col * n];
         }
@@ -499,7 +548,10 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
             const double x = y - t;
             /* e_j^T Q is row j of Q (the reference forms it with a dgemv over a unit vector) */
             double denom = 1.0;
-            if (x > 0) { denom = 0.0; for (int i = 0; i < n; i++) denom += sm.Q[j + i * n] * pht_exp(x * sm.evals[i]) * sm.Qinv_1[i]; }
+            if (x > 0) {
+                if (*sm.cplx) denom = spec_bilinear(sm.Q + j, n, sm.Qinv_1, sm.evals, sm.evi, n, x);
+                else { denom = 0.0; for (int i = 0; i < n; i++) denom += sm.Q[j + i * n] * pht_exp(x * sm.evals[i]) * sm.Qinv_1[i]; }
+            }
             if (rng.next(p, iter) < pht_exp(Sjj * (y - t)) / denom)                     /* :200-204 */
                 d = y - t + (1.0 / -Sjj) * (-pht_log(rng.next(p, iter)));
             else {
@@ -530,11 +582,19 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
                 sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
             }
             double r2 = 0.0;
+            const bool cx = *sm.cplx != 0;
+            if (cx) {
+                /* W = exp(x1 B) Q^-1 1 once; then every weight is a plain dot product with it */
+                spec_apply(sm.W + tid, ECS_THREADS, sm.Qinv_1, sm.evals, sm.evi, n, x1);
 #pragma unroll 1
-            for (int i = 0; i < n; i++) {
-                const double ex = pht_exp(x1 * sm.evals[i]);
-                sm.W[i * ECS_THREADS + tid] = ex;
-                r2 += sm.PQ[i * ECS_THREADS + tid] * ex * sm.Qinv_1[i];
+                for (int i = 0; i < n; i++) r2 += sm.PQ[i * ECS_THREADS + tid] * sm.W[i * ECS_THREADS + tid];
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < n; i++) {
+                    const double ex = pht_exp(x1 * sm.evals[i]);
+                    sm.W[i * ECS_THREADS + tid] = ex;
+                    r2 += sm.PQ[i * ECS_THREADS + tid] * ex * sm.Qinv_1[i];
+                }
             }
             double sofar = 0.0; k = 0;
 #pragma unroll 1
@@ -543,7 +603,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
                 if (Plk == 0.0) { k++; continue; }
                 double r1 = 0.0;
 #pragma unroll 1
-                for (int i = 0; i < n; i++) r1 += sm.Q[k + i * n] * sm.W[i * ECS_THREADS + tid] * sm.Qinv_1[i];
+                for (int i = 0; i < n; i++) r1 += cx ? sm.Q[k + i * n] * sm.W[i * ECS_THREADS + tid] : sm.Q[k + i * n] * sm.W[i * ECS_THREADS + tid] * sm.Qinv_1[i];
                 sofar += r1 * Plk / r2; k++;
             }
             k--; if (k < 0) k = 0;

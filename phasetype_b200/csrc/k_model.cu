@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(64) k_spectral_inject(UpdateParams p, const do
     const int n = p.n, tid = threadIdx.x;
     const ModelLayout L = ModelLayout::make(n, p.m);
     double *M = p.model;
-    for (int i = tid; i < n; i += blockDim.x) M[L.evals + i] = inject[i];
+    for (int i = tid; i < n; i += blockDim.x) { M[L.evals + i] = inject[i]; M[L.evals_im + i] = 0.0; }
     for (int i = tid; i < n * n; i += blockDim.x) { M[L.Q + i] = inject[n + i]; M[L.Qinv + i] = inject[n + n * n + i]; }
     __syncthreads();
     if (tid < n) {
@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(64) k_spectral_solve(UpdateParams p) {
     if (tid == 0) {
         const int st = pht_eigen_real(n, M + L.S, M + L.evals, M + L.Q, M + L.Qinv, w, w + n * n, w + 2 * n * n,
                                       w + 2 * n * n + n, w + 2 * n * n + 2 * n);
-        if (st & 2) atomicOr(&p.state->error, 16);
+        /* complex pairs (st & 2) are not an error: evals_im marks them and the samplers use the real block form */
         if (st & 5) atomicOr(&p.state->error, 32);
+        const double *im = w + 2 * n * n + 2 * n;
+        for (int i = 0; i < n; i++) M[L.evals_im + i] = im[i];
     }
     __syncthreads();
     if (tid < n) {

@@ -1,6 +1,10 @@
 /*
- * pht_eigen.h -- spectral decomposition S = Q diag(evals) Q^-1 of a small real matrix with real
- * spectrum, written once for the device (k_model.cu: k_spectral_solve) and the host checkers.
+ * pht_eigen.h -- spectral decomposition S = Q diag(evals) Q^-1 of a small real matrix, written once for the
+ * device (k_model.cu: k_spectral_solve) and the host checkers.  Real spectrum: exactly that.  Complex pairs
+ * a +- ib: the REAL block form S = Q B Q^-1, where the two columns of Q that belong to the pair hold the real and
+ * the imaginary part of its eigenvector and B has the 2x2 block [[a, b], [-b, a]] there, so that
+ * exp(xS) = Q exp(xB) Q^-1 with exp(x [[a, b], [-b, a]]) = e^{ax} [[cos bx, sin bx], [-sin bx, cos bx]] --
+ * everything stays real arithmetic (evals[] holds a twice, the work array e[] holds +b, -b on return).
  *
  * Replaces, for the engine, what the reference obtains from LAPACK dgeevx + dgetrf/dgetri
  * (src/utility.c:87-129 via LJMA_eigen / LJMA_inverse).  LAPACK is a third-party dependency of the
@@ -13,8 +17,9 @@
  * No balancing step (dgeevx is called with balanc = 'B'): generator matrices are already well scaled.
  *
  * Returns 0 on success; bit 0 set if the QR iteration did not converge, bit 1 if a complex pair was found
- * (the reference prints "Error: imaginary part of eigenvalue" and carries on with meaningless vectors,
- * src/utility.c:118-121), bit 2 if Q is numerically singular.
+ * (informational: the decomposition is then the block form above; the reference prints "Error: imaginary part of
+ * eigenvalue" and carries on using the packed columns as if they were real eigenvectors, src/utility.c:118-121),
+ * bit 2 if Q is numerically singular.
  *
  * Work space: H, V (n*n each, row-major), ort, d, e (n each).  S, Q, Qinv are column-major.
  */
@@ -29,6 +34,17 @@
 #define PHT_ESQRT(x) __builtin_sqrt(x)
 #endif
 #define PHT_EABS(x) ((x) < 0.0 ? -(x) : (x))
+
+/* (ar + i ai) / (br + i bi), Smith's scaling */
+PHT_HD void pht_cdiv(double ar, double ai, double br, double bi, double *cr, double *ci) {
+    if (PHT_EABS(br) > PHT_EABS(bi)) {
+        const double r = bi / br, dd = br + r * bi;
+        *cr = (ar + r * ai) / dd; *ci = (ai - r * ar) / dd;
+    } else {
+        const double r = br / bi, dd = bi + r * br;
+        *cr = (r * ar + ai) / dd; *ci = (r * ai - ar) / dd;
+    }
+}
 
 PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, double *Qinv,
                           double *H, double *V, double *ort, double *d, double *e) {
@@ -203,11 +219,55 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
         }
     }
 
-    /* ---- back-substitution: eigenvectors of the quasi-triangular form (real eigenvalues only) */
+    /* ---- back-substitution: eigenvectors of the quasi-triangular form */
     if (norm != 0.0 && !(status & 1)) {
         for (n = nn - 1; n >= 0; n--) {
             p = d[n]; q = e[n];
-            if (q != 0.0) continue;                     /* complex pair: flagged above, vectors left untouched */
+            if (q > 0.0) continue;                      /* first column of a complex pair: done together with the second */
+            if (q < 0.0) {
+                /* complex pair in rows/columns n-1, n: column n-1 receives the real, column n the imaginary part of the
+                 * eigenvector of d + i e[n-1] (the hqr2 back-substitution for a complex vector) */
+                int l = n - 1;
+                double cr, ci, ra, sa, vr, vi;
+                if (PHT_EABS(HH(n, n - 1)) > PHT_EABS(HH(n - 1, n))) {
+                    HH(n - 1, n - 1) = q / HH(n, n - 1);
+                    HH(n - 1, n) = -(HH(n, n) - p) / HH(n, n - 1);
+                } else {
+                    pht_cdiv(0.0, -HH(n - 1, n), HH(n - 1, n - 1) - p, q, &cr, &ci);
+                    HH(n - 1, n - 1) = cr; HH(n - 1, n) = ci;
+                }
+                HH(n, n - 1) = 0.0; HH(n, n) = 1.0;
+                for (int i = n - 2; i >= 0; i--) {
+                    ra = 0.0; sa = 0.0;
+                    for (int j = l; j <= n; j++) { ra = ra + HH(i, j) * HH(j, n - 1); sa = sa + HH(i, j) * HH(j, n); }
+                    w = HH(i, i) - p;
+                    if (e[i] < 0.0) { z = w; r = ra; s = sa; }
+                    else {
+                        l = i;
+                        if (e[i] == 0.0) {
+                            pht_cdiv(-ra, -sa, w, q, &cr, &ci);
+                            HH(i, n - 1) = cr; HH(i, n) = ci;
+                        } else {
+                            x = HH(i, i + 1); y = HH(i + 1, i);
+                            vr = (d[i] - p) * (d[i] - p) + e[i] * e[i] - q * q;
+                            vi = (d[i] - p) * 2.0 * q;
+                            if (vr == 0.0 && vi == 0.0) vr = eps * norm * (PHT_EABS(w) + PHT_EABS(q) + PHT_EABS(x) + PHT_EABS(y) + PHT_EABS(z));
+                            pht_cdiv(x * r - z * ra + q * sa, x * s - z * sa - q * ra, vr, vi, &cr, &ci);
+                            HH(i, n - 1) = cr; HH(i, n) = ci;
+                            if (PHT_EABS(x) > PHT_EABS(z) + PHT_EABS(q)) {
+                                HH(i + 1, n - 1) = (-ra - w * HH(i, n - 1) + q * HH(i, n)) / x;
+                                HH(i + 1, n) = (-sa - w * HH(i, n) - q * HH(i, n - 1)) / x;
+                            } else {
+                                pht_cdiv(-r - y * HH(i, n - 1), -s - y * HH(i, n), z, q, &cr, &ci);
+                                HH(i + 1, n - 1) = cr; HH(i + 1, n) = ci;
+                            }
+                        }
+                        t = PHT_EABS(HH(i, n - 1)); if (PHT_EABS(HH(i, n)) > t) t = PHT_EABS(HH(i, n));
+                        if ((eps * t) * t > 1) for (int j = i; j <= n; j++) { HH(j, n - 1) = HH(j, n - 1) / t; HH(j, n) = HH(j, n) / t; }
+                    }
+                }
+                continue;
+            }
             int l = n;
             HH(n, n) = 1.0;
             for (int i = n - 1; i >= 0; i--) {
@@ -245,6 +305,9 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
     for (int k = 0; k < nn; k++) {
         double nrm = 0.0;
         for (int i = 0; i < nn; i++) nrm += VV(i, k) * VV(i, k);
+        /* the two columns of a complex pair are one complex vector: one common factor, or S [p q] = [p q] B breaks */
+        if (e[k] > 0.0 && k + 1 < nn) for (int i = 0; i < nn; i++) nrm += VV(i, k + 1) * VV(i, k + 1);
+        if (e[k] < 0.0 && k > 0) for (int i = 0; i < nn; i++) nrm += VV(i, k - 1) * VV(i, k - 1);
         nrm = PHT_ESQRT(nrm);
         if (!(nrm > 0.0)) nrm = 1.0;
         evals[k] = d[k];

@@ -1,5 +1,5 @@
 """Edge cases of the path on the GPU, each checked against the oracle: a single phase, single and zero observations,
-every observation censored, an empty shard, a complex spectrum under a spectral sampler, and the L2-flush aid."""
+every observation censored, an empty shard, and the L2-flush aid (complex spectra: tests/test_complex_gpu.py)."""
 import numpy as np
 import pytest
 
@@ -93,21 +93,6 @@ def test_zero_observations_and_empty_shard(method):
     N, B, z = eng.sweep_stats()
     eng.close()
     assert not N.any() and not B.any() and not z.any()
-
-
-def test_complex_spectrum_is_reported_not_sampled():
-    """The reference carries on with a meaningless Q when S has complex eigenvalues (src/utility.c:118-121); the engine's
-    solver raises the error word instead."""
-    import phasetype_b200 as pb
-    wl = synth.config(3, "MHRS", l=256)          # unsymmetrised dense 8-phase generator: complex pairs
-    ev = np.linalg.eigvals(np.array(util.assemble(wl.T, wl.C, wl.theta, wl.n)[0]).reshape(wl.n, wl.n, order="F"))
-    if np.abs(ev.imag).max() < 1e-9:
-        pytest.skip("this generator happens to have a real spectrum")
-    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=2, seed=1)
-    eng.set_theta(wl.theta, next_iter=1)
-    with pytest.raises(pb.EngineError, match="complex eigenvalues"):
-        eng.run(1)
-    eng.close()
 
 
 def test_l2_flush_does_not_change_the_chain():

@@ -22,7 +22,7 @@ def _ndev():
 
 
 @pytest.mark.parametrize("method,cid,l,kswitch,cap,mhit", [("MHRS", 3, 60000, "512", "8", 1), ("MHRS", 2, 30000, "512", "4", 3),
-                                                           ("MHRS", 3, 300000, "", "", 1), ("ECS", 2, 8000, "", "", 1), ("ECS", 4, 4000, "", "", 1),
+                                                           ("MHRS", 3, 300000, "", "", 1), ("ECS", 2, 8000, "", "", 1), ("ECS", 4, 2000, "", "", 1),
                                                            ("DCS", 2, 8000, "", "", 1)])
 def test_ljma_gibbs_on_all_devices_equals_oracle(method, cid, l, kswitch, cap, mhit, monkeypatch):
     import phasetype_b200 as pb
