@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "libphtoracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libphtref.so")
 REF_LIBM_SO = os.path.join(HERE, "_ref", "libphtref_libm.so")
+REG_SO = os.path.join(HERE, "_ref", "PhaseType_reg.so")
 REFERENCE_ROOT = "/root/reference"
 
 N_COUNTERS = 16
@@ -36,6 +37,8 @@ def build(target="all"):
     if target in ("all", "ref") and os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
         targets.append("ref")
         targets.append("ref-libm")
+        if os.path.exists(os.path.join(HERE, "..", "phasetype_b200", "libpht_b200.so")):
+            targets.append("reg")
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
 
 

@@ -157,3 +157,22 @@ def test_start_row_follows_the_reference_rule_without_a_device():
     assert np.array_equal(res[0], want[0])
     res = pb.ljma_gibbs(3, 1, 2, 3, 2, nu, zeta, T, Cm, y, cens, [0.25, 7.5])
     assert np.array_equal(res[0], [0.25, 7.5]) and np.isnan(res[1:]).all()
+
+
+def test_reference_registration_table_binds_the_drop_in():
+    """The reference's src/Registrations.c, unmodified, compiled against stand-in R headers and linked with
+    libpht_b200.so (oracle/Makefile `reg`): R_init_PhaseType must register LJMA_Gibbs as a 15-argument .C routine with
+    the reference's argument types, pointing at the product library's symbol, and switch dynamic lookup off."""
+    import ctypes as C
+    from oracle import pyoracle as po
+    if not os.path.exists(po.REG_SO):
+        pytest.skip("oracle/_ref/PhaseType_reg.so not built (needs /root/reference)")
+    reg = C.CDLL(po.REG_SO)
+    fun = C.c_void_p(); nargs = C.c_int(); types = (C.c_uint * 32)(); dyn = C.c_int(); force = C.c_int()
+    assert reg.phtreg_lookup(b"LJMA_Gibbs", C.byref(fun), C.byref(nargs), types, 32, C.byref(dyn), C.byref(force)) == 0
+    INT, REAL = 13, 14
+    assert nargs.value == 15
+    assert list(types[:15]) == [INT] * 5 + [REAL] * 2 + [INT] + [REAL] * 2 + [INT] * 2 + [REAL, INT, REAL]
+    assert dyn.value == 0 and force.value == 1
+    assert fun.value == C.cast(pb.lib().LJMA_Gibbs, C.c_void_p).value
+    assert hasattr(reg, "R_init_PhaseType")
