@@ -449,6 +449,23 @@ def main():
                               "workload": wl_sym.name, "steps": 5, "warmup": 3, "gpu_launches": r2["launches"],
                               "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "issue", "kernel", "kernel_ms", "work_per_path")}}
             line["other_methods"] = others
+            # ---- the other BASELINE shapes, each at the size BASELINE.json states for one GPU's share (fewer sweeps):
+            # C2 = 4-phase Coxian, 10^6 exact observations; C4 = 16-phase tied-rate reliability structure, 10^7
+            # observations, ECS (its stated sampler; MHRS cannot sample observations whose survival probability is below
+            # 2^-32 and reports that); C5 = 32-phase general PHT: one GPU's share of a 2 x 10^7 slice (the full 10^8 is an
+            # 8-GPU job: profiles/r2_configs.md)
+            if args.config == 3:
+                oc = {}
+                for cid, m2, l2 in ((2, "MHRS", 10 ** 6), (2, "ECS", 10 ** 6), (2, "DCS", 10 ** 6), (4, "ECS", 10 ** 7), (5, "MHRS", 2500000)):
+                    wc = synth.config(cid, m2, l=l2)
+                    r2 = R.timed(wc, m2, np.ascontiguousarray(wc.y), np.ascontiguousarray(wc.censored), float(wc.y.sum()), 5, 3)
+                    rf = R.roofline(wc, m2, r2, wc.l, fma_rate)
+                    oc["C%d:%s" % (cid, m2)] = {"value": wc.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,
+                                                "workload": wc.name, "phases": wc.n, "parameters": wc.m, "observations": wc.l, "steps": 5, "warmup": 3,
+                                                "gpu_launches": r2["launches"],
+                                                "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_ms", "work_per_path")}}
+                    del wc
+                line["other_configs"] = oc
         if not args.no_cpu:
             from oracle import pyoracle as po
             po.build()

@@ -32,7 +32,15 @@ extern "C" {
  *   PHT_B200_DEVICE   (CUDA ordinal, default 0)
  *   PHT_B200_GRAPH    (0: launch the sweep's kernels directly instead of replaying a CUDA graph)
  *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail, default 256)
- * (multi-GPU runs are one process per GPU on the layer-2 API: pht_engine_create with rank/world + pht_engine_comm_init) */
+ *   PHT_B200_GPUS     (devices to fan out over, starting at PHT_B200_DEVICE; default: one per 2^19 observations, at most
+ *                      all visible.  One host thread + one engine per device, NCCL all-reduce of the statistics, peer
+ *                      windows for the global MHRS tail; the chain does not depend on the number of devices)
+ *   PHT_B200_ZBITS    (fractional bits of the fixed-point sojourn totals; default from sum(y))
+ *   PHT_B200_SEED_EXACT (use PHT_B200_SEED as is even with start values given; default: the start vector is mixed into
+ *                      the key so that a resumed run does not replay the streams of the run it continues)
+ *   PHT_B200_BETA     (comma-separated Dirichlet prior of the start distribution, n values: switches its update on;
+ *                      PHT_B200_PI0 = comma-separated initial pi, default e1; PHT_B200_PI_OUT = file that receives the
+ *                      it x n draws as text, one row per iteration -- `res` has no columns for them) */
 void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, double *zeta,
                 int *T, double *C, double *y, int *l, int *censored, double *start,
                 int *silent, double *res);
@@ -93,6 +101,15 @@ int pht_engine_peer_attach(pht_engine *e, const void *handles);
 /* parameter vector (length m) the next sweep starts from, and the index that sweep gets */
 int pht_engine_set_theta(pht_engine *e, const double *theta, uint32_t next_iter);
 int pht_engine_get_theta(pht_engine *e, double *theta);
+
+/* Start distribution.  The reference fixes pi = e1 and leaves its update as FIX ME (src/PHT_MCMC_Aslett.c:190-193) although
+ * R passes a Dirichlet prior `beta` down to the wrapper (R/phtMCMC2.R:20-21).  pi (n values, may be NULL: keep) sets the
+ * distribution the samplers start their paths from; beta (n positive values, may be NULL: no update) switches on the
+ * conjugate update pi | paths ~ Dirichlet(beta + B) at the end of every sweep.  pht_engine_pi_rows returns the draws of
+ * the last pht_engine_run (rows x n, row-major). */
+int pht_engine_set_pi(pht_engine *e, const double *pi, const double *beta);
+int pht_engine_get_pi(pht_engine *e, double *pi);
+int pht_engine_pi_rows(pht_engine *e, int rows, double *out);
 
 /* run `nsweeps` Gibbs sweeps; row r of out (nsweeps x m, row-major) is the draw of sweep r.
  * out may be NULL (results stay on the device; fetch later with pht_engine_get_theta). */

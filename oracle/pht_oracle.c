@@ -86,6 +86,15 @@ void pho_embedded(int n, const double *S, const double *s, double *P, double *Pf
 /* ------------------------------------------------------------------ a6 */
 typedef struct { int B, pre; } path_ends;
 
+/* Start distribution of the paths.  The reference fixes it to e1 (src/PHT_MCMC_Aslett.c:190-193) but every sampler takes
+ * it as an argument; pho_set_pi lets a test run them from another one (n = 0 restores e1). */
+static double g_pi[64]; static int g_pi_n = 0;
+void pho_set_pi(const double *pi, int n) { g_pi_n = (pi && n > 0 && n <= 64) ? n : 0; for (int i = 0; i < g_pi_n; i++) g_pi[i] = pi[i]; }
+static void pi_init(double *pi, int n) {
+    if (g_pi_n == n) for (int i = 0; i < n; i++) pi[i] = g_pi[i];
+    else { for (int i = 0; i < n; i++) pi[i] = 0.0; pi[0] = 1.0; }
+}
+
 /* One call of the rejection sampler: src/Simulate_AbsCTMC_gt_Bladt_MHRS.c:34-160.
  * `st` continues across calls exactly as R's generator would; one sub-stream per
  * attempt (LJMA_GUI at :120). */
@@ -146,7 +155,7 @@ int pho_mhrs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long co
     double *za = (double *)calloc(n, sizeof(double)), *zb = (double *)calloc(n, sizeof(double));
     int *Na = (int *)calloc((size_t)n * n, sizeof(int)), *Nb = (int *)calloc((size_t)n * n, sizeof(int));
     if (!pi || !za || !zb || !Na || !Nb) return -1;
-    pi[0] = 1.0;                                                      /* src/PHT_MCMC_Aslett.c:191-192 */
+    pi_init(pi, n);                                                   /* src/PHT_MCMC_Aslett.c:191-192 */
     for (long k = 0; k < count; k++) {
         pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
         double *zc = za, *zp = zb; int *Nc = Na, *Np = Nb;
@@ -324,7 +333,7 @@ int pho_dcs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     double *pi = (double *)calloc(n, sizeof(double)), *wk = (double *)calloc(4 * (size_t)n, sizeof(double));
     double *z = (double *)calloc(n, sizeof(double)); int *N = (int *)calloc((size_t)n * n, sizeof(int));
     if (!pi || !wk || !z || !N) return -1;
-    pi[0] = 1.0;
+    pi_init(pi, n);
     for (long k = 0; k < count; k++) {
         pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
         const int b = hob_end_state(&st, y[k], n, pi, Q, evals, Qinv, s, wk, wk + n);
@@ -665,7 +674,7 @@ int pho_ecs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     double *pi = (double *)calloc(n, sizeof(double)), *wk = (double *)calloc(4 * (size_t)n, sizeof(double));
     double *z = (double *)calloc(n, sizeof(double)); int *N = (int *)calloc((size_t)n * n, sizeof(int));
     if (!pi || !wk || !z || !N) return -1;
-    pi[0] = 1.0;
+    pi_init(pi, n);
     for (long k = 0; k < count; k++) {
         pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
         int B;

@@ -46,6 +46,9 @@ void pho_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double pho_unif_at(uint64_t seed, uint32_t iter, uint32_t obs, uint32_t sub, uint32_t d);
 double pho_rgamma_at(uint64_t seed, uint32_t iter, uint32_t sub, double shape, double scale);
 
+/* start distribution used by the *_paths functions (default e1 as in the reference; n = 0 restores it) */
+void pho_set_pi(const double *pi, int n);
+
 /* a2: embedded jump chain, src/PHT_MCMC_Aslett.c:280-297 */
 void pho_embedded(int n, const double *S, const double *s, double *P, double *Pfull);
 

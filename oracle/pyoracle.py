@@ -88,6 +88,7 @@ def oracle():
         L.pho_rgamma_at.restype = C.c_double
         L.pho_rgamma_at.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_double]
         L.pho_embedded.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        L.pho_set_pi.argtypes = [C.c_void_p, C.c_int]; L.pho_set_pi.restype = None
         L.pho_mhrs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
                                      _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _up]
         for f in ("pho_dcs_paths", "pho_ecs_paths", "pho_eigen", "pho_gibbs", "pho_sweep_stats", "pho_update",
@@ -151,6 +152,8 @@ def _load_ref(path):
         L.phtref_dcs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
                                        _dp, _dp, _dp, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, _up]
         L.phtref_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        if hasattr(L, "phtref_set_pi"):
+            L.phtref_set_pi.argtypes = [C.c_void_p, C.c_int]; L.phtref_set_pi.restype = None
         L.phtref_gibbs.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                    _ip, _dp, _dp, C.c_int, _ip, _dp, _dp]
     return r
@@ -253,6 +256,21 @@ def spectral_paths(impl, method, seed, it, y, cens, S, s, obs0=0, stride=1, want
     if B is None:
         return None, None, None, counters
     return B, N.reshape(count, n * n), z.reshape(count, n), counters
+
+
+def set_pi(pi=None):
+    """Start distribution for the *_paths functions of both checkers (None: the reference's e1)."""
+    a = None if pi is None else _f64(pi)
+    n = 0 if a is None else a.shape[0]
+    oracle().lib.pho_set_pi(_ptr(a), n)
+    if have_ref():
+        ref().lib.phtref_set_pi(_ptr(a), n)
+    if have_ref_libm() and hasattr(ref(True).lib, "phtref_set_pi"):
+        ref(True).lib.phtref_set_pi(_ptr(a), n)
+
+
+def rgamma_at(seed, it, sub, shape, scale):
+    return float(oracle().pho_rgamma_at(int(seed), int(it), int(sub), float(shape), float(scale)))
 
 
 def choose_zbits(sum_y):

@@ -39,6 +39,10 @@ typedef struct {
     double *workD; int *workI; double *z; int *N, *B; double *pi;
 } scratch;
 
+/* start distribution handed to the reference's samplers (they all take it as an argument); default e1 */
+static double g_pi[64]; static int g_pi_n = 0;
+void phtref_set_pi(const double *pi, int n) { g_pi_n = (pi && n > 0 && n <= 64) ? n : 0; for (int i = 0; i < g_pi_n; i++) g_pi[i] = pi[i]; }
+
 static int scratch_init(scratch *w, int n) {
     w->workD = (double *)calloc(WORK, sizeof(double));
     w->workI = (int *)calloc(WORK, sizeof(int));
@@ -47,7 +51,8 @@ static int scratch_init(scratch *w, int n) {
     w->B = (int *)calloc(n, sizeof(int));
     w->pi = (double *)calloc(n, sizeof(double));
     if (!w->workD || !w->workI || !w->z || !w->N || !w->B || !w->pi) return -1;
-    w->pi[0] = 1.0;            /* src/PHT_MCMC_Aslett.c:191-192 */
+    if (g_pi_n == n) for (int i = 0; i < n; i++) w->pi[i] = g_pi[i];
+    else w->pi[0] = 1.0;       /* src/PHT_MCMC_Aslett.c:191-192 */
     return 0;
 }
 static void scratch_free(scratch *w) {

@@ -18,7 +18,7 @@ SYMBOLS = [
     "pht_engine_destroy", "pht_comm_unique_id", "pht_engine_comm_init", "pht_engine_set_theta",
     "pht_engine_get_theta", "pht_engine_run", "pht_engine_enqueue", "pht_engine_sync", "pht_engine_last_ms",
     "pht_engine_sweep_stats", "pht_engine_paths", "pht_engine_set_spectral", "pht_engine_get_model",
-    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush", "pht_engine_peer_handle", "pht_engine_peer_attach", "pht_engine_round_trace",
+    "pht_engine_counters", "pht_fp64_fma_rate", "pht_engine_set_l2_flush", "pht_engine_peer_handle", "pht_engine_peer_attach", "pht_engine_round_trace", "pht_engine_set_pi", "pht_engine_get_pi", "pht_engine_pi_rows",
 ]
 PEER_HANDLE_BYTES = 128
 CNT_NAMES = ["paths", "attempts", "jumps", "dens_evals", "env_updates", "brent_evals", "arms_calls",
@@ -73,6 +73,9 @@ def lib():
     L.pht_fp64_fma_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.pht_engine_set_l2_flush.argtypes = [C.c_void_p, C.c_ulonglong]
     L.pht_engine_round_trace.argtypes = [C.c_void_p, _up]
+    L.pht_engine_set_pi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pht_engine_get_pi.argtypes = [C.c_void_p, _dp]
+    L.pht_engine_pi_rows.argtypes = [C.c_void_p, C.c_int, _dp]
     L.pht_engine_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
     L.pht_engine_peer_attach.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
@@ -192,6 +195,21 @@ class Engine:
                "evals": np.zeros(n), "Q": np.zeros(n * n), "Qinv": np.zeros(n * n)}
         _check(lib().pht_engine_get_model(self._h, *[out[k].ctypes.data for k in
                                                      ("S", "s", "P", "Pfull", "evals", "Q", "Qinv")]))
+        return out
+
+    def set_pi(self, pi=None, beta=None):
+        a = None if pi is None else np.ascontiguousarray(pi, dtype=np.float64)
+        b = None if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
+        _check(lib().pht_engine_set_pi(self._h, None if a is None else a.ctypes.data, None if b is None else b.ctypes.data))
+
+    def get_pi(self):
+        out = np.zeros(self.n)
+        _check(lib().pht_engine_get_pi(self._h, out))
+        return out
+
+    def pi_rows(self, rows):
+        out = np.zeros((int(rows), self.n))
+        _check(lib().pht_engine_pi_rows(self._h, int(rows), out))
         return out
 
     def round_trace(self):

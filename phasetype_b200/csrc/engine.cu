@@ -73,6 +73,7 @@ struct pht_engine {
     TailItem *d_items = nullptr; uint32_t *d_pend0 = nullptr, *d_pend1 = nullptr, *d_done = nullptr;
     unsigned long long *d_found = nullptr; uint32_t item_cap = 0;
     double *d_res = nullptr; int res_rows = 0;
+    double *d_beta = nullptr, *d_pires = nullptr;      /* Dirichlet prior of pi (n) and the pi draws of the last run (res_rows x n) */
     uint32_t *d_idx_exact = nullptr, *d_idx_cens = nullptr; unsigned long long n_exact = 0, n_cens = 0;   /* ECS launch lists */
     std::vector<uint8_t> h_cens;       /* host copy of the flags (ECS parity ranges) */
     double *d_inject = nullptr;        /* host-supplied evals | Q | Qinv (parity hook), else nullptr */
@@ -126,6 +127,7 @@ static UpdateParams update_params(pht_engine *e, double *res, int res_rows) {
     u.var_ptr = e->d_var_ptr; u.cell_i = e->d_cell_i; u.cell_j = e->d_cell_j;
     u.n = e->cfg.n; u.m = e->cfg.m; u.zbits = e->cfg.zbits;
     u.k0 = (uint32_t)e->cfg.seed; u.k1 = (uint32_t)(e->cfg.seed >> 32);
+    u.beta = e->d_beta; u.pires = (e->d_beta && res) ? e->d_pires : nullptr;
     return u;
 }
 
@@ -190,7 +192,7 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (void *q : e->ipc_opened) cudaIpcCloseMemHandle(q);
     void *bufs[] = { e->d_ys, e->d_cs, e->d_perm, e->d_glist, e->d_xw, e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_beta, e->d_pires, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -312,6 +314,8 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         e->grid_blocks = pht_dcs_grid_blocks(cfg->device, n);
         if (e->grid_blocks <= 0) { fail("DCS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
+    { const double one = 1.0;         /* start distribution e1, as the reference fixes it (src/PHT_MCMC_Aslett.c:190-193) */
+      CUE(cudaMemcpyAsync(e->d_model + e->L.pi, &one, sizeof(double), cudaMemcpyHostToDevice, e->stream)); CUE(cudaStreamSynchronize(e->stream)); }
     /* sweep index 1, start-value assembly (src/PHT_MCMC_Aslett.c:268) */
     DevState st; memset(&st, 0, sizeof(st)); st.iter = 1; st.first_assembly = 1;
     CUE(cudaMemcpyAsync(e->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
@@ -409,10 +413,48 @@ extern "C" int pht_engine_get_theta(pht_engine *e, double *theta) {
     return 0;
 }
 
+extern "C" int pht_engine_set_pi(pht_engine *e, const double *pi, const double *beta) {
+    if (!e) return fail("null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    const int n = e->cfg.n;
+    if (pi) {
+        double sum = 0.0;
+        for (int i = 0; i < n; i++) { if (!(pi[i] >= 0.0)) return fail("pi[%d] = %g is not a probability", i, pi[i]); sum += pi[i]; }
+        if (!(sum > 0.999999 && sum < 1.000001)) return fail("pi sums to %g, not 1", sum);
+        CU(cudaMemcpy(e->d_model + e->L.pi, pi, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }     /* kernel parameters change */
+    if (beta) {
+        for (int i = 0; i < n; i++) if (!(beta[i] > 0.0)) return fail("beta[%d] = %g: Dirichlet parameters must be positive", i, beta[i]);
+        if (!e->d_beta) CU(cudaMalloc(&e->d_beta, sizeof(double) * n));
+        CU(cudaMemcpy(e->d_beta, beta, sizeof(double) * n, cudaMemcpyHostToDevice));
+    } else if (e->d_beta) { CU(cudaFree(e->d_beta)); e->d_beta = nullptr; }
+    return 0;
+}
+extern "C" int pht_engine_get_pi(pht_engine *e, double *pi) {
+    if (!e || !pi) return fail("null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(pi, e->d_model + e->L.pi, sizeof(double) * e->cfg.n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int pht_engine_pi_rows(pht_engine *e, int rows, double *out) {
+    if (!e || !out || rows < 0) return fail("bad argument");
+    if (!e->d_beta || !e->d_pires) return fail("pi is not being inferred (pht_engine_set_pi with a prior first)");
+    if (rows > e->res_rows) return fail("%d rows asked, the last run produced at most %d", rows, e->res_rows);
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (rows) CU(cudaMemcpy(out, e->d_pires, sizeof(double) * (size_t)rows * e->cfg.n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 static int ensure_res(pht_engine *e, int rows) {
     if (rows <= e->res_rows) return 0;
     if (e->d_res) { CU(cudaFree(e->d_res)); e->d_res = nullptr; }
     CU(cudaMalloc(&e->d_res, sizeof(double) * (size_t)rows * e->cfg.m));
+    if (e->d_pires) { CU(cudaFree(e->d_pires)); e->d_pires = nullptr; }
+    CU(cudaMalloc(&e->d_pires, sizeof(double) * (size_t)rows * e->cfg.n));
     e->res_rows = rows;
     return 0;
 }

@@ -135,6 +135,8 @@ struct UpdateParams {
     const int *T; const double *C; const double *nu; const double *zeta;
     const int *var_ptr; const int *cell_i; const int *cell_j;   /* CSR: parameter -> cells in reference insertion order */
     int n, m, zbits; uint32_t k0, k1;
+    const double *beta;        /* Dirichlet prior of the start distribution (n), nullptr: pi stays as it is */
+    double *pires;             /* res_rows x n draws of pi, nullptr when pi is not inferred */
 };
 
 /* kernel launchers (each returns the cudaError of the launch) */

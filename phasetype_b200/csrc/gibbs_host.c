@@ -34,6 +34,18 @@ double unif_rand(void);
 
 #define MAX_GPUS 16
 
+/* comma-separated doubles from the environment: exactly n of them, else NULL */
+static double *env_vector(const char *name, int n) {
+    const char *s = getenv(name);
+    if (s == NULL || *s == 0 || n < 1) return NULL;
+    double *v = (double *)malloc(sizeof(double) * (size_t)n);
+    if (!v) return NULL;
+    int k = 0; char *end = NULL;
+    while (k < n) { v[k] = strtod(s, &end); if (end == s) break; k++; s = end; while (*s == ',' || *s == ' ') s++; if (*s == 0) break; }
+    if (k != n) { Rprintf("Warning (LJMA_Gibbs): %s needs %d comma-separated values; ignored\n", name, n); free(v); return NULL; }
+    return v;
+}
+
 static uint64_t env_u64(const char *name, int *found) {
     const char *s = getenv(name);
     *found = (s != NULL && *s != 0);
@@ -58,6 +70,8 @@ typedef struct {
     char err[512];
     pthread_mutex_t err_lock;
     int devices[MAX_GPUS];
+    /* inference of the start distribution (PHT_B200_BETA): prior, initial value, and the draws (IT x n, row-major) */
+    int n; const double *beta, *pi0; double *pi_chain;
 } shared_t;
 
 typedef struct { shared_t *sh; int rank; } rank_arg;
@@ -96,6 +110,7 @@ static void *rank_main(void *argp) {
         if (!sh->failed && pht_engine_peer_attach(eng, sh->handles) != 0) set_error(sh, rank, pht_last_error());
         pthread_barrier_wait(&sh->bar);
     }
+    if (!sh->failed && (sh->beta || sh->pi0) && pht_engine_set_pi(eng, sh->pi0, sh->beta) != 0) set_error(sh, rank, pht_last_error());
     if (!sh->failed && pht_engine_set_theta(eng, sh->theta, 1u) != 0) set_error(sh, rank, pht_last_error());
     double *rows = NULL;
     if (rank == 0) {
@@ -115,6 +130,7 @@ static void *rank_main(void *argp) {
         if (rank == 0) {
             for (int r = 0; r < k; r++)
                 for (int v = 0; v < sh->M; v++) sh->res[(size_t)(1 + done - k + r) + (size_t)v * sh->IT] = rows[(size_t)r * sh->M + v];
+            if (sh->pi_chain && pht_engine_pi_rows(eng, k, sh->pi_chain + (size_t)(1 + done - k) * sh->n) != 0) set_error(sh, rank, pht_last_error());
             sh->done_rows = 1 + done;
             if (!sh->silent) {
                 Rprintf("\rProcessing iteration %d of %d (%.1lf%%)\r", done + 1, sh->IT, (100.0 * (done + 1)) / sh->IT); R_FlushConsole();
@@ -203,6 +219,13 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
     if (!*silent) { sh.batch = sh.sweeps / 100; if (sh.batch < 1) sh.batch = 1; }
     sh.base = &cfg; sh.y = y; sh.censored = censored; sh.l = (long)*l; sh.theta = theta; sh.res = res;
     sh.done_rows = 1;
+    /* start distribution: PHT_B200_BETA switches the Dirichlet update on, PHT_B200_PI0 sets the initial value */
+    double *beta = env_vector("PHT_B200_BETA", *n), *pi0 = env_vector("PHT_B200_PI0", *n);
+    sh.n = *n; sh.beta = beta; sh.pi0 = pi0;
+    if (beta) {
+        sh.pi_chain = (double *)calloc((size_t)IT * (size_t)*n, sizeof(double));
+        if (sh.pi_chain) for (int i = 0; i < *n; i++) sh.pi_chain[i] = pi0 ? pi0[i] : (i == 0 ? 1.0 : 0.0);
+    }
     pthread_mutex_init(&sh.err_lock, NULL);
     rank_arg args[MAX_GPUS];
     if (gpus == 1) {
@@ -232,6 +255,15 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
         const double na = na_real();
         for (int r = sh.done_rows; r < IT; r++) for (int v = 0; v < M; v++) res[(size_t)r + (size_t)v * IT] = na;
     }
+    if (sh.pi_chain && !sh.failed) {
+        const char *path = getenv("PHT_B200_PI_OUT");
+        FILE *f = (path && *path) ? fopen(path, "w") : NULL;
+        if (f) {
+            for (int r = 0; r < IT; r++) { for (int i = 0; i < *n; i++) fprintf(f, i ? ",%.17g" : "%.17g", sh.pi_chain[(size_t)r * *n + i]); fprintf(f, "\n"); }
+            fclose(f);
+        } else if (path && *path) Rprintf("Warning (LJMA_Gibbs): cannot write %s\n", path);
+    }
+    free(sh.pi_chain); free(beta); free(pi0);
     pthread_mutex_destroy(&sh.err_lock);
     free(theta);
 

@@ -47,21 +47,25 @@ struct DcsSmem {
     unsigned long long *zlo; long long *zhi; unsigned int *Nacc, *Bacc, *deg;
     __device__ __forceinline__ void carve(unsigned char *raw, int n) {
         double *d = reinterpret_cast<double *>(raw);
-        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * n; D = d; d += n * n;
+        /* Qinv and D are read with a lane-varying COLUMN (b) resp. ROW (j) and a uniform other index: their leading
+         * dimension is padded to an odd number of doubles so that those reads spread over the banks (with ld = n = 8
+         * they were 4-way conflicts: 3.8e9 per sweep, profiles/r1_final_dcs_1e7_ncu_full.md) */
+        const int ld = n | 1;
+        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * ld; D = d; d += n * ld;
         evals = d; d += n; s = d; d += n; pi = d; d += n; PIQ = d; d += n;
         X = d; d += n * THREADS; E = d; d += n * THREADS; P = d; d += n * THREADS; Z = d; d += n * THREADS;
         zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
         Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n; deg = Bacc + n;
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(4 * n * n + 4 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
+        return sizeof(double) * (size_t)(2 * n * n + 2 * n * (n | 1) + 4 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
     }
 };
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dcs_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, tid = threadIdx.x;
+    const int n = p.n, tid = threadIdx.x, ld = n | 1;
     const unsigned FULL = 0xffffffffu;
     const ModelLayout ML = ModelLayout::make(n, p.m);
     DcsSmem<THREADS> sm; sm.carve(smem_raw, n);
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     { bool cplx = false; for (int i = 0; i < n; i++) cplx = cplx || (p.model[ML.evals_im + i] != 0.0);
       if (cplx) { if (tid == 0 && blockIdx.x == 0) atomicOr(&p.state->error, 16); return; } }
     for (int i = tid; i < n * n; i += THREADS) {
-        sm.S[i] = p.model[ML.S + i]; sm.Q[i] = p.model[ML.Q + i]; sm.Qinv[i] = p.model[ML.Qinv + i]; sm.Nacc[i] = 0u;
+        sm.S[i] = p.model[ML.S + i]; sm.Q[i] = p.model[ML.Q + i]; sm.Qinv[(i % n) + (i / n) * ld] = p.model[ML.Qinv + i]; sm.Nacc[i] = 0u;
     }
     for (int i = tid; i < n; i += THREADS) {
         sm.evals[i] = p.model[ML.evals + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     /* observation-independent tables: D[j][i] = ev_i - S_jj, the degenerate flags, and pi^T Q in reference-BLAS order */
     for (int e = tid; e < n * n; e += THREADS) {
         const int j = e / n, i = e % n;
-        sm.D[j * n + i] = sm.evals[i] - sm.S[j + j * n];
+        sm.D[j * ld + i] = sm.evals[i] - sm.S[j + j * n];
     }
     for (int c = tid; c < n; c += THREADS) {
         double acc = 0.0;
@@ -154,14 +158,14 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 const double Sjj = sm.S[j_r + j_r * n];
                 eS = pht_exp(Sjj * T_r);
                 Ei = sm.E[gi * THREADS + col];
-                val1 = sm.Q[j_r + gi * n] * Ei * sm.Qinv[gi + b_r * n];                                      /* :118-121 */
+                val1 = sm.Q[j_r + gi * n] * Ei * sm.Qinv[gi + b_r * ld];                                      /* :118-121 */
             }
             if (wn) sm.X[gi * THREADS + col] = sm.PIQ[gi] * sm.X[gi * THREADS + col];                        /* p = (pi^T Q) o exp(ev y) */
             __syncwarp();
             if (wn) {                                                                                        /* (p^T Q^-1)_i s_i */
                 double acc = 0.0;
 #pragma unroll 1
-                for (int q = 0; q < n; q++) acc += sm.Qinv[q + gi * n] * sm.X[q * THREADS + col];
+                for (int q = 0; q < n; q++) acc += sm.Qinv[q + gi * ld] * sm.X[q * THREADS + col];
                 val1 = (0.0 + 1.0 * acc) * sm.s[gi];
             }
             double sum1 = 0.0;                                                                               /* P_ab, or the weights' total */
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             for (int q = 0; q < n; q++) sum1 += __shfl_sync(FULL, val1, gbase + q);
             if (wj) {
                 const unsigned dg = sm.deg[j_r];
-                sm.X[gi * THREADS + col] = ((dg >> gi) & 1u) ? T_r * Ei : (Ei - eS) / sm.D[j_r * n + gi];    /* :137-144 */
+                sm.X[gi * THREADS + col] = ((dg >> gi) & 1u) ? T_r * Ei : (Ei - eS) / sm.D[j_r * ld + gi];    /* :137-144 */
             }
             if (wn) sm.P[gi * THREADS + col] = val1 / sum1;
             __syncwarp();
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 if (gi != j_r) {                                                                              /* :148-159 */
                     double tmp = 0.0;
 #pragma unroll 1
-                    for (int q = 0; q < n; q++) tmp += sm.Q[gi + q * n] * sm.X[q * THREADS + col] * sm.Qinv[q + b_r * n];
+                    for (int q = 0; q < n; q++) tmp += sm.Q[gi + q * n] * sm.X[q * THREADS + col] * sm.Qinv[q + b_r * ld];
                     v = sm.S[j_r + gi * n] / sum1 * tmp;
                 }
                 sm.P[gi * THREADS + col] = v;
@@ -207,8 +211,8 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
 #pragma unroll 1
             for (int i = 0; i < n; i++) {
                 const double Ei = sm.E[i * THREADS + tid];
-                const double Ji = ((dg >> i) & 1u) ? bb * Ei : (Ei - sm.X[i * THREADS + tid]) / sm.D[j * n + i];
-                tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + b * n];
+                const double Ji = ((dg >> i) & 1u) ? bb * Ei : (Ei - sm.X[i * THREADS + tid]) / sm.D[j * ld + i];
+                tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + b * ld];
             }
             fb = coef * tmp - u;
             c_evals++;

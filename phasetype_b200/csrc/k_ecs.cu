@@ -113,17 +113,19 @@ static __device__ __noinline__ double ecs_dens_gt(const double *pq, const double
     else dens = (-d / scale) - pht_log(scale);
     return pht_log(r1) + dens;
 }
+template <bool CPLX>
 struct DensExact {
     double y_t, Sjj;
     __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
-        if (*sm.cplx) return pht_log(spec_bilinear(sm.PQ + threadIdx.x, ECS_THREADS, sm.Qinv_s, sm.evals, sm.evi, n, y_t - d)) + Sjj * d;
+        if (CPLX) return pht_log(spec_bilinear(sm.PQ + threadIdx.x, ECS_THREADS, sm.Qinv_s, sm.evals, sm.evi, n, y_t - d)) + Sjj * d;
         return ecs_dens_exact(sm.PQ + threadIdx.x, sm.evals, sm.Qinv_s, n, y_t, Sjj, d);
     }
 };
+template <bool CPLX>
 struct DensGt {
     double rem, scale;
     __device__ __forceinline__ double operator()(const EcsSmem &sm, int n, double d) const {
-        if (*sm.cplx) {
+        if (CPLX) {
             const double x1 = rem - d;
             const double r1 = x1 > 0 ? spec_bilinear(sm.PQ + threadIdx.x, ECS_THREADS, sm.Qinv_1, sm.evals, sm.evi, n, x1) : 1.0;
             double dens;
@@ -410,13 +412,12 @@ struct ListDispenser {
 };
 
 /* ------------------------------------------------------------------ exact observations */
-__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_ecs_exact(SweepParams p, ObsList list) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, tid = threadIdx.x;
+template <bool CPLX>
+__device__ __forceinline__ void ecs_exact_body(const SweepParams &p, const ObsList &list, EcsSmem &sm, int n) {
+    const int tid = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
-    EcsSmem sm; sm.carve(smem_raw, n);
     const uint32_t iter = p.state->iter;
-    ecs_load_model(p, sm, n);
+    constexpr bool cplx = CPLX;
     EcsCounters c = {0, 0, 0, 0, 0, 0, 0};
     ListDispenser disp; disp.init(list.count, &p.state->next_obs);
     PathRng rng; rng.seek(0);
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         if (step && sm.s[j] > 0.0) {                                                            /* :251-255, probAbsorb :120-136 */
             const double num = (Sjj * y_t) + pht_log(sm.s[j]);
             double den = 0.0;
-            if (*sm.cplx) den = spec_bilinear(sm.Q + j, n, sm.Qinv_s, sm.evals, sm.evi, n, y_t);
+            if (cplx) den = spec_bilinear(sm.Q + j, n, sm.Qinv_s, sm.evals, sm.evi, n, y_t);
             else {
 #pragma unroll 1
                 for (int i = 0; i < n; i++) den += sm.Q[j + i * n] * pht_exp(sm.evals[i] * y_t) * sm.Qinv_s[i];
@@ -477,7 +478,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
             for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.W[i * ECS_THREADS + tid];
             sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
         }
-        DensExact f; f.y_t = y_t; f.Sjj = Sjj;
+        DensExact<CPLX> f; f.y_t = y_t; f.Sjj = Sjj;
         double xinit[4];
         xinit[0] = y_t / 1e6; xinit[1] = y_t / 3.0; xinit[2] = xinit[1] * 2.0; xinit[3] = y_t - xinit[0];   /* :315-318 */
         const double d = arms_draw(p, iter, rng, sm, n, f, xinit, y_t, c);              /* :338 */
@@ -486,10 +487,10 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         const double rem = y_t - d;
 #pragma unroll 1
         for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] = 0.0;
-        if (*sm.cplx) spec_apply(sm.PQ + tid, ECS_THREADS, sm.Qinv_s, sm.evals, sm.evi, n, rem);      /* PQ is free now: exp(rem B) Q^-1 s */
+        if (cplx) spec_apply(sm.PQ + tid, ECS_THREADS, sm.Qinv_s, sm.evals, sm.evi, n, rem);      /* PQ is free now: exp(rem B) Q^-1 s */
 #pragma unroll 1
         for (int col = 0; col < n; col++) {
-            const double tv = *sm.cplx ? sm.PQ[col * ECS_THREADS + tid] : 1.0 * (pht_exp(sm.evals[col] * rem) * sm.Qinv_s[col]);
+            const double tv = cplx ? sm.PQ[col * ECS_THREADS + tid] : 1.0 * (pht_exp(sm.evals[col] * rem) * sm.Qinv_s[col]);
 #pragma unroll 1
             for (int r = 0; r < n; r++) sm.W[r * ECS_THREADS + tid] += tv * sm.Q[r + col * n];
         }
@@ -506,15 +507,23 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
     }
     ecs_finish(p, n, sm, c);
 }
+/* The spectrum of the sweep's generator is known on the device only: both variants are compiled into the kernel and the
+ * block takes one of them (the real-spectrum variant is the reference's arithmetic, bit for bit). */
+__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_ecs_exact(SweepParams p, ObsList list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n;
+    EcsSmem sm; sm.carve(smem_raw, n);
+    ecs_load_model(p, sm, n);
+    if (*sm.cplx) ecs_exact_body<true>(p, list, sm, n); else ecs_exact_body<false>(p, list, sm, n);
+}
 
 /* ------------------------------------------------------------------ censored observations */
-__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_ecs_gt(SweepParams p, ObsList list) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, tid = threadIdx.x;
+template <bool CPLX>
+__device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList &list, EcsSmem &sm, int n) {
+    const int tid = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
-    EcsSmem sm; sm.carve(smem_raw, n);
     const uint32_t iter = p.state->iter;
-    ecs_load_model(p, sm, n);
+    constexpr bool cplx = CPLX;
     EcsCounters c = {0, 0, 0, 0, 0, 0, 0};
     ListDispenser disp; disp.init(list.count, &p.state->unit_counter);
     PathRng rng; rng.seek(0);
@@ -549,7 +558,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
             /* e_j^T Q is row j of Q (the reference forms it with a dgemv over a unit vector) */
             double denom = 1.0;
             if (x > 0) {
-                if (*sm.cplx) denom = spec_bilinear(sm.Q + j, n, sm.Qinv_1, sm.evals, sm.evi, n, x);
+                if (cplx) denom = spec_bilinear(sm.Q + j, n, sm.Qinv_1, sm.evals, sm.evi, n, x);
                 else { denom = 0.0; for (int i = 0; i < n; i++) denom += sm.Q[j + i * n] * pht_exp(x * sm.evals[i]) * sm.Qinv_1[i]; }
             }
             if (rng.next(p, iter) < pht_exp(Sjj * (y - t)) / denom)                     /* :200-204 */
@@ -562,7 +571,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
                     for (int i = 0; i < n; i++) acc += sm.Q[i + col * n] * sm.P[j + i * n];
                     sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
                 }
-                DensGt f; f.rem = y - t; f.scale = -1.0 / Sjj;
+                DensGt<CPLX> f; f.rem = y - t; f.scale = -1.0 / Sjj;
                 double xinit[4];
                 xinit[0] = (y - t) / 1e6; xinit[1] = (y - t) / 3.0; xinit[2] = xinit[1] * 2.0; xinit[3] = y - t - xinit[0];   /* :227-230 */
                 d = arms_draw(p, iter, rng, sm, n, f, xinit, y - t, c);                 /* :250 */
@@ -582,7 +591,7 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
                 sm.PQ[col * ECS_THREADS + tid] = 0.0 + 1.0 * acc;
             }
             double r2 = 0.0;
-            const bool cx = *sm.cplx != 0;
+            const bool cx = cplx;
             if (cx) {
                 /* W = exp(x1 B) Q^-1 1 once; then every weight is a plain dot product with it */
                 spec_apply(sm.W + tid, ECS_THREADS, sm.Qinv_1, sm.evals, sm.evi, n, x1);
@@ -626,6 +635,13 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
         }
     }
     ecs_finish(p, n, sm, c);
+}
+__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_ecs_gt(SweepParams p, ObsList list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n;
+    EcsSmem sm; sm.carve(smem_raw, n);
+    ecs_load_model(p, sm, n);
+    if (*sm.cplx) ecs_gt_body<true>(p, list, sm, n); else ecs_gt_body<false>(p, list, sm, n);
 }
 
 int pht_ecs_grid_blocks(int device, int n) {

@@ -73,10 +73,11 @@ __global__ void __launch_bounds__(64) k_assemble(UpdateParams p) {
         for (int k = 0; k <= n; k++) { sofar += Pf[i + k * n]; cum[k] = sofar; }
     }
     if (tid == n) {
-        /* start distribution is fixed to e1 in the reference (src/PHT_MCMC_Aslett.c:190-193) */
-        double *pi = M + L.pi, *cum = M + L.cum + n * n1;
+        /* running sums of the start distribution (row n of the scan tables).  pi is e1 unless the caller set another
+         * one or switched its Dirichlet update on (the reference fixes it to e1: src/PHT_MCMC_Aslett.c:190-193) */
+        const double *pi = M + L.pi; double *cum = M + L.cum + n * n1;
         double sofar = 0.0;
-        for (int k = 0; k < n; k++) { pi[k] = (k == 0) ? 1.0 : 0.0; sofar += pi[k]; cum[k] = sofar; }
+        for (int k = 0; k < n; k++) { sofar += pi[k]; cum[k] = sofar; }
         cum[n] = sofar;
     }
 }
@@ -108,8 +109,31 @@ __global__ void __launch_bounds__(128) k_update(UpdateParams p) {
         p.model[L.theta + v] = th;
         if (p.res != nullptr && row < (uint32_t)p.res_rows) p.res[(size_t)row * m + v] = th;
     }
+    /* start distribution: pi | paths ~ Dirichlet(beta + B), B = start-state counts of the sweep (the conjugate update the
+     * reference leaves as FIX ME, src/PHT_MCMC_Aslett.c:190-193; beta is R/phtMCMC2.R:20-21's prior).  Drawn as n
+     * Gamma(beta_i + B_i, 1) variates from parameter sub-streams m .. m+n-1, normalised in index order. */
+    __shared__ double gpi[PHT_NMAX];
+    if (p.beta != nullptr) {
+        const long long *Bacc = p.stats + n * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            pht_stream st; st.k0 = p.k0; st.k1 = p.k1;
+            pht_stream_seek(&st, iter, PHT_OBS_PARAM, (uint32_t)(m + i), 0);
+            gpi[i] = pht_rgamma(&st, p.beta[i] + (double)Bacc[i], 1.0);
+        }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { p.state->iter = iter + 1; p.state->first_assembly = 0; p.state->res_row = row + 1; }
+    if (threadIdx.x == 0) {
+        if (p.beta != nullptr) {
+            double sum = 0.0;
+            for (int i = 0; i < n; i++) sum += gpi[i];
+            for (int i = 0; i < n; i++) {
+                const double v = gpi[i] / sum;
+                p.model[L.pi + i] = v;
+                if (p.pires != nullptr && row < (uint32_t)p.res_rows) p.pires[(size_t)row * n + i] = v;
+            }
+        }
+        p.state->iter = iter + 1; p.state->first_assembly = 0; p.state->res_row = row + 1;
+    }
 }
 
 /* Spectral data for ECS / DCS (reference src/utility.c:87-129 via LJMA_eigen, then the GEMVs of
