@@ -105,8 +105,10 @@ int pht_engine_get_theta(pht_engine *e, double *theta);
 /* Start distribution.  The reference fixes pi = e1 and leaves its update as FIX ME (src/PHT_MCMC_Aslett.c:190-193) although
  * R passes a Dirichlet prior `beta` down to the wrapper (R/phtMCMC2.R:20-21).  pi (n values, may be NULL: keep) sets the
  * distribution the samplers start their paths from; beta (n positive values, may be NULL: no update) switches on the
- * conjugate update pi | paths ~ Dirichlet(beta + B) at the end of every sweep.  pht_engine_pi_rows returns the draws of
- * the last pht_engine_run (rows x n, row-major). */
+ * conjugate update pi | paths ~ Dirichlet(beta + B) at the end of every sweep (method MHRS only: a rejection sampler
+ * started from pi draws the start state from its conditional law given y; the reference's ECS and DCS samplers draw it
+ * from pi itself, which is exact for the degenerate pi the reference uses and nothing else).  pht_engine_pi_rows returns
+ * the draws of the last pht_engine_run (rows x n, row-major). */
 int pht_engine_set_pi(pht_engine *e, const double *pi, const double *beta);
 int pht_engine_get_pi(pht_engine *e, double *pi);
 int pht_engine_pi_rows(pht_engine *e, int rows, double *out);

@@ -426,6 +426,11 @@ extern "C" int pht_engine_set_pi(pht_engine *e, const double *pi, const double *
     }
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }     /* kernel parameters change */
     if (beta) {
+        /* The update needs start states drawn from their conditional law given y.  MHRS does that by construction (a
+         * rejection sampler from pi).  The reference's ECS and DCS samplers draw the start state from pi itself
+         * (src/Simulate_AbsCTMC_eq_Aslett_ECS.c:231-238, src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:88-95) -- exact only for
+         * the degenerate pi the reference always uses -- so B carries no information about pi there. */
+        if (method_of(e->cfg) != PHT_METHOD_MHRS) return fail("the start-distribution update needs method MHRS (ECS and DCS draw the start state from pi, not from its conditional law given y)");
         for (int i = 0; i < n; i++) if (!(beta[i] > 0.0)) return fail("beta[%d] = %g: Dirichlet parameters must be positive", i, beta[i]);
         if (!e->d_beta) CU(cudaMalloc(&e->d_beta, sizeof(double) * n));
         CU(cudaMemcpy(e->d_beta, beta, sizeof(double) * n, cudaMemcpyHostToDevice));

@@ -94,11 +94,26 @@ def test_posterior_of_pi_finds_the_truth():
     T, C, theta = util.general_model(R, s)
     m = theta.shape[0]
     # rates pinned by a tight prior at the truth, so that the chain explores pi only
-    eng = pb.Engine(n, T, C, np.full(m, 4000.0), 4000.0 / theta, y, np.zeros(l, dtype=np.int32), method=2, seed=5)
+    # MHRS with many MH proposals per sweep: on exact observations it reaches the conditional law as mhit grows
+    eng = pb.Engine(n, T, C, np.full(m, 4000.0), 4000.0 / theta, y, np.zeros(l, dtype=np.int32), method=1, mhit=100, seed=5)
     eng.set_pi(np.full(n, 1.0 / n), np.ones(n))
     eng.set_theta(theta, next_iter=1)
     eng.run(400)
     rows = eng.pi_rows(400)
     eng.close()
     post = rows[100:].mean(0)
-    assert np.abs(post - pi_true).max() < 0.05
+    # (the residual bias of the restarted independence sampler at mhit = 100 is ~0.02; at mhit = 1 the chain collapses
+    # onto the slowest phase -- SURVEY H6 applies to B as it does to N and z)
+    assert np.abs(post - pi_true).max() < 0.06
+
+
+def test_pi_update_is_refused_under_ecs_and_dcs():
+    import phasetype_b200 as pb
+    from phasetype_b200 import synth
+    wl = synth.config(2, "ECS", l=64)
+    for code in (2, 4):
+        eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=code, seed=1)
+        with pytest.raises(pb.EngineError, match="needs method MHRS"):
+            eng.set_pi(None, np.ones(wl.n))
+        eng.set_pi(np.full(wl.n, 1.0 / wl.n))          # a fixed general pi is fine (reference draw order)
+        eng.close()
