@@ -222,17 +222,21 @@ class Runner:
         self.last_create_s = time.perf_counter() - t0          # engine creation = upload of the shard (no communicator yet)
         if self.world > 1:
             torch, dist = self.torch, self.dist
-            buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if self.rank == 0:
-                import ctypes as C
-                raw = (C.c_char * 128)()
-                if pb.lib().pht_comm_unique_id(raw) != 0:
-                    raise RuntimeError(pb.lib().pht_last_error().decode())
-                buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-            dist.broadcast(buf, 0)
-            e.comm_init(bytes(buf.cpu().numpy().tobytes()))
+            use_nccl = os.environ.get("PHT_B200_NCCL", "0") not in ("", "0") or bool(os.environ.get("PHT_BENCH_NO_PEERS"))
+            if use_nccl:
+                # the statistics all-reduce as an ncclAllReduce inside the captured sweep (comparison arm)
+                buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if self.rank == 0:
+                    import ctypes as C
+                    raw = (C.c_char * 128)()
+                    if pb.lib().pht_comm_unique_id(raw) != 0:
+                        raise RuntimeError(pb.lib().pht_last_error().decode())
+                    buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+                dist.broadcast(buf, 0)
+                e.comm_init(bytes(buf.cpu().numpy().tobytes()))
             if not os.environ.get("PHT_BENCH_NO_PEERS"):
-                # the engines' exchange windows (global MHRS tail): every rank opens every other rank's through CUDA IPC
+                # the engines' exchange windows (statistics all-reduce + global MHRS tail, both inside the sweep's own
+                # kernels): every rank opens every other rank's through CUDA IPC
                 from phasetype_b200._lib import PEER_HANDLE_BYTES
                 mine = torch.frombuffer(bytearray(e.peer_handle()), dtype=torch.uint8).cuda()
                 allh = [torch.zeros(PEER_HANDLE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
@@ -382,7 +386,7 @@ def main():
                 "gibbs_iters_per_sec": args.steps / (res["total_ms"] * 1e-3),
                 "config": {"workload": wl.name, "method": method, "mhit": args.mhit, "phases": wl.n, "parameters": wl.m,
                            "observations": l_global, "observations_per_gpu": l_local,
-                           "sharding": "observation i of the %d -> rank i mod %d; per sweep one NCCL all-reduce of n^2+3n+1 int64 and the global MHRS tail over peer memory" % (l_global, world)
+                           "sharding": "observation i of the %d -> rank i mod %d; per sweep one all-reduce of n^2+3n+1 int64 (%s) and the global MHRS tail over peer memory" % (l_global, world, "ncclAllReduce" if os.environ.get("PHT_B200_NCCL", "0") not in ("", "0") else "k_allreduce_peer: NVLink peer stores + flag barrier, no library call")
                            if world > 1 else "single GPU",
                            "l2": "flushed: a %d MiB memset on the sweep stream before every sweep, inside the timed region" % (FLUSH_BYTES >> 20)},
                 "gpu_launches": res["launches"], "wall_ms_per_step": 1e3 * res["wall"] / args.steps,
@@ -431,7 +435,7 @@ def main():
         e2e = {"value": l_global * args.steps / dt if dt > 0 else None, "unit": "paths/s", "h2d_bytes_per_step": int(12 * l_global / args.steps),
                "d2h_bytes_per_step": int(8 * wl.m), "seconds": dt, "runs": 3,
                "note": "one LJMA_Gibbs(it=%d) call on host vectors driving %d GPU(s): engine creation, upload of y/censored (once per call, amortised over "
-                       "the sweeps), %s%d sweeps, download of res" % (args.steps + 1, world, "NCCL communicator and peer-window set-up, " if world > 1 else "", args.steps)}
+                       "the sweeps), %s%d sweeps, download of res" % (args.steps + 1, world, "peer-window set-up (no NCCL in the call), " if world > 1 else "", args.steps)}
     if rank == 0:
         line["e2e"] = e2e
         # ---- the other two samplers on the same shape (N = 1 only; fewer sweeps)

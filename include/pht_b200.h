@@ -33,8 +33,10 @@ extern "C" {
  *   PHT_B200_GRAPH    (0: launch the sweep's kernels directly instead of replaying a CUDA graph)
  *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail, default 256)
  *   PHT_B200_GPUS     (devices to fan out over, starting at PHT_B200_DEVICE; default: one per 2^19 observations, at most
- *                      all visible.  One host thread + one engine per device, NCCL all-reduce of the statistics, peer
- *                      windows for the global MHRS tail; the chain does not depend on the number of devices)
+ *                      all visible.  One host thread + one engine per device; the all-reduce of the statistics and the
+ *                      global MHRS tail run through peer memory inside the sweep's kernels; the chain does not depend
+ *                      on the number of devices)
+ *   PHT_B200_NCCL     (1: all-reduce the statistics with ncclAllReduce instead of the engine's own peer-memory kernel)
  *   PHT_B200_ZBITS    (fractional bits of the fixed-point sojourn totals; default from sum(y))
  *   PHT_B200_SEED_EXACT (use PHT_B200_SEED as is even with start values given; default: the start vector is mixed into
  *                      the key so that a resumed run does not replay the streams of the run it continues)
@@ -83,17 +85,22 @@ int pht_engine_create(pht_engine **out, const pht_config *cfg, const double *y_l
                       const int *cens_local, long l_local);
 void pht_engine_destroy(pht_engine *e);
 
-/* multi-GPU, one process per GPU: rank 0 calls pht_comm_unique_id, the 128 bytes
- * travel over the launcher's own channel, every rank calls pht_engine_comm_init. */
+/* multi-GPU, one process per GPU, statistics all-reduced by NCCL: rank 0 calls pht_comm_unique_id, the 128 bytes
+ * travel over the launcher's own channel, every rank calls pht_engine_comm_init.  Not needed when the engines'
+ * exchange windows are attached (below): the all-reduce then runs through them (k_allreduce_peer), unless
+ * PHT_B200_NCCL=1 asks for NCCL. */
 int pht_comm_unique_id(void *id128);
 int pht_engine_comm_init(pht_engine *e, const void *id128);
 
-/* MHRS, several GPUs of one box: the deepest part of the rejection tail (observations that need 10^5..10^8
- * attempts) is searched by all ranks together through peer memory (NVLink): each engine owns an exchange window,
+/* Several GPUs of one box: each engine owns an exchange window in device memory that its peers write into over NVLink.
+ * Two things run through it, inside the sweep's own kernels (no host, no library call): the per-sweep all-reduce of
+ * the statistics block (every method), and for MHRS the deepest part of the rejection tail (observations that need
+ * 10^5..10^8 attempts), which all ranks search together.
  * pht_engine_peer_handle writes an opaque PHT_PEER_HANDLE_BYTES handle for it, the launcher gathers the handles of
  * all ranks (rank order) and every rank calls pht_engine_peer_attach with the concatenation.  Works between
- * processes (CUDA IPC) and between engines of one process (direct peer access).  Optional: without it the tail
- * rounds stay local to each rank and the chain is the same, only slower to finish. */
+ * processes (CUDA IPC) and between engines of one process (direct peer access).  A multi-rank run needs either the
+ * windows or an NCCL communicator (pht_engine_comm_init) for its statistics; with NCCL only, the MHRS tail rounds stay
+ * local to each rank and the chain is the same, only slower to finish. */
 #define PHT_PEER_HANDLE_BYTES 128
 int pht_engine_peer_handle(pht_engine *e, void *handle);
 int pht_engine_peer_attach(pht_engine *e, const void *handles);

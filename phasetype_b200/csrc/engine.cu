@@ -66,6 +66,7 @@ struct pht_engine {
     double *d_ys = nullptr; uint8_t *d_cs = nullptr; uint32_t *d_perm = nullptr;   /* MHRS: the same observations by decreasing y */
     uint32_t *d_glist = nullptr; XchgWindow *d_xw = nullptr;                        /* MHRS global tail */
     XchgWindow *xpeer[PHT_MAX_WORLD] = {}; std::vector<void *> ipc_opened; bool peers_attached = false;
+    bool peer_reduce = false;          /* statistics all-reduced by k_allreduce_peer through the windows (else NCCL, if a communicator exists) */
     uint32_t k_switch = 1u << 15;
     double *d_model = nullptr; long long *d_stats = nullptr; DevState *d_state = nullptr;
     int *d_T = nullptr; double *d_C = nullptr, *d_nu = nullptr, *d_zeta = nullptr;
@@ -171,7 +172,13 @@ static int enqueue_sweep(pht_engine *e, double *res, int res_rows, bool time_ker
     if (time_kernel && e->kev_used + 2 <= (int)e->kev.size()) CU(cudaEventRecord(e->kev[e->kev_used++], e->stream));
     if (enqueue_paths(e, p)) return -1;
     if (time_kernel && (e->kev_used & 1)) CU(cudaEventRecord(e->kev[e->kev_used++], e->stream));
-    if (e->comm) {
+    if (e->peer_reduce) {
+        ReduceParams r; memset(&r, 0, sizeof(r));
+        r.stats = e->d_stats; r.len = stats_len(e->cfg.n); r.state = e->d_state; r.xw = e->d_xw;
+        r.rank = (uint32_t)e->cfg.rank; r.world = (uint32_t)e->cfg.world;
+        for (int k = 0; k < e->cfg.world && k < PHT_MAX_WORLD; k++) r.xpeer[k] = e->xpeer[k];
+        CU(pht_launch_peer_allreduce(r, e->stream)); e->launches++;
+    } else if (e->comm) {
         CU(pht_launch_pack_error(u, e->stream)); e->launches++;
         int rc = g_nccl.AllReduce(e->d_stats, e->d_stats, (size_t)stats_len(e->cfg.n), NCCL_INT64, NCCL_SUM, e->comm, e->stream);
         if (rc != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
@@ -268,6 +275,13 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     CUE(cudaMalloc(&e->d_cell_i, sizeof(int) * cell_i.size())); CUE(cudaMemcpy(e->d_cell_i, cell_i.data(), sizeof(int) * cell_i.size(), cudaMemcpyHostToDevice));
     CUE(cudaMalloc(&e->d_cell_j, sizeof(int) * cell_j.size())); CUE(cudaMemcpy(e->d_cell_j, cell_j.data(), sizeof(int) * cell_j.size(), cudaMemcpyHostToDevice));
 
+    if (cfg->world > 1) {
+        /* this rank's exchange window: all-reduce slots (every method) and the global MHRS tail (flags 0, found words NONE) */
+        CUE(cudaMalloc(&e->d_xw, sizeof(XchgWindow)));
+        CUE(cudaMemsetAsync(e->d_xw, 0, sizeof(XchgWindow), e->stream));
+        CUE(cudaMemsetAsync(e->d_xw->gfound, 0xFF, sizeof(e->d_xw->gfound), e->stream));
+        CUE(cudaStreamSynchronize(e->stream));
+    }
     if (method_of(e->cfg) == PHT_METHOD_MHRS) {
         /* Tail work lists: one arena with room for a quarter of the shard (at least 2^20 observations, at most all of
          * them).  In practice ~1 % of the observations plus one per resident lane are handed over; if the lists ever
@@ -288,15 +302,9 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
             CUE(cudaMalloc(&e->d_ys, ln * sizeof(double))); CUE(cudaMalloc(&e->d_cs, ln)); CUE(cudaMalloc(&e->d_perm, ln * sizeof(uint32_t)));
             CUE(pht_sort_by_y_desc(e->d_y, e->d_cens, l_local, e->d_ys, e->d_cs, e->d_perm, e->stream));
         }
-        /* global tail: the canonical list and this rank's exchange window (flags 0, found words NONE) */
+        /* global tail: the canonical list */
         if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
-        if (cfg->world > 1) {
-            CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
-            CUE(cudaMalloc(&e->d_xw, sizeof(XchgWindow)));
-            CUE(cudaMemsetAsync(e->d_xw, 0, sizeof(XchgWindow), e->stream));
-            CUE(cudaMemsetAsync(e->d_xw->gfound, 0xFF, sizeof(e->d_xw->gfound), e->stream));
-            CUE(cudaStreamSynchronize(e->stream));
-        }
+        if (cfg->world > 1) CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
         if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks) != 0) e->grid_blocks = 0;
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
@@ -367,7 +375,7 @@ extern "C" int pht_engine_peer_handle(pht_engine *e, void *handle) {
 
 extern "C" int pht_engine_peer_attach(pht_engine *e, const void *handles) {
     if (!e || !handles) return fail("null argument");
-    if (e->cfg.world == 1 || !e->d_xw) return 0;           /* nothing to share (single rank, or not an MHRS engine) */
+    if (e->cfg.world == 1 || !e->d_xw) return 0;           /* nothing to share (single rank) */
     CU(cudaSetDevice(e->cfg.device));
     for (int r = 0; r < e->cfg.world; r++) {
         PeerHandle h; memcpy(&h, (const char *)handles + (size_t)r * PHT_PEER_HANDLE_BYTES, sizeof(h));
@@ -391,6 +399,8 @@ extern "C" int pht_engine_peer_attach(pht_engine *e, const void *handles) {
         }
     }
     e->peers_attached = true;
+    /* the statistics go through the windows too, unless the launcher asks for the NCCL all-reduce (PHT_B200_NCCL=1) */
+    { const char *ev = getenv("PHT_B200_NCCL"); e->peer_reduce = !(ev && *ev && *ev != '0'); }
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }     /* kernel parameters change */
     return 0;
 }

@@ -82,7 +82,13 @@ struct TailItem {
  * flags), its owner only reads it locally. */
 #define PHT_MAX_WORLD 16
 #define PHT_GCAP 2048                     /* observations one rank can contribute to a global tail */
+#define PHT_STATS_MAX (PHT_NMAX * PHT_NMAX + 3 * PHT_NMAX + 1)
 struct XchgWindow {
+    /* all-reduce of the statistics block (k_allreduce_peer, every method): rank r stores its block into slot r of
+     * every window and raises sflags[r]; double buffered by the parity of the all-reduce count */
+    unsigned long long sflags[2][PHT_MAX_WORLD];
+    long long sstats[2][PHT_MAX_WORLD][PHT_STATS_MAX];
+    /* global MHRS tail */
     unsigned long long flags[PHT_MAX_WORLD];                      /* flags[r]: last barrier epoch rank r arrived at */
     unsigned long long gfound[2][PHT_MAX_WORLD * PHT_GCAP];        /* lowest surviving attempt per item, by round parity */
     uint32_t gcount[2][PHT_MAX_WORLD];                             /* items contributed by rank r, by sweep parity */
@@ -104,6 +110,7 @@ struct DevState {
     uint32_t n_gpend;          /* global tail: items not finished yet */
     uint32_t xdead;            /* a peer barrier timed out: no further waiting */
     unsigned long long xepoch; /* barrier epochs completed (monotonic over the life of the engine) */
+    unsigned long long sepoch; /* peer all-reduces completed (monotonic over the life of the engine) */
     unsigned long long counters[PHT_CNT_COUNT];
     /* measurement aid: per tail round (index = round number, accumulated over sweeps) the device-timer ns block 0 spent
      * searching / waiting at the barrier after the search / advancing, and the sum of pending items and of K */
@@ -139,7 +146,15 @@ struct UpdateParams {
     double *pires;             /* res_rows x n draws of pi, nullptr when pi is not inferred */
 };
 
+/* all-reduce of the statistics block through the exchange windows */
+struct ReduceParams {
+    long long *stats; int len; DevState *state;
+    XchgWindow *xw; XchgWindow *xpeer[PHT_MAX_WORLD];
+    uint32_t rank, world;
+};
+
 /* kernel launchers (each returns the cudaError of the launch) */
+cudaError_t pht_launch_peer_allreduce(const ReduceParams &p, cudaStream_t st);
 cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_pack_error(const UpdateParams &p, cudaStream_t st);

@@ -10,9 +10,9 @@
  *
  * Several GPUs: R calls the routine once, in one process (R/phtMCMC2.R:73), so the fan-out
  * happens here: one engine and one host thread per device, observation i -> device i mod G,
- * an NCCL communicator over the devices for the per-sweep all-reduce of the statistics, and
- * the engines' exchange windows attached to one another for the global MHRS tail.  Every
- * device draws the same parameters from the shared key, so rank 0's rows are the result.
+ * and the engines' exchange windows attached to one another (peer memory over NVLink) for the
+ * per-sweep all-reduce of the statistics and the global MHRS tail.  Every device draws the
+ * same parameters from the shared key, so rank 0's rows are the result.
  *
  * There is no CPU path: if an engine cannot be created, or the device raises its error word,
  * the routine reports through Rprintf and fills the rows it could not produce with NA, so
@@ -57,7 +57,7 @@ static double na_real(void) { const uint64_t u = 0x7FF00000000007A2ULL; double d
 
 /* what the host threads share */
 typedef struct {
-    int world, IT, M, sweeps, batch, silent;
+    int world, IT, M, sweeps, batch, silent, use_nccl;
     const pht_config *base;
     const double *y; const int *censored; long l;
     const double *theta;
@@ -103,10 +103,13 @@ static void *rank_main(void *argp) {
     if (!sh->failed && pht_engine_create(&eng, &cfg, yl, cl, l_local) != 0) set_error(sh, rank, pht_last_error());
     free(ys); free(cs);
     if (world > 1) {
-        if (rank == 0 && !sh->failed && pht_comm_unique_id(sh->nccl_id) != 0) set_error(sh, rank, pht_last_error());
+        /* The engines' exchange windows are attached to one another (direct peer pointers: one process): the per-sweep
+         * all-reduce of the statistics and the global MHRS tail both run through them, inside the sweep's own kernels.
+         * PHT_B200_NCCL=1 routes the all-reduce through an NCCL communicator instead (its set-up costs ~1 s on 8 GPUs). */
+        if (sh->use_nccl && rank == 0 && !sh->failed && pht_comm_unique_id(sh->nccl_id) != 0) set_error(sh, rank, pht_last_error());
         if (eng && pht_engine_peer_handle(eng, sh->handles + (size_t)rank * PHT_PEER_HANDLE_BYTES) != 0) set_error(sh, rank, pht_last_error());
         pthread_barrier_wait(&sh->bar);
-        if (!sh->failed && pht_engine_comm_init(eng, sh->nccl_id) != 0) set_error(sh, rank, pht_last_error());
+        if (sh->use_nccl && !sh->failed && pht_engine_comm_init(eng, sh->nccl_id) != 0) set_error(sh, rank, pht_last_error());
         if (!sh->failed && pht_engine_peer_attach(eng, sh->handles) != 0) set_error(sh, rank, pht_last_error());
         pthread_barrier_wait(&sh->bar);
     }
@@ -213,6 +216,7 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
     if (*silent) {
         Rprintf(" silent processing selected, there will be no further feedback until MCMC run complete"); R_FlushConsole();
     }
+    { const char *ev = getenv("PHT_B200_NCCL"); sh.use_nccl = (ev && *ev && *ev != '0'); }
     sh.world = gpus; sh.IT = IT; sh.M = M; sh.sweeps = IT - 1; sh.silent = *silent;
     /* progress text as the reference prints it (:273), once per batch of sweeps instead of per sweep */
     sh.batch = sh.sweeps;

@@ -209,6 +209,55 @@ cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st) {
 __global__ void k_pack_error(long long *stats, int len, const DevState *state) {
     if (threadIdx.x == 0) stats[len - 1] = state->error != 0 ? 1 : 0;
 }
+/* All-reduce (sum, int64) of the statistics block over the GPUs of the run WITHOUT a library call: every rank stores
+ * its block into its slot of every rank's exchange window (NVLink peer stores; its own window included), raises its
+ * flag there, waits until every rank's flag has arrived in its own window, and sums the slots it now holds locally,
+ * in rank order.  ~len * world 8-byte stores per rank and one flag round trip: the payload is n^2+3n+1 words, so this
+ * is a latency-sized exchange (a few microseconds over NVSwitch), captured in the sweep graph like any kernel.
+ * Slots and flags are double buffered by the parity of the all-reduce count: a rank can be at most one all-reduce
+ * ahead of the slowest (it needs everybody's flag to pass), so the buffer it overwrites has been read by all.
+ * The last word of the block says whether this rank's error word is raised, so every rank learns it (k_update). */
+__device__ __forceinline__ unsigned long long reduce_timer() {
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t;
+}
+__global__ void __launch_bounds__(256) k_allreduce_peer(const __grid_constant__ ReduceParams p) {
+    const int tid = threadIdx.x;
+    __shared__ unsigned long long s_epoch;
+    if (tid == 0) { p.stats[p.len - 1] = p.state->error != 0 ? 1 : 0; s_epoch = p.state->sepoch + 1ull; }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch; const int par = (int)(epoch & 1ull);
+    for (uint32_t r = 0; r < p.world; r++) {
+        volatile long long *dst = p.xpeer[r]->sstats[par][p.rank];
+        for (int i = tid; i < p.len; i += blockDim.x) dst[i] = p.stats[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < (int)p.world && p.state->xdead == 0u) {
+        volatile unsigned long long *mine = &p.xpeer[tid]->sflags[par][p.rank];
+        *mine = epoch;
+        __threadfence_system();
+        volatile unsigned long long *theirs = &p.xw->sflags[par][tid];
+        const unsigned long long t0 = reduce_timer();
+        while (*theirs < epoch) {
+            if (reduce_timer() - t0 > 4000000000ull) { p.state->xdead = 1u; atomicOr(&p.state->error, 64); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (p.state->xdead == 0u) {
+        for (int i = tid; i < p.len; i += blockDim.x) {
+            long long sum = 0;
+            for (uint32_t r = 0; r < p.world; r++) sum += const_cast<volatile long long *>(p.xw->sstats[par][r])[i];
+            p.stats[i] = sum;
+        }
+    } else if (tid == 0) p.stats[p.len - 1] = 1;
+    if (tid == 0) p.state->sepoch = epoch;
+}
+cudaError_t pht_launch_peer_allreduce(const ReduceParams &p, cudaStream_t st) {
+    k_allreduce_peer<<<1, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t pht_launch_pack_error(const UpdateParams &p, cudaStream_t st) {
     k_pack_error<<<1, 32, 0, st>>>(p.stats, stats_len(p.n), p.state);
     return cudaGetLastError();
