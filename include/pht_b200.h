@@ -52,6 +52,14 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
 #define PHT_METHOD_MHRS 1   /* reference src/PHT_MCMC_Aslett.c:69-71 */
 #define PHT_METHOD_ECS  2
 #define PHT_METHOD_DCS  4
+/* The two sampler variants the reference compiles but never dispatches, reachable here behind
+ * two further bits of the same mask; they have the lowest priority, so every mask the reference understands keeps its
+ * meaning.  Both take `mhit` like MHRS. */
+#define PHT_METHOD_MHS_HOBOLTH 8    /* LJMA_MHsample_Hobolth, src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:268-355: Hobolth paths
+                                       conditioned on the exit set {j : s_j > 0} + independence MH; censoring ignored by
+                                       the chain sampler (the MH step is skipped for a censored observation) */
+#define PHT_METHOD_MHS_ASLETT 16    /* LJMA_MHsample_Aslett (reverse = 0), src/Simulate_AbsCTMC_eq_Aslett_DCS.c:49-143: the
+                                       Aslett-DCS "alive at y" sampler for every observation + independence MH */
 #define PHT_MAX_PHASES  32
 
 typedef struct pht_engine pht_engine;

@@ -282,10 +282,12 @@ static int hob_end_state(pht_stream *st, double y, int n, const double *pi, cons
     return cat_scan(p, 1, n - 1, runif01(st));
 }
 
-/* src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:74-226 with w = Q^-1 e_b (column b of Q^-1, :124-130 of the caller) */
-static int hob_path(pht_stream *st, double y, int b, int n, const double *pi, const double *S, const double *Q,
+/* src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:74-226.  Live caller (eq_AslettHobolth_DCS.c:124-133): bvec = e_b, i.e. the
+ * exit set is the single state b and w = Q^-1 e_b (column b of Q^-1); then bvec may be NULL.  The MH variant
+ * (:268-355) passes a general indicator vector bvec with w = Q^-1 bvec.  *pre = the state the chain stays in to the end. */
+static int hob_path(pht_stream *st, double y, int b, const double *bvec, int n, const double *pi, const double *S, const double *Q,
                     const double *evals, const double *w, double *z, int *N, double *J, double *p,
-                    unsigned long long *cnt) {
+                    int *pre, unsigned long long *cnt) {
     for (int i = 0; i < n; i++) z[i] = 0.0;
     memset(N, 0, sizeof(int) * (size_t)n * n);
     const int B = cat_scan(pi, 1, n - 1, runif01(st));                               /* :88-95 */
@@ -295,8 +297,8 @@ static int hob_path(pht_stream *st, double y, int b, int n, const double *pi, co
         const double T = y - t, Sjj = S[j + j * n];
         double Pab = 0.0;
         for (int i = 0; i < n; i++) Pab += Q[j + i * n] * pht_exp(evals[i] * T) * w[i];     /* :118-121 */
-        if (j == b) {                                                                /* :124 (b[j] > 0) */
-            if (runif01(st) < pht_exp(Sjj * T) / Pab) { z[j] += T; N[j + j * n] = 1; break; }
+        if (bvec ? (bvec[j] > 0.0) : (j == b)) {                                     /* :124 (b[j] > 0) */
+            if (runif01(st) < pht_exp(Sjj * T) / Pab) { z[j] += T; N[j + j * n] = 1; if (pre) *pre = j; break; }   /* :125-130 */
         }
         for (int i = 0; i < n; i++) {                                                /* :137-144 */
             if (fabs((evals[i] - Sjj) / Sjj) < 1e-13) J[i] = T * pht_exp(evals[i] * T);
@@ -337,7 +339,7 @@ int pho_dcs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     for (long k = 0; k < count; k++) {
         pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
         const int b = hob_end_state(&st, y[k], n, pi, Q, evals, Qinv, s, wk, wk + n);
-        const int B = hob_path(&st, y[k], b, n, pi, S, Q, evals, Qinv + (size_t)b * n, z, N, wk + 2 * n, wk + 3 * n, counters);
+        const int B = hob_path(&st, y[k], b, NULL, n, pi, S, Q, evals, Qinv + (size_t)b * n, z, N, wk + 2 * n, wk + 3 * n, NULL, counters);
         if (counters) counters[PHO_C_PATHS]++;
         if (outB) {
             outB[k] = B;
@@ -608,7 +610,7 @@ static double gt_dens(double d, void *vp) {
 /* src/Simulate_AbsCTMC_gt_Aslett_DCS.c:299-418 (reverse = 0) with condjump_r_ars :184-260 */
 static int gt_path(pht_stream *st, double y, int censored, int n, const double *pi, const double *S, const double *Q,
                    const double *evals, const double *Qinv_1, const double *P, const double *Pfull,
-                   double *z, int *N, double *wk, unsigned long long *cnt) {
+                   double *z, int *N, double *wk, int *pre, unsigned long long *cnt) {
     double *pv = wk, *pq = wk + n, *ex = wk + 2 * n;
     for (int i = 0; i < n; i++) z[i] = 0.0;
     memset(N, 0, sizeof(int) * (size_t)n * n);
@@ -662,6 +664,7 @@ static int gt_path(pht_stream *st, double y, int censored, int n, const double *
     }
     if (!censored) z[lastj] += y - lastt; else z[lastj] += t - lastt;                /* :390-391 */
     N[lastj + lastj * n]++;                                                          /* :392 */
+    if (pre) *pre = lastj;                                                           /* :393 */
     return B;
 }
 
@@ -678,7 +681,7 @@ int pho_ecs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     for (long k = 0; k < count; k++) {
         pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
         int B;
-        if (cens[k]) B = gt_path(&st, y[k], 1, n, pi, S, Q, evals, Qinv_1, P, Pfull, z, N, wk, counters);
+        if (cens[k]) B = gt_path(&st, y[k], 1, n, pi, S, Q, evals, Qinv_1, P, Pfull, z, N, wk, NULL, counters);
         else B = ecs_exact_path(&st, y[k], n, pi, S, s, Q, evals, Qinv_s, P, z, N, wk, counters);
         if (counters) counters[PHO_C_PATHS]++;
         if (outB) {
@@ -690,6 +693,99 @@ int pho_ecs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
     free(pi); free(wk); free(z); free(N);
     return 0;
 }
+
+/* ------------------------------------------------------------------ f1: the two compiled-but-unreachable MH variants
+ * Both wrap a direct conditional sampler of "alive at y" paths in the independence Metropolis-Hastings step of
+ * MHRS (accept ratio s[p_pre] / s[c_pre]).  Every chain ends with LJMA_GUI() (gt_Hobolth_DCS.c:224,
+ * gt_Aslett_DCS.c:416), the sub-stream hook of the Philox contract: chain k of an observation is its sub-stream k,
+ * and the accept uniform that follows a proposal is draw 0 of the next sub-stream -- the same layout as MHRS. */
+#define CHAIN(call) ((tmpB = (call)), next_substream(&st), tmpB)
+
+/* The exit set the (non-existent) caller of LJMA_MHsample_Hobolth would pass: b_j = 1 where s_j > 0, and
+ * Qinv_b = Q^-1 b formed as the reference forms such products (dgemv 'N': y_i accumulated over j,
+ * eq_AslettHobolth_DCS.c:131). */
+void pho_exit_set(int n, const double *s, const double *Qinv, double *bvec, double *Qinv_b) {
+    for (int j = 0; j < n; j++) bvec[j] = (s[j] > 0.0) ? 1.0 : 0.0;
+    for (int i = 0; i < n; i++) Qinv_b[i] = 0.0;
+    for (int j = 0; j < n; j++) { const double t = 1.0 * bvec[j]; for (int i = 0; i < n; i++) Qinv_b[i] += t * Qinv[i + j * n]; }
+}
+
+/* src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:268-355 (LJMA_MHsample_Hobolth).  Reproduced as written: the retry loop
+ * of a PROPOSAL tests s[c_pre] (:312), which is non-zero by then, so an invalid proposal is never redrawn --
+ * it is rejected by the accept ratio 0 instead. */
+int pho_mhs_hobolth_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                          const double *y, const int *cens, int n, const double *S, const double *s,
+                          const double *evals, const double *Q, const double *Qinv, int mhit,
+                          int *outB, int *outN, double *outz, unsigned long long *counters) {
+    double *pi = (double *)calloc(n, sizeof(double)), *wk = (double *)calloc(4 * (size_t)n, sizeof(double));
+    double *za = (double *)calloc(n, sizeof(double)), *zb = (double *)calloc(n, sizeof(double));
+    int *Na = (int *)calloc((size_t)n * n, sizeof(int)), *Nb = (int *)calloc((size_t)n * n, sizeof(int));
+    if (!pi || !wk || !za || !zb || !Na || !Nb) return -1;
+    pi_init(pi, n);
+    double *bvec = wk, *Qb = wk + n;
+    pho_exit_set(n, s, Qinv, bvec, Qb);
+    for (long k = 0; k < count; k++) {
+        pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
+        double *zc = za, *zp = zb; int *Nc = Na, *Np = Nb;
+        int c_pre = 0, p_pre = 0, tmpB = 0;
+        int cB = CHAIN(hob_path(&st, y[k], 0, bvec, n, pi, S, Q, evals, Qb, zc, Nc, wk + 2 * n, wk + 3 * n, &c_pre, counters));       /* :297 */
+        while (s[c_pre] == 0.0) cB = CHAIN(hob_path(&st, y[k], 0, bvec, n, pi, S, Q, evals, Qb, zc, Nc, wk + 2 * n, wk + 3 * n, &c_pre, counters));   /* :299-301 */
+        if (!cens[k]) {                                                                                      /* :308 */
+            for (int it = 0; it < mhit; it++) {
+                const int pB = CHAIN(hob_path(&st, y[k], 0, bvec, n, pi, S, Q, evals, Qb, zp, Np, wk + 2 * n, wk + 3 * n, &p_pre, counters));   /* :311; :312 never loops */
+                const double U = runif01(&st);                                                               /* :317 */
+                if (U < s[p_pre] / s[c_pre]) {                                                               /* :320 */
+                    double *tz = zc; zc = zp; zp = tz; int *tN = Nc; Nc = Np; Np = tN;
+                    cB = pB; c_pre = p_pre;
+                }
+            }
+        }
+        if (counters) counters[PHO_C_PATHS]++;
+        outB[k] = cB;
+        memcpy(outN + (size_t)k * n * n, Nc, sizeof(int) * (size_t)n * n);
+        memcpy(outz + (size_t)k * n, zc, sizeof(double) * (size_t)n);
+    }
+    free(pi); free(wk); free(za); free(zb); free(Na); free(Nb);
+    return 0;
+}
+
+/* src/Simulate_AbsCTMC_eq_Aslett_DCS.c:49-143 (LJMA_MHsample_Aslett) with reverse = 0: the gt sampler of
+ * src/Simulate_AbsCTMC_gt_Aslett_DCS.c:299-418 called with the observation's own censoring flag. */
+int pho_mhs_aslett_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                         const double *y, const int *cens, int n, const double *S, const double *s,
+                         const double *P, const double *Pfull, const double *evals, const double *Q, const double *Qinv_1,
+                         int mhit, int *outB, int *outN, double *outz, unsigned long long *counters) {
+    double *pi = (double *)calloc(n, sizeof(double)), *wk = (double *)calloc(4 * (size_t)n, sizeof(double));
+    double *za = (double *)calloc(n, sizeof(double)), *zb = (double *)calloc(n, sizeof(double));
+    int *Na = (int *)calloc((size_t)n * n, sizeof(int)), *Nb = (int *)calloc((size_t)n * n, sizeof(int));
+    if (!pi || !wk || !za || !zb || !Na || !Nb) return -1;
+    pi_init(pi, n);
+    for (long k = 0; k < count; k++) {
+        pht_stream st = stream_for(seed, iter, (uint32_t)(obs0 + k * stride));
+        double *zc = za, *zp = zb; int *Nc = Na, *Np = Nb;
+        int c_pre = 0, p_pre = 0, tmpB = 0;
+        int cB = CHAIN(gt_path(&st, y[k], cens[k], n, pi, S, Q, evals, Qinv_1, P, Pfull, zc, Nc, wk, &c_pre, counters));            /* :93 */
+        while (s[c_pre] == 0.0) cB = CHAIN(gt_path(&st, y[k], cens[k], n, pi, S, Q, evals, Qinv_1, P, Pfull, zc, Nc, wk, &c_pre, counters));   /* :95-97 */
+        if (!cens[k]) {                                                                                      /* :100 */
+            for (int it = 0; it < mhit; it++) {
+                int pB = CHAIN(gt_path(&st, y[k], 0, n, pi, S, Q, evals, Qinv_1, P, Pfull, zp, Np, wk, &p_pre, counters));          /* :103 */
+                while (s[p_pre] == 0.0) pB = CHAIN(gt_path(&st, y[k], 0, n, pi, S, Q, evals, Qinv_1, P, Pfull, zp, Np, wk, &p_pre, counters));   /* :104-106 */
+                const double U = runif01(&st);                                                               /* :109 */
+                if (U < s[p_pre] / s[c_pre]) {                                                               /* :112 */
+                    double *tz = zc; zc = zp; zp = tz; int *tN = Nc; Nc = Np; Np = tN;
+                    cB = pB; c_pre = p_pre;
+                }
+            }
+        }
+        if (counters) counters[PHO_C_PATHS]++;
+        outB[k] = cB;
+        memcpy(outN + (size_t)k * n * n, Nc, sizeof(int) * (size_t)n * n);
+        memcpy(outz + (size_t)k * n, zc, sizeof(double) * (size_t)n);
+    }
+    free(pi); free(wk); free(za); free(zb); free(Na); free(Nb);
+    return 0;
+}
+#undef CHAIN
 
 /* ------------------------------------------------------------------ the engine's own spectral solver, on the host */
 #include "../phasetype_b200/csrc/pht_eigen.h"
@@ -735,6 +831,9 @@ static int method_pick(int method) {        /* dispatch priority of src/PHT_MCMC
     if (method & PHO_MHRS) return PHO_MHRS;
     if (method & PHO_DCS) return PHO_DCS;
     if (method & PHO_ECS) return PHO_ECS;
+    /* the engine's extension: the two variants the reference compiles but never dispatches (section 8(f)1) */
+    if (method & PHO_MHS_HOBOLTH) return PHO_MHS_HOBOLTH;
+    if (method & PHO_MHS_ASLETT) return PHO_MHS_ASLETT;
     return 0;
 }
 
@@ -770,6 +869,8 @@ int pho_sweep_stats(uint64_t seed, uint32_t iter, int first, int mhit, int metho
     if (rc == 0) {
         if (which == PHO_MHRS) rc = pho_mhrs_paths(seed, iter, rank, world, cnt, yl, cl, n, S, s, Pfull, mhit, B, N, z, counters);
         else if (which == PHO_DCS) rc = pho_dcs_paths(seed, iter, rank, world, cnt, yl, n, S, s, ev, Q, Qi, B, N, z, counters);
+        else if (which == PHO_MHS_HOBOLTH) rc = pho_mhs_hobolth_paths(seed, iter, rank, world, cnt, yl, cl, n, S, s, ev, Q, Qi, mhit, B, N, z, counters);
+        else if (which == PHO_MHS_ASLETT) rc = pho_mhs_aslett_paths(seed, iter, rank, world, cnt, yl, cl, n, S, s, P, Pfull, ev, Q, Q1, mhit, B, N, z, counters);
         else rc = pho_ecs_paths(seed, iter, rank, world, cnt, yl, cl, n, S, s, P, Pfull, ev, Q, Qs, Q1, B, N, z, counters);
     }
     if (rc == 0) {

@@ -23,7 +23,9 @@
 extern "C" {
 #endif
 
-enum { PHO_MHRS = 1, PHO_ECS = 2, PHO_DCS = 4 };
+enum { PHO_MHRS = 1, PHO_ECS = 2, PHO_DCS = 4,
+       PHO_MHS_HOBOLTH = 8,     /* LJMA_MHsample_Hobolth, src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:268-355 (no caller in the reference) */
+       PHO_MHS_ASLETT = 16 };   /* LJMA_MHsample_Aslett, src/Simulate_AbsCTMC_eq_Aslett_DCS.c:49-143 (no caller in the reference) */
 
 /* event counters (define the algorithmic work W of BASELINE.md section 4) */
 enum {
@@ -73,6 +75,17 @@ int pho_ecs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long cou
                   const double *P, const double *Pfull,
                   const double *evals, const double *Q, const double *Qinv_s, const double *Qinv_1,
                   int *outB, int *outN, double *outz, unsigned long long *counters);
+
+/* f1: the two MH variants the reference compiles but never calls; exit set b_j = [s_j > 0], Qinv_b = Q^-1 b */
+void pho_exit_set(int n, const double *s, const double *Qinv, double *bvec, double *Qinv_b);
+int pho_mhs_hobolth_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                          const double *y, const int *cens, int n, const double *S, const double *s,
+                          const double *evals, const double *Q, const double *Qinv, int mhit,
+                          int *outB, int *outN, double *outz, unsigned long long *counters);
+int pho_mhs_aslett_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                         const double *y, const int *cens, int n, const double *S, const double *s,
+                         const double *P, const double *Pfull, const double *evals, const double *Q, const double *Qinv_1,
+                         int mhit, int *outB, int *outN, double *outz, unsigned long long *counters);
 
 /* fixed-point scale used for the sojourn totals (same rule as the engine) */
 int pho_choose_zbits(double sum_y);

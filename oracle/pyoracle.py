@@ -105,6 +105,10 @@ def oracle():
         if hasattr(L, "pho_ecs_paths"):
             L.pho_ecs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
                                         _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _up]
+        L.pho_mhs_hobolth_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                            _dp, _dp, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _up]
+        L.pho_mhs_aslett_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                           _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _up]
         if hasattr(L, "pho_choose_zbits"):
             L.pho_choose_zbits.restype = C.c_int; L.pho_choose_zbits.argtypes = [C.c_double]
         if hasattr(L, "pho_gibbs"):
@@ -152,6 +156,12 @@ def _load_ref(path):
         L.phtref_dcs_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
                                        _dp, _dp, _dp, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, _up]
         L.phtref_eigen.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+        if hasattr(L, "phtref_mhs_hobolth_paths"):
+            L.phtref_mhs_hobolth_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                                   _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _up]
+            L.phtref_mhs_aslett_paths.argtypes = [C.c_uint64, C.c_uint32, C.c_long, C.c_long, C.c_long, _dp, _ip, C.c_int,
+                                                  _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, _up]
         if hasattr(L, "phtref_set_pi"):
             L.phtref_set_pi.argtypes = [C.c_void_p, C.c_int]; L.phtref_set_pi.restype = None
         L.phtref_gibbs.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp,
@@ -255,6 +265,41 @@ def spectral_paths(impl, method, seed, it, y, cens, S, s, obs0=0, stride=1, want
     counters = _counters(cnt) if impl == "oracle" else {"paths": count, "uniforms": int(cnt[0]), "jumps": int(cnt[4])}
     if B is None:
         return None, None, None, counters
+    return B, N.reshape(count, n * n), z.reshape(count, n), counters
+
+
+def mh_variant_paths(impl, method, seed, it, y, cens, S, s, mhit=1, obs0=0, stride=1, spectral=None):
+    """The two MH variants the reference compiles but never dispatches: method "MHS_HOBOLTH"
+    (LJMA_MHsample_Hobolth) or "MHS_ASLETT" (LJMA_MHsample_Aslett, reverse = 0), per-observation statistics from
+    `impl` in {"oracle", "ref"}."""
+    y = _f64(y); cens = _i32(cens); S = _f64(S); s = _f64(s)
+    n = s.shape[0]; count = y.shape[0]
+    ev, Q, Qi = spectral if spectral is not None else eigen("oracle", S, n)
+    ev = _f64(ev); Q = _f64(Q); Qi = _f64(Qi)
+    P, Pfull = embedded(S, s)
+    cnt = np.zeros(N_COUNTERS, dtype=np.uint64)
+    B, N, z = _out(count, n, True)
+    if method == "MHS_HOBOLTH":
+        if impl == "oracle":
+            rc = oracle().pho_mhs_hobolth_paths(seed, it, obs0, stride, count, y, cens, n, S, s, ev, Q, Qi, mhit, B, N, z, cnt)
+        else:
+            rc = ref().phtref_mhs_hobolth_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), ev.copy(), Q.copy(),
+                                                Qi.copy(), mhit, _ptr(B), _ptr(N), _ptr(z), cnt)
+    elif method == "MHS_ASLETT":
+        Qm = Qi.reshape(n, n, order="F")
+        Qinv_1 = np.zeros(n)
+        for j in range(n):
+            Qinv_1 += 1.0 * Qm[:, j]
+        if impl == "oracle":
+            rc = oracle().pho_mhs_aslett_paths(seed, it, obs0, stride, count, y, cens, n, S, s, P, Pfull, ev, Q, Qinv_1, mhit, B, N, z, cnt)
+        else:
+            rc = ref().phtref_mhs_aslett_paths(seed, it, obs0, stride, count, y, cens, n, S.copy(), s.copy(), P.copy(), Pfull.copy(),
+                                               ev.copy(), Q.copy(), Qinv_1, Qi.copy(), mhit, _ptr(B), _ptr(N), _ptr(z), cnt)
+    else:
+        raise ValueError(method)
+    if rc != 0:
+        raise RuntimeError("%s %s paths failed rc=%d" % (impl, method, rc))
+    counters = _counters(cnt) if impl == "oracle" else {"paths": count, "uniforms": int(cnt[0]), "jumps": int(cnt[4])}
     return B, N.reshape(count, n * n), z.reshape(count, n), counters
 
 

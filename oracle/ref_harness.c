@@ -22,6 +22,12 @@ void LJMA_MHsample_Aslett2(double *y, int *censored, int *m, double *pi, double 
 void LJMA_MHsample_Hobolth2(double *y, int *censored, int *m, double *pi, double *S, double *s, double *Q,
                             double *evals, double *Qinv_b, double *bvec, double *Qinv, int *n, int *iter,
                             double *res_z, int *res_B, int *res_N, double *workD, int *workI);
+void LJMA_MHsample_Hobolth(double *y, int *censored, int *m, double *pi, double *S, double *s, double *Q, double *evals,
+                           double *Qinv_b, double *b, double *Qinv, int *n, int *iter, double *res_z, int *res_B, int *res_N,
+                           double *workD, int *workI);
+void LJMA_MHsample_Aslett(double *y, int *censored, int *m, double *pi, double *S, double *s, double *P, double *Pfull,
+                          double *Q, double *evals, double *Qinv_1, double *Qinv, int *n, int *iter, int *reverse,
+                          double *res_z, int *res_B, int *res_N, double *workD, int *workI);
 int LJMA_eigen(int *n, double *S, double *evals, double *Q, double *Qinv, double *workD, int *workI);
 void LJMA_LAPACKspace(int *n);
 void LJMA_LAPACKspaceFree(void);
@@ -127,6 +133,51 @@ int phtref_dcs_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long 
     }
     counters_out(counters);
     free(Qinv_b); free(bvec);
+    scratch_free(&w);
+    return 0;
+}
+
+/* The two MH variants nothing in the reference calls (src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:268,
+ * src/Simulate_AbsCTMC_eq_Aslett_DCS.c:49): driven here one observation at a time like the live ones.  The exit set
+ * handed to the Hobolth variant is b_j = [s_j > 0] with Qinv_b = Q^-1 b in dgemv-'N' order (the caller's choice;
+ * the oracle and the engine make the same one). */
+int phtref_mhs_hobolth_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                             const double *y, const int *cens, int n, double *S, double *s,
+                             double *evals, double *Q, double *Qinv, int mhit,
+                             int *outB, int *outN, double *outz, unsigned long long *counters) {
+    scratch w; if (scratch_init(&w, n)) return -1;
+    double *Qinv_b = (double *)calloc(n, sizeof(double)), *bvec = (double *)calloc(n, sizeof(double));
+    for (int j = 0; j < n; j++) bvec[j] = (s[j] > 0.0) ? 1.0 : 0.0;
+    for (int j = 0; j < n; j++) { const double t = 1.0 * bvec[j]; for (int i = 0; i < n; i++) Qinv_b[i] += t * Qinv[i + j * n]; }
+    phtshim_seed(seed); LJMA_counter = 0;
+    int one = 1;
+    for (long k = 0; k < count; k++) {
+        double yk = y[k]; int ck = cens[k];
+        phtshim_key(iter, (uint32_t)(obs0 + k * stride));
+        LJMA_MHsample_Hobolth(&yk, &ck, &one, w.pi, S, s, Q, evals, Qinv_b, bvec, Qinv, &n, &mhit, w.z, w.B, w.N, w.workD, w.workI);
+        if (outB) emit(&w, n, k, outB, outN, outz);
+    }
+    counters_out(counters);
+    free(Qinv_b); free(bvec);
+    scratch_free(&w);
+    return 0;
+}
+
+int phtref_mhs_aslett_paths(uint64_t seed, uint32_t iter, long obs0, long stride, long count,
+                            const double *y, const int *cens, int n, double *S, double *s, double *P, double *Pfull,
+                            double *evals, double *Q, double *Qinv_1, double *Qinv, int mhit,
+                            int *outB, int *outN, double *outz, unsigned long long *counters) {
+    scratch w; if (scratch_init(&w, n)) return -1;
+    phtshim_seed(seed); LJMA_counter = 0;
+    int one = 1, reverse = 0;
+    for (long k = 0; k < count; k++) {
+        double yk = y[k]; int ck = cens[k];
+        phtshim_key(iter, (uint32_t)(obs0 + k * stride));
+        LJMA_MHsample_Aslett(&yk, &ck, &one, w.pi, S, s, P, Pfull, Q, evals, Qinv_1, Qinv, &n, &mhit, &reverse,
+                             w.z, w.B, w.N, w.workD, w.workI);
+        if (outB) emit(&w, n, k, outB, outN, outz);
+    }
+    counters_out(counters);
     scratch_free(&w);
     return 0;
 }

@@ -136,6 +136,8 @@ static int method_of(const pht_config &c) {       /* dispatch priority of src/PH
     if (c.method & PHT_METHOD_MHRS) return PHT_METHOD_MHRS;
     if (c.method & PHT_METHOD_DCS) return PHT_METHOD_DCS;
     if (c.method & PHT_METHOD_ECS) return PHT_METHOD_ECS;
+    if (c.method & PHT_METHOD_MHS_HOBOLTH) return PHT_METHOD_MHS_HOBOLTH;      /* the engine's extension (pht_b200.h) */
+    if (c.method & PHT_METHOD_MHS_ASLETT) return PHT_METHOD_MHS_ASLETT;
     return 0;
 }
 
@@ -150,6 +152,12 @@ static int enqueue_paths(pht_engine *e, const SweepParams &p, const uint32_t *id
         break;
     case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->tail_blocks, e->stream)); e->launches++; break;
     case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); break;
+    case PHT_METHOD_MHS_HOBOLTH: CU(pht_launch_dcs(p, e->grid_blocks, e->stream, true)); break;
+    case PHT_METHOD_MHS_ASLETT:
+        /* every observation through one kernel: the window list in parity mode, else the whole shard (identity) */
+        if (lists_given) CU(pht_launch_mhs_aslett(p, e->grid_blocks, idx_exact, n_exact, e->stream));
+        else CU(pht_launch_mhs_aslett(p, e->grid_blocks, nullptr, (unsigned long long)e->l_local, e->stream));
+        break;
     default: return fail("sampling method %d has no kernel in this build", e->cfg.method);
     }
     e->launches++;
@@ -317,6 +325,10 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         if (!ic.empty()) CUE(cudaMemcpy(e->d_idx_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
         e->grid_blocks = pht_ecs_grid_blocks(cfg->device, n);
         if (e->grid_blocks <= 0) { fail("ECS kernels do not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
+    }
+    if (method_of(e->cfg) == PHT_METHOD_MHS_HOBOLTH || method_of(e->cfg) == PHT_METHOD_MHS_ASLETT) {
+        e->grid_blocks = method_of(e->cfg) == PHT_METHOD_MHS_HOBOLTH ? pht_dcs_grid_blocks(cfg->device, n, true) : pht_mhs_aslett_grid_blocks(cfg->device, n);
+        if (e->grid_blocks <= 0) { fail("the MH sampler variant does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
     if (method_of(e->cfg) == PHT_METHOD_DCS) {
         e->grid_blocks = pht_dcs_grid_blocks(cfg->device, n);
@@ -609,6 +621,12 @@ extern "C" int pht_engine_paths(pht_engine *e, long first, long count, int *B, i
             if (!ie.empty()) CUP(cudaMemcpy(t_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice));
             if (!ic.empty()) CUP(cudaMemcpy(t_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
             if (enqueue_paths(e, p, t_exact, ie.size(), t_cens, ic.size(), true)) goto out;
+        } else if (method_of(e->cfg) == PHT_METHOD_MHS_ASLETT) {
+            std::vector<uint32_t> all((size_t)count);
+            for (long i = 0; i < count; i++) all[(size_t)i] = (uint32_t)(first + i);
+            CUP(cudaMalloc(&t_exact, sizeof(uint32_t) * all.size()));
+            CUP(cudaMemcpy(t_exact, all.data(), sizeof(uint32_t) * all.size(), cudaMemcpyHostToDevice));
+            if (enqueue_paths(e, p, t_exact, all.size(), nullptr, 0, true)) goto out;
         } else if (enqueue_paths(e, p)) goto out;
         if (pht_engine_sync(e)) goto out;
         CUP(cudaMemcpy(B, dB, sizeof(int) * count, cudaMemcpyDeviceToHost));

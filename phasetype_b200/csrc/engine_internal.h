@@ -159,12 +159,16 @@ cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_pack_error(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, cudaStream_t st);
-cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st);
-int pht_dcs_grid_blocks(int device, int n);
+/* mh: the LJMA_MHsample_Hobolth variant (method bit 8) instead of the live DCS sampler */
+cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st, bool mh = false);
+int pht_dcs_grid_blocks(int device, int n, bool mh = false);
 /* ECS: exact and right-censored observations are separate launches over index lists (nullptr = identity) */
 cudaError_t pht_launch_ecs(const SweepParams &p, int grid_blocks, const uint32_t *idx_exact, unsigned long long n_exact,
                            const uint32_t *idx_cens, unsigned long long n_cens, cudaStream_t st);
 int pht_ecs_grid_blocks(int device, int n);
+/* the LJMA_MHsample_Aslett variant (method bit 16): every observation of the list through the gt sampler + MH wrapper */
+cudaError_t pht_launch_mhs_aslett(const SweepParams &p, int grid_blocks, const uint32_t *idx, unsigned long long count, cudaStream_t st);
+int pht_mhs_aslett_grid_blocks(int device, int n);
 /* spectral data of the sweep: inject != nullptr copies host-supplied (evals | Q | Qinv) instead of solving on the device */
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st);
 int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks);

@@ -51,18 +51,22 @@ struct DcsSmem {
          * dimension is padded to an odd number of doubles so that those reads spread over the banks (with ld = n = 8
          * they were 4-way conflicts: 3.8e9 per sweep, profiles/r1_final_dcs_1e7_ncu_full.md) */
         const int ld = n | 1;
-        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * ld; D = d; d += n * ld;
+        /* (Qinv has one more column, n: Q^-1 b of the MH variant's exit set, so that "column b" reads work for both) */
+        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += (n + 1) * ld; D = d; d += n * ld;
         evals = d; d += n; s = d; d += n; pi = d; d += n; PIQ = d; d += n;
         X = d; d += n * THREADS; E = d; d += n * THREADS; P = d; d += n * THREADS; Z = d; d += n * THREADS;
         zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
         Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n; deg = Bacc + n;
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(2 * n * n + 2 * n * (n | 1) + 4 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
+        return sizeof(double) * (size_t)(2 * n * n + (2 * n + 1) * (n | 1) + 4 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
     }
 };
 
-template <int THREADS>
+/* MH = false: the live DCS sampler.  MH = true: LJMA_MHsample_Hobolth (gt_Hobolth_DCS.c:268-355, method bit 8; nothing
+ * in the reference calls it): no end-state draw, the chain is conditioned on being in the exit set {j : s_j > 0} at y
+ * (w = Q^-1 b, kept as column n of the Qinv table), and the chains go through the MH wrapper of path_common.cuh. */
+template <int THREADS, bool MH>
 __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dcs_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x, ld = n | 1;
@@ -81,6 +85,16 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
         sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
     }
     __syncthreads();
+    uint32_t bmask = 0u;                /* MH: the exit set */
+    if (MH) {
+        for (int i = 0; i < n; i++) bmask |= (sm.s[i] > 0.0) ? (1u << i) : 0u;
+        /* Q^-1 b in dgemv-'N' order: y_i accumulated over the columns j (eq_AslettHobolth_DCS.c:131) */
+        for (int i = tid; i < n; i += THREADS) {
+            double acc = 0.0;
+            for (int jj = 0; jj < n; jj++) acc += (1.0 * (((bmask >> jj) & 1u) ? 1.0 : 0.0)) * sm.Qinv[i + jj * ld];
+            sm.Qinv[i + n * ld] = acc;
+        }
+    }
     /* observation-independent tables: D[j][i] = ev_i - S_jj, the degenerate flags, and pi^T Q in reference-BLAS order */
     for (int e = tid; e < n * n; e += THREADS) {
         const int j = e / n, i = e % n;
@@ -100,6 +114,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     unsigned c_jumps = 0, c_evals = 0, c_paths = 0, c_fail = 0;
     Dispenser disp; disp.init(p);
     PathRng rng; rng.seek(0);
+    MhChain mh; mh.begin(false);
     int kind = K_IDLE;
     double y = 0.0, t = 0.0, T = 0.0, alpha = 0.0, beta = 0.0, u = 0.0, coef = 0.0;
     double ba = 0.0, bb = 0.0, bc = 0.0, fa = 0.0, fb = 0.0, fc = 0.0;
@@ -118,6 +133,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             if (o != ~0ull) {
                 kind = K_NEW; y = p.y[o]; out_idx = (long)o - p.first; t = 0.0;
                 rng.seek(p.obs_rank + (uint32_t)o * p.obs_world);
+                if (MH) mh.begin(p.cens[o] != 0);
                 alpha = y; beta = 0.0;
             }
             idle = __ballot_sync(FULL, kind == K_IDLE);
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
          * candidate state i (JUMP), or component i of the end-state weights (NEW); sums that the reference accumulates
          * in index order are accumulated in index order over the group's lanes */
         double sv_Pab = 0.0, sv_eS = 0.0, sv_psum = 0.0;
-        unsigned need = __ballot_sync(FULL, kind0 == K_JUMP || kind0 == K_NEW);
+        unsigned need = __ballot_sync(FULL, kind0 == K_JUMP || (!MH && kind0 == K_NEW));
         while (need) {
             int r = -1; unsigned served = 0u;
             {
@@ -222,10 +238,10 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             /* ---- the requesting lane's own part of the jump: stay test, next state, root-finder set-up (:124-190) */
             const double Pab = sv_Pab, eS = sv_eS, p_sum = sv_psum;
             bool stay = false;
-            if (j == b) stay = rng.next(p, iter) < eS / Pab;                                   /* :124-132 */
+            if (MH ? (((bmask >> j) & 1u) != 0u) : (j == b)) stay = rng.next(p, iter) < eS / Pab;   /* :124-132 */
             if (stay) {
                 sm.Z[j * THREADS + tid] += T;
-                count_transition(p, n, sm.Nacc, out_idx, j, j);
+                if (!MH || mh.rec) count_transition(p, n, sm.Nacc, out_idx, j, j);
                 flush = true;
             } else {
                 const double target = (p_sum == 0.0) ? 0.0 : 0.0 + (p_sum - 0.0) * rng.next(p, iter);   /* runif(0, p_sum), :164 */
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
         } else if (kind0 == K_NEW) {
             /* ---- new path: end state b from the weights the warp just formed (eq_AslettHobolth_DCS.c:41-50), then the
              * start state (gt_Hobolth_DCS.c:88-95) */
-            b = slab_scan<THREADS>(sm.P, n, rng.next(p, iter));
+            if (MH) b = n; else b = slab_scan<THREADS>(sm.P, n, rng.next(p, iter));
             {
                 const double target = rng.next(p, iter);
                 double sofar = 0.0; int q = 0;
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 int guard = 0;
 #pragma unroll 1
                 while (t + jtime >= y && guard++ < 2000) jtime = jtime / 2;                     /* :204-206 */
-                count_transition(p, n, sm.Nacc, out_idx, j, k);                                 /* :209 */
+                if (!MH || mh.rec) count_transition(p, n, sm.Nacc, out_idx, j, k);              /* :209 */
                 sm.Z[j * THREADS + tid] += jtime;                                               /* :210 */
                 t += jtime; j = k;
                 c_jumps++;
@@ -304,8 +320,14 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             else { T = y - t; alpha = T; beta = 0.0; kind = K_JUMP; }
         }
         if (flush) {
-            path_flush<THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
-            c_paths++; kind = K_IDLE;
+            /* MH: the chain that just ended stayed in j to the end (res_pre, :128); the wrapper says what runs next */
+            if (!MH || mh.chain_end<false>(j, sm.s, p.mhit, p, iter, rng.obs)) {
+                path_flush<THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
+                c_paths++; kind = K_IDLE;
+            } else {
+                rng.seek_sub(mh.chain, mh.off, p, iter);
+                kind = K_NEW; t = 0.0; alpha = y; beta = 0.0;
+            }
         }
     }
 
@@ -324,24 +346,29 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
 
 static int dcs_threads(int n) { return n <= 16 ? 128 : 64; }
 
-int pht_dcs_grid_blocks(int device, int n) {
+template <int THREADS, bool MH>
+static cudaError_t dcs_occupancy(int n, int *per_sm) {
+    const size_t smem = DcsSmem<THREADS>::bytes(n);
+    cudaError_t e = cudaFuncSetAttribute(k_dcs_sweep<THREADS, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_dcs_sweep<THREADS, MH>, THREADS, smem);
+    return e;
+}
+int pht_dcs_grid_blocks(int device, int n, bool mh) {
     int per_sm = 0, sms = 0; cudaError_t e;
-    if (dcs_threads(n) == 128) {
-        const size_t smem = DcsSmem<128>::bytes(n);
-        e = cudaFuncSetAttribute(k_dcs_sweep<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dcs_sweep<128>, 128, smem);
-    } else {
-        const size_t smem = DcsSmem<64>::bytes(n);
-        e = cudaFuncSetAttribute(k_dcs_sweep<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dcs_sweep<64>, 64, smem);
-    }
+    if (dcs_threads(n) == 128) e = mh ? dcs_occupancy<128, true>(n, &per_sm) : dcs_occupancy<128, false>(n, &per_sm);
+    else e = mh ? dcs_occupancy<64, true>(n, &per_sm) : dcs_occupancy<64, false>(n, &per_sm);
     if (e != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
     return per_sm * sms;
 }
 
-cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st) {
-    if (dcs_threads(p.n) == 128) k_dcs_sweep<128><<<grid_blocks, 128, DcsSmem<128>::bytes(p.n), st>>>(p);
-    else k_dcs_sweep<64><<<grid_blocks, 64, DcsSmem<64>::bytes(p.n), st>>>(p);
+cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st, bool mh) {
+    if (dcs_threads(p.n) == 128) {
+        if (mh) k_dcs_sweep<128, true><<<grid_blocks, 128, DcsSmem<128>::bytes(p.n), st>>>(p);
+        else k_dcs_sweep<128, false><<<grid_blocks, 128, DcsSmem<128>::bytes(p.n), st>>>(p);
+    } else {
+        if (mh) k_dcs_sweep<64, true><<<grid_blocks, 64, DcsSmem<64>::bytes(p.n), st>>>(p);
+        else k_dcs_sweep<64, false><<<grid_blocks, 64, DcsSmem<64>::bytes(p.n), st>>>(p);
+    }
     return cudaGetLastError();
 }

@@ -517,8 +517,12 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
     if (*sm.cplx) ecs_exact_body<true>(p, list, sm, n); else ecs_exact_body<false>(p, list, sm, n);
 }
 
-/* ------------------------------------------------------------------ censored observations */
-template <bool CPLX>
+/* ------------------------------------------------------------------ censored observations
+ * MH = false: the live use (censored observations of ECS, censored = 1 throughout).  MH = true: LJMA_MHsample_Aslett
+ * (eq_Aslett_DCS.c:49-143 with reverse = 0, method bit 16; nothing in the reference calls it): every observation goes
+ * through this sampler with its own censoring flag -- an uncensored path stops at the first jump time beyond y
+ * (gt_Aslett_DCS.c:339,381,390) -- and the chains go through the MH wrapper of path_common.cuh. */
+template <bool CPLX, bool MH>
 __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList &list, EcsSmem &sm, int n) {
     const int tid = threadIdx.x;
     const unsigned FULL = 0xffffffffu;
@@ -527,6 +531,7 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
     EcsCounters c = {0, 0, 0, 0, 0, 0, 0};
     ListDispenser disp; disp.init(list.count, &p.state->unit_counter);
     PathRng rng; rng.seek(0);
+    MhChain mh; mh.begin(true);
     bool active = false;
     double y = 0.0, t = 0.0; int j = 0, B = 0; long out_idx = 0;
 
@@ -538,6 +543,7 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
                 const uint32_t o = list.idx ? list.idx[k] : (uint32_t)k;
                 active = true; y = p.y[o]; out_idx = (long)o - p.first; t = 0.0;
                 rng.seek(p.obs_rank + o * p.obs_world);
+                if (MH) mh.begin(p.cens[o] != 0);
                 B = start_state(sm, n, rng.next(p, iter));                              /* gt_Aslett_DCS.c:313-320 */
                 j = B;
 #pragma unroll 1
@@ -548,7 +554,7 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
         if (idle == FULL) { if (disp.exhausted) break; else continue; }
         __syncwarp();                       /* refilled and continuing lanes take the step together (see k_ecs_exact) */
         if (active) {
-        /* ---- one step (gt_Aslett_DCS.c:339-384 with censored = 1) */
+        /* ---- one step (gt_Aslett_DCS.c:339-384; censored = 1 unless MH) */
         const double lastt = t; const int lastj = j;
         const double Sjj = sm.S[j + j * n];
         double d;
@@ -622,14 +628,24 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
             while (sofar < target && k <= n) { sofar += sm.Pfull[lastj + k * n]; k++; }
             k--; if (k < 0) k = 0;
         }
-        if (k == n) {                                                                   /* :379, :390-392 */
-            sm.Z[lastj * ECS_THREADS + tid] += t - lastt;
-            count_transition(p, n, sm.Nacc, out_idx, lastj, lastj);
-            path_flush<ECS_THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
-            c.paths++; active = false;
+        const bool uncens = MH && !mh.cens;
+        if (k == n || (uncens && !(t < y))) {                                           /* :379 / loop test :339, then :390-393 */
+            sm.Z[lastj * ECS_THREADS + tid] += (uncens ? y : t) - lastt;
+            if (!MH || mh.rec) count_transition(p, n, sm.Nacc, out_idx, lastj, lastj);
+            if (!MH || mh.chain_end<true>(lastj, sm.s, p.mhit, p, iter, rng.obs)) {
+                path_flush<ECS_THREADS>(p, n, sm.Z, sm.zlo, sm.zhi, sm.Bacc, B, out_idx);
+                c.paths++; active = false;
+            } else {
+                /* the next chain of this observation: its own sub-stream, a fresh start state, an empty z */
+                rng.seek_sub(mh.chain, mh.off, p, iter);
+                B = start_state(sm, n, rng.next(p, iter));
+                j = B; t = 0.0;
+#pragma unroll 1
+                for (int i = 0; i < n; i++) sm.Z[i * ECS_THREADS + tid] = 0.0;
+            }
         } else {
             sm.Z[lastj * ECS_THREADS + tid] += t - lastt;                               /* :382 */
-            count_transition(p, n, sm.Nacc, out_idx, lastj, k);                         /* :383 */
+            if (!MH || mh.rec) count_transition(p, n, sm.Nacc, out_idx, lastj, k);      /* :383 */
             j = k;
         }
         }
@@ -641,7 +657,14 @@ __global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREA
     const int n = p.n;
     EcsSmem sm; sm.carve(smem_raw, n);
     ecs_load_model(p, sm, n);
-    if (*sm.cplx) ecs_gt_body<true>(p, list, sm, n); else ecs_gt_body<false>(p, list, sm, n);
+    if (*sm.cplx) ecs_gt_body<true, false>(p, list, sm, n); else ecs_gt_body<false, false>(p, list, sm, n);
+}
+__global__ void __launch_bounds__(ECS_THREADS, ECS_WARPS_PER_SM * 32 / ECS_THREADS) k_mhs_aslett(SweepParams p, ObsList list) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n;
+    EcsSmem sm; sm.carve(smem_raw, n);
+    ecs_load_model(p, sm, n);
+    if (*sm.cplx) ecs_gt_body<true, true>(p, list, sm, n); else ecs_gt_body<false, true>(p, list, sm, n);
 }
 
 int pht_ecs_grid_blocks(int device, int n) {
@@ -653,6 +676,20 @@ int pht_ecs_grid_blocks(int device, int n) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_ecs_gt, ECS_THREADS, smem) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
     return (a < b ? a : b) * sms;
+}
+
+int pht_mhs_aslett_grid_blocks(int device, int n) {
+    int a = 0, sms = 0;
+    const size_t smem = EcsSmem::bytes(n);
+    if (cudaFuncSetAttribute(k_mhs_aslett, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_mhs_aslett, ECS_THREADS, smem) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    return a * sms;
+}
+cudaError_t pht_launch_mhs_aslett(const SweepParams &p, int grid_blocks, const uint32_t *idx, unsigned long long count, cudaStream_t st) {
+    ObsList l; l.idx = idx; l.count = count;
+    if (count) k_mhs_aslett<<<grid_blocks, ECS_THREADS, EcsSmem::bytes(p.n), st>>>(p, l);
+    return cudaGetLastError();
 }
 
 cudaError_t pht_launch_ecs(const SweepParams &p, int grid_blocks, const uint32_t *idx_exact, unsigned long long n_exact,

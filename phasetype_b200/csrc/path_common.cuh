@@ -49,15 +49,64 @@ static __device__ __noinline__ pht_u32x4 pht_philox_call(uint32_t c0, uint32_t c
     return pht_philox4x32_10(c0, c1, c2, c3, k0, k1);
 }
 
-/* sequential uniforms of one path: sub-stream 0 of (iter, observation) */
+/* sequential uniforms of one path: sub-stream `sub` of (iter, observation); the live ECS / DCS samplers draw a whole
+ * path from sub-stream 0, the MH variants (MhChain below) give every chain of an observation its own sub-stream */
 struct PathRng {
-    uint32_t obs, b; double spare; bool odd;
-    __device__ __forceinline__ void seek(uint32_t obs_global) { obs = obs_global; b = 0; odd = false; spare = 0.0; }
+    uint32_t obs, b, sub; double spare; bool odd;
+    __device__ __forceinline__ void seek(uint32_t obs_global) { obs = obs_global; b = 0; sub = 0u; odd = false; spare = 0.0; }
     __device__ __forceinline__ double next(const SweepParams &p, uint32_t iter) {
         if (odd) { odd = false; return spare; }
-        pht_u32x4 r = pht_philox_call(b++, 0u, obs, iter, p.k0, p.k1);
+        pht_u32x4 r = pht_philox_call(b++, sub, obs, iter, p.k0, p.k1);
         spare = pht_u01(r.v[2], r.v[3]); odd = true;
         return pht_u01(r.v[0], r.v[1]);
+    }
+    /* position on draw 0 (skip_first: draw 1) of sub-stream s of the same observation */
+    __device__ __forceinline__ void seek_sub(uint32_t s, bool skip_first, const SweepParams &p, uint32_t iter) {
+        sub = s; b = 0; odd = false; spare = 0.0;
+        if (skip_first) (void)next(p, iter);
+    }
+};
+
+/* The independence Metropolis-Hastings wrapper of the two sampler variants the reference compiles but never
+ * dispatches (src/Simulate_AbsCTMC_gt_Hobolth_DCS.c:268-355, src/Simulate_AbsCTMC_eq_Aslett_DCS.c:49-143), as a
+ * per-lane state machine around a chain sampler.  Every chain ends with LJMA_GUI(), the sub-stream hook of the Philox
+ * contract, so chain k of an observation IS its sub-stream k and the accept uniform that follows a proposal is draw 0
+ * of the next sub-stream (the MHRS layout).  A chain is therefore a pure function of (observation, k, starts at draw
+ * 0 or 1), and the wrapper works like the MHRS search / replay split instead of the reference's double buffers: the
+ * chains are first run with recording OFF, only (k, offset, last state) of the current one is kept through the accept
+ * tests, and the chain that wins is run once more with recording ON. */
+struct MhChain {
+    uint32_t chain, c_chain, kprop; int c_pre;
+    bool off, c_off, have_cur, rec, cens;
+    __device__ __forceinline__ void begin(bool censored) {
+        chain = 0u; c_chain = 0u; kprop = 0u; c_pre = 0; off = false; c_off = false; have_cur = false; rec = false; cens = censored;
+    }
+    /* the chain just simulated ended in state `pre`.  Returns true when it was the recorded replay (the caller adds
+     * the path to the statistics and takes the next observation); otherwise (chain, off, rec) describe the chain to
+     * run next.  RETRY_PROPOSALS: an invalid proposal (s[pre] == 0) is redrawn (eq_Aslett_DCS.c:104-106); the Hobolth
+     * variant tests the CURRENT chain there (gt_Hobolth_DCS.c:312), so it never redraws a proposal. */
+    template <bool RETRY_PROPOSALS>
+    __device__ __forceinline__ bool chain_end(int pre, const double *s, int mhit, const SweepParams &p, uint32_t iter, uint32_t obs) {
+        if (rec) return true;
+        bool replay = false;
+        if (!have_cur) {
+            if (s[pre] == 0.0) { chain++; off = false; }                    /* redraw the current chain */
+            else {
+                have_cur = true; c_chain = chain; c_off = off; c_pre = pre;
+                if (cens || mhit == 0) replay = true;                        /* no MH step for a censored observation */
+                else { chain++; off = false; }                              /* first proposal */
+            }
+        } else if (RETRY_PROPOSALS && s[pre] == 0.0) { chain++; off = false; }
+        else {
+            const pht_u32x4 r = pht_philox_call(0u, chain + 1u, obs, iter, p.k0, p.k1);
+            const double U = pht_u01(r.v[0], r.v[1]);
+            if (U < s[pre] / s[c_pre]) { c_chain = chain; c_off = off; c_pre = pre; }
+            kprop++;
+            if ((int)kprop >= mhit) replay = true;
+            else { chain++; off = true; }                                    /* the next proposal starts behind the accept uniform */
+        }
+        if (replay) { rec = true; chain = c_chain; off = c_off; }
+        return false;
     }
 };
 

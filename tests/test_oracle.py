@@ -67,6 +67,42 @@ def test_oracle_equals_reference_bit_for_bit(method, n, kind, fc):
 
 
 @needs_ref
+@pytest.mark.parametrize("variant", ["MHS_HOBOLTH", "MHS_ASLETT"])
+@pytest.mark.parametrize("n,zero_exits,mhit", [(3, False, 1), (5, True, 3), (8, False, 0), (16, False, 2)])
+def test_dead_variants_equal_reference_bit_for_bit(variant, n, zero_exits, mhit):
+    """LJMA_MHsample_Hobolth / LJMA_MHsample_Aslett have no caller in the reference, but they are external
+    symbols of its build; the restatement is pinned against them, chain = sub-stream (every chain ends with LJMA_GUI())."""
+    rng = np.random.default_rng(31 * n + mhit)
+    R, s = util.dense_rates(n, rng, symmetric=True)
+    if zero_exits:
+        s[1] = 0.0; s[3] = 0.0            # states that cannot exit: the retry loops run
+    S = _S(R, s)
+    l = 400 if n <= 8 else 120
+    y = util.simulate_pht(R, s, l, rng); cens = (rng.uniform(size=l) < 0.25).astype(np.int32)
+    spec = po.eigen("ref", S, n)
+    a = po.mh_variant_paths("oracle", variant, 5, 2, y, cens, S, s, mhit=mhit, spectral=spec)
+    b = po.mh_variant_paths("ref", variant, 5, 2, y, cens, S, s, mhit=mhit, spectral=spec)
+    for u, v in zip(a[:3], b[:3]):
+        assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("variant", ["MHS_HOBOLTH", "MHS_ASLETT"])
+def test_dead_variants_reach_the_conditional_law(variant):
+    """Tier 2 for the MH variants: with enough MH proposals the chain statistics match the analytic conditional
+    expectations given absorption AT y (Hobolth-Jensen), although the chain samplers only condition on `alive at y`."""
+    Sm = np.array([[-4.1, 1.8, 1.8], [9.5, -11.3, 0.0], [9.5, 0.0, -15.5]]); s = -Sm.sum(1)
+    y0, l = 1.5, 20000
+    y = np.full(l, y0); cens = np.zeros(l, dtype=np.int32)
+    B, N, z, _ = po.mh_variant_paths("oracle", variant, 42, 1, y, cens, Sm.ravel(order="F").copy(), s, mhit=25)
+    Ez, EN, exit_p = hobolth_jensen(Sm, s, y0, False)
+    Nm = N.mean(0).reshape(3, 3, order="F")
+    assert np.abs(z.mean(0) - Ez).max() < 5 * z.std(0).max() / np.sqrt(l) + 2e-3
+    off = ~np.eye(3, dtype=bool)
+    assert np.abs(Nm[off] - EN[off]).max() < 0.04
+    assert np.abs(np.diag(Nm) - exit_p).max() < 0.015
+
+
+@needs_ref
 def test_lapack_binding_matches_reference_eigen():
     rng = np.random.default_rng(0)
     R, s = util.dense_rates(8, rng, symmetric=True)
