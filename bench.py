@@ -275,7 +275,7 @@ class Runner:
         tot2, kern_ms = eng2.last_ms()
         if os.environ.get("PHT_BENCH_VERBOSE"):
             cc = eng2.counters()
-            sys.stderr.write("rank %d: path kernels %.3f ms/sweep (lanes %.2f, local tail %.2f, global tail %.2f, tail replay %.2f ms), %d observations handed to the tail, %.1f tail rounds per sweep\n"
+            sys.stderr.write("rank %d: path kernels %.3f ms/sweep (lanes %.2f, local tail %.2f, global tail %.2f, replay kernel %.2f ms), %d observations handed to the tail, %.1f tail rounds per sweep\n"
                              % (self.rank, kern_ms, cc["ns_lane"] * 1e-6 / (warmup + k), cc["ns_tail"] * 1e-6 / (warmup + k), cc["ns_global"] * 1e-6 / (warmup + k),
                                 cc["ns_replay"] * 1e-6 / (warmup + k), cc["deferred"] // (warmup + k), cc["tail_rounds"] / float(warmup + k)))
         kern_ms = self.reduce(kern_ms)
@@ -293,7 +293,7 @@ class Runner:
         W = work_per_path(method, wl.n, ev)
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
-        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
+        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail + k_mhrs_replay", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
         cap = ncu_capture(method, l_local)
         issue = None
         mhz = (res.get("clocks") or {}).get("sm_mhz") or getattr(self, "sm_mhz", None)
@@ -412,6 +412,30 @@ def main():
                             "ms_per_step": rw["total_ms"] / args.steps, "kernel_ms": rw["kern_ms"]}
         del wlw
 
+    # ---- the two BASELINE shapes that are 8-GPU jobs as stated (config 4: 10^7 observations, ECS; config 5: 10^8
+    # observations, 32 phases): sharded over the ranks like the headline.  Every rank simulates its own shard (an
+    # independent stream of the same model); for C5 it simulates 2.5 x 10^6 observations and tiles them to its share --
+    # the paths still differ, they are keyed by the global observation index -- because simulating 10^8 32-phase
+    # absorption times on the host would take longer than the whole bench.
+    if world >= 8 and args.config == 3 and not args.no_others:
+        oc = {}
+        for cid, m2, l2, sim in ((4, "ECS", 10 ** 7, None), (5, "MHRS", 10 ** 8, 2500000)):
+            per = l2 // world
+            wc = synth.config(cid, m2, l=min(per, sim or per), shard=rank)
+            reps = -(-per // wc.l)
+            yc = np.ascontiguousarray(np.tile(wc.y, reps)[:per]); cc = np.ascontiguousarray(np.tile(wc.censored, reps)[:per])
+            sum_c = R.reduce(float(yc.sum()), "max") * world * 1.0000001
+            r2 = R.timed(wc, m2, yc, cc, sum_c, 3, 3)
+            if rank == 0:
+                rf = R.roofline(wc, m2, r2, per, pb.fp64_fma_rate(local_rank))
+                oc["C%d:%s" % (cid, m2)] = {"value": per * world * 3 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 3,
+                                            "workload": wc.name, "phases": wc.n, "parameters": wc.m, "observations": per * world,
+                                            "observations_per_gpu": per, "simulated_per_gpu": wc.l, "steps": 3, "warmup": 3,
+                                            "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_ms", "work_per_path")}}
+            del wc, yc, cc
+        if rank == 0:
+            line["other_configs"] = oc
+
     # ---- end to end through the drop-in routine with host buffers (upload, communicator set-up, sweeps, download)
     e2e = None
     if not args.no_e2e:
@@ -440,13 +464,14 @@ def main():
         line["e2e"] = e2e
         # ---- the other two samplers on the same shape (N = 1 only; fewer sweeps)
         if world == 1 and not args.no_others:
+            # ECS runs on the headline workload itself (general dense S: complex eigenvalue pairs go through the real
+            # block form of the spectral formulas); DCS -- whose formulas, the reference's, need a real spectrum and
+            # which reports a complex one instead of sampling from it -- on the symmetrised variant of the same shape
             others = {}
-            wl_sym = None
             for m2 in ("ECS", "DCS"):
                 if m2 == method:
                     continue
-                if wl_sym is None:
-                    wl_sym = synth.config(args.config, m2, l=full_l)
+                wl_sym = synth.config(args.config, "MHRS" if m2 == "ECS" else m2, l=full_l)
                 r2 = R.timed(wl_sym, m2, np.ascontiguousarray(wl_sym.y), np.ascontiguousarray(wl_sym.censored), float(wl_sym.y.sum()), 5, 3)
                 rf = R.roofline(wl_sym, m2, r2, wl_sym.l, fma_rate)
                 others[m2] = {"value": wl_sym.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,

@@ -80,7 +80,8 @@ struct pht_engine {
     double *d_inject = nullptr;        /* host-supplied evals | Q | Qinv (parity hook), else nullptr */
     void *d_flush = nullptr; size_t flush_bytes = 0;   /* L2 flush scratch (measurement aid) */
     ModelLayout L;
-    int grid_blocks = 0, tail_blocks = 0;
+    int grid_blocks = 0, tail_blocks = 0, replay_blocks = 0;
+    uint4 *d_recs = nullptr;           /* MHRS search -> replay records, one per observation position */
     /* graph */
     cudaGraphExec_t graph_exec = nullptr; int graph_res_rows = -1; double *graph_res = nullptr;
     unsigned long long graph_launches = 0;      /* kernels one replay of the captured sweep launches */
@@ -117,7 +118,7 @@ static SweepParams sweep_params(pht_engine *e) {
     p.items = e->d_items; p.pend0 = e->d_pend0; p.pend1 = e->d_pend1; p.done = e->d_done; p.found = e->d_found;
     p.item_cap = e->item_cap; p.mhrs_cap = e->cfg.mhrs_cap;
     if (e->d_ys) { p.y = e->d_ys; p.cens = e->d_cs; p.perm = e->d_perm; }      /* production layout: decreasing y */
-    p.glist = e->d_glist; p.k_switch = e->k_switch;
+    p.glist = e->d_glist; p.k_switch = e->k_switch; p.recs = e->d_recs;
     if (e->peers_attached) { p.xw = e->d_xw; for (int r = 0; r < e->cfg.world && r < PHT_MAX_WORLD; r++) p.xpeer[r] = e->xpeer[r]; }
     return p;
 }
@@ -150,7 +151,7 @@ static int enqueue_paths(pht_engine *e, const SweepParams &p, const uint32_t *id
         else CU(pht_launch_ecs(p, e->grid_blocks, e->d_idx_exact, e->n_exact, e->d_idx_cens, e->n_cens, e->stream));
         e->launches += (lists_given ? (n_exact != 0) + (n_cens != 0) : (e->n_exact != 0) + (e->n_cens != 0)) - 1;
         break;
-    case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->tail_blocks, e->stream)); e->launches++; break;
+    case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->tail_blocks, e->replay_blocks, e->stream)); e->launches += 2; break;
     case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); break;
     case PHT_METHOD_MHS_HOBOLTH: CU(pht_launch_dcs(p, e->grid_blocks, e->stream, true)); break;
     case PHT_METHOD_MHS_ASLETT:
@@ -206,7 +207,7 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (void *q : e->ipc_opened) cudaIpcCloseMemHandle(q);
-    void *bufs[] = { e->d_ys, e->d_cs, e->d_perm, e->d_glist, e->d_xw, e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
+    void *bufs[] = { e->d_recs, e->d_ys, e->d_cs, e->d_perm, e->d_glist, e->d_xw, e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
                      e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_beta, e->d_pires, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -313,7 +314,8 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         /* global tail: the canonical list */
         if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
         if (cfg->world > 1) CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
-        if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks) != 0) e->grid_blocks = 0;
+        CUE(cudaMalloc(&e->d_recs, ln * sizeof(uint4)));
+        if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks, &e->replay_blocks) != 0) e->grid_blocks = 0;
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }
     if (method_of(e->cfg) == PHT_METHOD_ECS) {

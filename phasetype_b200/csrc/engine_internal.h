@@ -105,7 +105,8 @@ struct DevState {
     unsigned long long unit_counter;
     uint32_t n_items;          /* items appended by the lane phase */
     uint32_t n_pend[2];        /* pending list sizes (double buffered) */
-    uint32_t n_done;           /* finished items awaiting replay */
+    uint32_t n_done;           /* (unused) */
+    unsigned long long replay_next;   /* MHRS replay kernel: next record to hand out */
     uint32_t any_fail[2];      /* MHRS tail, by round parity: some pending observation found no surviving attempt */
     uint32_t n_gpend;          /* global tail: items not finished yet */
     uint32_t xdead;            /* a peer barrier timed out: no further waiting */
@@ -129,6 +130,8 @@ struct SweepParams {
     /* MHRS tail lists */
     TailItem *items; uint32_t *pend0, *pend1, *done; unsigned long long *found; uint32_t item_cap;
     int mhrs_cap;
+    uint4 *recs;               /* MHRS: one 16-byte record per observation position, written by whichever kernel finishes the
+                                  observation's search (lanes or tail), read by the replay kernel */
     uint32_t *glist;           /* global tail: the gathered items in canonical (rank-major) order */
     XchgWindow *xw;            /* this rank's exchange window; nullptr = tail rounds stay local */
     XchgWindow *xpeer[PHT_MAX_WORLD];   /* every rank's window as mapped on this device (xpeer[rank] == xw) */
@@ -158,7 +161,7 @@ cudaError_t pht_launch_peer_allreduce(const ReduceParams &p, cudaStream_t st);
 cudaError_t pht_launch_assemble(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_update(const UpdateParams &p, cudaStream_t st);
 cudaError_t pht_launch_pack_error(const UpdateParams &p, cudaStream_t st);
-cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, cudaStream_t st);
+cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, int replay_blocks, cudaStream_t st);
 /* mh: the LJMA_MHsample_Hobolth variant (method bit 8) instead of the live DCS sampler */
 cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st, bool mh = false);
 int pht_dcs_grid_blocks(int device, int n, bool mh = false);
@@ -171,7 +174,7 @@ cudaError_t pht_launch_mhs_aslett(const SweepParams &p, int grid_blocks, const u
 int pht_mhs_aslett_grid_blocks(int device, int n);
 /* spectral data of the sweep: inject != nullptr copies host-supplied (evals | Q | Qinv) instead of solving on the device */
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st);
-int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks);
+int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks, int *replay_blocks);
 size_t pht_mhrs_smem_bytes(int n);
 cudaError_t pht_sort_by_y_desc(const double *y, const uint8_t *cens, long l, double *ys, uint8_t *cs, uint32_t *perm, cudaStream_t st);
 

@@ -29,9 +29,9 @@
  *     decreasing y (the attempt count is Geometric(survival(y))), so the stream ends with the
  *     cheapest observations and the drain is short.  Every lane holds one prefetched
  *     observation; empty slots are refilled eight or more at a time from a global counter.
- *     A finished observation goes to a per-warp ring with its one or two surviving attempts;
- *     when the ring holds two warps' worth the whole warp runs the MH accept tests and the
- *     exact replays together (converged), instead of each lane on its own.
+ *     A finished observation leaves a 16-byte RECORD (its one or two surviving attempts and the
+ *     end states the accept test needs) in a list indexed by its position; the replay is the
+ *     third kernel's business.
  *   - A lane gives up after `cap` attempts (attempt counts have a heavy tail) and
  *     appends the observation to the tail list.
  *   - Tail phase (same cooperative launch, grid barriers between rounds): the attempts of every
@@ -48,6 +48,13 @@
  *     every rank's `found` word with a system-scope atomicMin, rounds end with a flag barrier in
  *     peer memory, and every rank advances the (identical) MH state machines redundantly.  The
  *     owner replays.  No host, no NCCL call inside the sweep kernel.
+ *   - Replay kernel (k_mhrs_replay, after the tail): persistent lanes stream through the record
+ *     list, make the pending MH accept test, and run the accepted attempt once more with the
+ *     exact FP64 walker, recording on.  A lane takes the next record as soon as its path ends
+ *     (refilled eight or more lanes at a time), so the FP64-heavy recording code runs on nearly
+ *     full warps -- inside the lane kernel it ran in waves at a third of the lanes and was a
+ *     third of that kernel's instructions (profiles/r2c_mhrs_1e7_ncu_full.md) -- and the per-path
+ *     fixed-point z goes to per-lane integer accumulators, reduced once at the end (n <= 8).
  *   - Statistics: N, B in shared-memory integer atomics; z per path in FP64 exactly like the
  *     reference's z2, then added as int64 fixed point, so the sweep totals do not depend on
  *     scheduling or on the number of GPUs.
@@ -82,8 +89,12 @@ namespace cg = cooperative_groups;
 #ifndef END_CAP
 #define END_CAP 32u                 /* attempts a lane still tries once no observations are left */
 #endif
-#define RING 96                     /* per-warp ring of finished observations awaiting accept test + replay */
-#define RING_TRIGGER 64
+#ifndef MHRS_REPLAY_MIN_BLOCKS
+#define MHRS_REPLAY_MIN_BLOCKS 3         /* replay kernel: 80 registers */
+#endif
+#ifndef REPLAY_REFILL_MIN
+#define REPLAY_REFILL_MIN 8         /* idle lanes of a warp that trigger a refill from the record list */
+#endif
 #ifndef PREFETCH_MIN
 #define PREFETCH_MIN 8              /* empty prefetch slots in a warp that trigger a refill */
 #endif
@@ -121,10 +132,11 @@ namespace cg = cooperative_groups;
 #define LOWBITS (1u << 20)          /* exponential uniforms below 2^-12 go to the exact walker */
 #define XBAR_TIMEOUT_NS 4000000000ull
 
-/* ring record flags */
-#define RF_CENS 1u
-#define RF_PROP 2u                  /* a2/j2 hold an MH proposal whose accept test is still to be made */
-#define RF_OFF 4u                   /* a1 runs one draw into its sub-stream */
+/* record of a finished observation (SweepParams::recs[position]): x = accepted attempt so far, y = proposal, z = flags
+ * (bits 8..15: end state of x, bits 16..23: end state of y) */
+#define RF_PROP 2u                  /* y holds an MH proposal whose accept test is still to be made */
+#define RF_OFF 4u                   /* x runs one draw into its sub-stream */
+#define RF_SKIP 8u                  /* no path (the observation was dropped with error word 8) */
 
 template <int NC>
 struct MhrsSmem {
@@ -134,15 +146,11 @@ struct MhrsSmem {
     double scale[NC];                           /* 1 / -S_jj */
     double s[NC];                               /* exit rates (MH accept ratio) */
     double inv_smax;                            /* 1 / max_j scale[j]: the filter clock's unit */
-    double ring_y[MHRS_WARPS * RING];
     unsigned long long zlo[NC];                 /* fixed-point sojourn totals, two limbs (engine_internal.h) */
     long long zhi[NC];
     unsigned int Nacc[NC * NC];
     unsigned int Bacc[NC];
     float A[R + 3];                             /* -ln2 * scale[k] / smax (entry n = 0: absorbed, the clock stands) */
-    uint32_t ring_pos[MHRS_WARPS * RING], ring_og[MHRS_WARPS * RING], ring_a1[MHRS_WARPS * RING],
-             ring_a2[MHRS_WARPS * RING], ring_fl[MHRS_WARPS * RING];
-    unsigned int ring_n[MHRS_WARPS];
     unsigned int paths_done;                    /* replays finished by this block */
     unsigned int scan[MHRS_WARPS + 1];          /* block-level compaction of the global list */
     /* per-lane state that is touched once or twice per observation lives here, not in registers: the prefetched
@@ -250,99 +258,103 @@ MHRS_COLD uint32_t exact_attempt(uint32_t a, bool off, double y, bool cens, uint
     return (ok ? 1u : 0u) | ((uint32_t)w.j << 8) | ((st > 0xffffu ? 0xffffu : st) << 16);
 }
 
-/* Replay one wave of accepted attempts, one per lane (have = this lane holds one), with recording on:
- * gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:104-110.  The walk loop is warp-uniform (lanes that have finished
- * wait for the longest path of the wave: paths of one wave belong to neighbours in the y-ordered layout and are of
- * similar length), so that the bookkeeping after it -- the path's z per state rounded to fixed point, reduced over the
- * warp with shuffles, one shared atomic per state -- runs converged instead of lane by lane. */
+/* ------------------------------------------------------------------------------------------ replay
+ * Persistent lanes over the record list [obs_begin, obs_end): gt_Bladt_MHRS.c:135-137, then eq_Bladt_MHRS.c:79-82 (the
+ * accept test left pending by the lane phase when mhit = 1) and :104-110.  Finished lanes park until REPLAY_REFILL_MIN of
+ * the warp are idle (or nothing is left), then fold their path into the statistics and take new records together. */
 template <int NC>
-__device__ __forceinline__ unsigned replay_wave(bool have, uint32_t pos, uint32_t og, uint32_t a, bool off, double y, bool cens,
-                                                const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n) {
+__device__ __forceinline__ void replay_phase(const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n,
+                                             uint32_t obs_begin, uint32_t obs_end, unsigned &c_jumps) {
     const unsigned FULL = 0xffffffffu; const int lane = threadIdx.x & 31;
-    double z2[NC];
+    constexpr bool LANE_Z = NC <= 8;                    /* per-lane fixed-point totals in registers */
+    long long ztot[LANE_Z ? NC : 1];
 #pragma unroll
-    for (int i = 0; i < NC; i++) z2[i] = 0.0;
+    for (int i = 0; i < (LANE_Z ? NC : 1); i++) ztot[i] = 0;
+    double z2[NC];
     Walk w; Rec rec; rec.lastt = 0.0; rec.B = 0; rec.z2 = z2; rec.out_idx = 0;
-    if (have) {
-        rec.out_idx = (long)(p.perm ? p.perm[pos] : pos) - p.first;
-        walk_begin(w, a, off, og, p, iter);
-    } else { w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true; }
-    unsigned steps = 0;
-    bool act = have;
-    while (__any_sync(FULL, act)) {
-        if (act) { steps++; if (walk_step<true>(w, y, cens, og, p, sm, iter, n, rec)) act = false; }
-    }
-    if (have) z2[w.j] += (cens ? w.t : y) - rec.lastt;
-    if (p.outB != nullptr) {
-        if (have) {
-            p.outB[rec.out_idx] = rec.B;
-            p.outN[rec.out_idx * n * n + w.j + w.j * n]++;
+    w.t = 0.0; w.spare = 0.0; w.spare_hi = 0u; w.a = 0u; w.b = 0u; w.j = 0; w.odd = false; w.fresh = true;
+    double y = 0.0; bool cens = false, act = false, fin = false, dry = false, bad = false; uint32_t og = 0u;
+    unsigned paths = 0;
+    const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !act);
+        if (idle == FULL || (unsigned)__popc(idle) >= REPLAY_REFILL_MIN) {
+            if (fin) {
+                /* ---- the path that ended on this lane: last sojourn, exit count, start count, z in fixed point */
+                fin = false; paths++;
+                z2[w.j] += (cens ? w.t : y) - rec.lastt;
+                if (p.outB != nullptr) {
+                    p.outB[rec.out_idx] = rec.B;
+                    p.outN[rec.out_idx * n * n + w.j + w.j * n]++;
 #pragma unroll 1
-            for (int i = 0; i < n; i++) p.outz[rec.out_idx * n + i] = z2[i];
+                    for (int i = 0; i < n; i++) p.outz[rec.out_idx * n + i] = z2[i];
+                } else {
+                    atomicAdd(&sm.Nacc[w.j + w.j * n], 1u); atomicAdd(&sm.Bacc[rec.B], 1u);
+#pragma unroll
+                    for (int i = 0; i < NC; i++) {
+                        if (i < n) {
+                            const double v = z2[i];
+                            bad = bad || !(v * zs < 4.0e18);
+                            const long long fx = __double2ll_rn(v * zs);
+                            if (LANE_Z) { ztot[LANE_Z ? i : 0] += fx; bad = bad || ztot[LANE_Z ? i : 0] < 0; }
+                            else if (fx != 0) pht_zfix_add(sm.zlo, sm.zhi, i, fx);
+                        }
+                    }
+                }
+            }
+            if (!dry) {
+                const unsigned cnt = __popc(idle);
+                unsigned long long base = 0;
+                if (lane == 0) base = (unsigned long long)obs_begin + atomicAdd(&p.state->replay_next, (unsigned long long)cnt);
+                base = __shfl_sync(FULL, base, 0);
+                const unsigned long long left = base < obs_end ? (unsigned long long)obs_end - base : 0ull;
+                const unsigned avail = left < cnt ? (unsigned)left : cnt;
+                if (avail < cnt) dry = true;
+                const unsigned rank = __popc(idle & ((1u << lane) - 1u));
+                if (!act && rank < avail) {
+                    const unsigned long long pos = base + rank;
+                    const uint4 r = p.recs[pos];
+                    if (!(r.z & RF_SKIP)) {
+                        const uint32_t obs_local = p.perm ? p.perm[pos] : (uint32_t)pos;
+                        y = p.y[pos]; cens = p.cens[pos] != 0; og = p.obs_rank + obs_local * p.obs_world;
+                        rec.out_idx = (long)obs_local - p.first; rec.lastt = 0.0; rec.B = 0;
+                        uint32_t a = r.x;
+                        if (r.z & RF_PROP) {                                                   /* eq_Bladt_MHRS.c:79-82 */
+                            const pht_u32x4 q = philox_block(0u, r.y + 1u, og, iter, p);
+                            const double U = pht_u01(q.v[0], q.v[1]);
+                            if (U < sm.s[(r.z >> 16) & 0xffu] / sm.s[(r.z >> 8) & 0xffu]) a = r.y;
+                        }
+#pragma unroll
+                        for (int i = 0; i < NC; i++) z2[i] = 0.0;
+                        walk_begin(w, a, (r.z & RF_OFF) != 0u, og, p, iter);
+                        act = true;
+                    }
+                }
+            }
         }
-    } else {
-        if (have) { atomicAdd(&sm.Nacc[w.j + w.j * n], 1u); atomicAdd(&sm.Bacc[rec.B], 1u); }
-        const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
-        bool bad = false;
-#pragma unroll 1
-        for (int i = 0; i < n; i++) {
-            const double v = have ? z2[i] : 0.0;
-            bad = bad || !(v * zs < 4.0e18);
-            const long long fx = __double2ll_rn(v * zs);
-            unsigned long long lo = (unsigned long long)fx & 0xffffffffull; long long hi = fx >> 32;
-            for (int d = 16; d > 0; d >>= 1) { lo += __shfl_xor_sync(FULL, lo, d); hi += __shfl_xor_sync(FULL, hi, d); }
-            if (lane == 0 && (lo | (unsigned long long)hi)) {
-                atomicAdd(&sm.zlo[i], lo); atomicAdd(reinterpret_cast<unsigned long long *>(&sm.zhi[i]), (unsigned long long)hi);
+        if (__ballot_sync(FULL, act) == 0u) { if (dry) break; else continue; }
+        __syncwarp();
+        if (act) { c_jumps++; if (walk_step<true>(w, y, cens, og, p, sm, iter, n, rec)) { act = false; fin = true; } }
+    }
+    /* (the loop ends through the refill branch with every lane idle: nothing is left parked) */
+    if (p.outB == nullptr) {
+        if (LANE_Z) {
+#pragma unroll
+            for (int i = 0; i < NC; i++) {
+                if (i < n) {
+                    const long long fx = ztot[LANE_Z ? i : 0];
+                    unsigned long long lo = (unsigned long long)fx & 0xffffffffull; long long hi = fx >> 32;
+                    for (int d = 16; d > 0; d >>= 1) { lo += __shfl_xor_sync(FULL, lo, d); hi += __shfl_xor_sync(FULL, hi, d); }
+                    if (lane == 0 && (lo | (unsigned long long)hi)) {
+                        atomicAdd(&sm.zlo[i], lo); atomicAdd(reinterpret_cast<unsigned long long *>(&sm.zhi[i]), (unsigned long long)hi);
+                    }
+                }
             }
         }
         if (bad) atomicOr(&p.state->error, 2);
     }
-    return steps;
-}
-
-/* the whole warp works through the finished observations waiting in its ring: MH accept test where a proposal is
- * pending (eq_Bladt_MHRS.c:79-82), then the exact replay of the accepted attempt */
-template <int NC>
-MHRS_COLD unsigned replay_session(const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n, int warp) {
-    const int lane = threadIdx.x & 31;
-    unsigned c_jumps = 0;
-    __syncwarp();
-    const unsigned count = sm.ring_n[warp];
-    for (unsigned e0 = 0; e0 < count; e0 += 32u) {
-        const unsigned e = e0 + lane;
-        const bool have = e < count;
-        const unsigned q = warp * RING + (have ? e : 0u);
-        const uint32_t fl = sm.ring_fl[q], og = sm.ring_og[q];
-        uint32_t a = sm.ring_a1[q];
-        if (have && (fl & RF_PROP)) {
-            const uint32_t a2 = sm.ring_a2[q];
-            pht_u32x4 r = philox_block(0u, a2 + 1u, og, iter, p);
-            const double U = pht_u01(r.v[0], r.v[1]);
-            if (U < sm.s[(fl >> 16) & 0xffu] / sm.s[(fl >> 8) & 0xffu]) a = a2;
-        }
-        __syncwarp();
-        c_jumps += replay_wave(have, sm.ring_pos[q], og, a, (fl & RF_OFF) != 0u, sm.ring_y[q], (fl & RF_CENS) != 0u, p, sm, iter, n);
-    }
-    __syncwarp();
-    if (lane == 0) { atomicAdd(&sm.paths_done, count); sm.ring_n[warp] = 0u; }
-    __syncwarp();
-    return c_jumps;
-}
-
-/* replay of the tail's finished observations: waves over the done list, all warps of the grid */
-template <int NC>
-MHRS_COLD unsigned replay_done_list(const SweepParams &p, MhrsSmem<NC> &sm, uint32_t iter, int n,
-                                                         uint32_t n_done, uint32_t gwarp, uint32_t nwarps) {
-    const int lane = threadIdx.x & 31;
-    unsigned c_jumps = 0;
-    for (uint32_t base = gwarp * 32u; base < n_done; base += nwarps * 32u) {
-        const bool have = base + lane < n_done;
-        TailItem it; it.y = 0.0; it.og = 0u; it.pos = 0u; it.a = 0u; it.cur_a = 0u; it.flags = 0u; it.owner = 0u;
-        if (have) it = p.items[p.done[base + lane]];
-        c_jumps += replay_wave(have, it.pos, it.og, it.cur_a, (it.flags & TI_CUROFF) != 0u, it.y, (it.flags & TI_CENS) != 0u, p, sm, iter, n);
-        if (lane == 0) atomicAdd(&sm.paths_done, (n_done - base < 32u) ? n_done - base : 32u);
-    }
-    return c_jumps;
+    for (int d = 16; d > 0; d >>= 1) paths += __shfl_xor_sync(FULL, paths, d);
+    if (lane == 0 && paths) atomicAdd(&sm.paths_done, paths);
 }
 
 /* ------------------------------------------------------------------------------------------ filter walk
@@ -441,7 +453,6 @@ __device__ __forceinline__ void build_tables(const SweepParams &p, MhrsSmem<NC> 
         }
         sm.thr[e] = t52; sm.cum[e] = c;
     }
-    if (tid < MHRS_WARPS) sm.ring_n[tid] = 0u;
     if (tid == 0) sm.paths_done = 0u;
     __syncthreads();
     for (int e = tid; e < (n + 1) * GUIDE; e += MHRS_THREADS) {
@@ -762,9 +773,7 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
             }
             sm.mh_cur_a[tid] = cur_a; sm.mh_misc[tid] = (uint32_t)cur_pre | (cur_off ? 0x100u : 0u) | (kprop << 16);
             if (complete) {
-                const unsigned e = warp * RING + atomicAdd(&sm.ring_n[warp], 1u);
-                sm.ring_y[e] = p.y[pos]; sm.ring_pos[e] = pos; sm.ring_og[e] = o.og; sm.ring_a1[e] = ra1; sm.ring_a2[e] = ra2;
-                sm.ring_fl[e] = rfl | (o.cens ? RF_CENS : 0u);
+                p.recs[pos] = make_uint4(ra1, ra2, rfl, 0u);
                 fl &= ~LF_RUN; surv = false;
             } else if (kprop == 0u) {
                 /* first survivor of an exact observation: go on to the proposal search */
@@ -792,17 +801,15 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
             } else a_lim = 0xFFFFFFFFu;          /* no room: the lane keeps the observation */
         }
         __syncwarp();
-        if (sm.ring_n[warp] >= RING_TRIGGER) c_jumps += replay_session(p, sm, iter, n, warp);
     }
-    c_jumps += replay_session(p, sm, iter, n, warp);
 }
 
 /* block accumulators and per-thread event counts -> global memory */
 template <int NC>
-__device__ __forceinline__ void flush_block(const SweepParams &p, MhrsSmem<NC> &sm, int n, bool per_obs, unsigned c_attempts, unsigned c_jumps) {
+__device__ __forceinline__ void flush_block(const SweepParams &p, MhrsSmem<NC> &sm, int n, bool stats, unsigned c_attempts, unsigned c_jumps) {
     const unsigned FULL = 0xffffffffu; const int tid = threadIdx.x;
     __syncthreads();
-    if (!per_obs) {
+    if (stats) {
         unsigned long long *gN = reinterpret_cast<unsigned long long *>(p.stats);
         for (int i = tid; i < n * n; i += MHRS_THREADS) if (sm.Nacc[i]) atomicAdd(&gN[i], (unsigned long long)sm.Nacc[i]);
         for (int i = tid; i < n; i += MHRS_THREADS) {
@@ -841,7 +848,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_MIN_BLOCKS) k_mhrs_lanes(co
     const uint32_t cap = p.mhrs_cap > 0 ? (uint32_t)p.mhrs_cap : 256u;
     unsigned c_attempts = 0, c_jumps = 0;      /* per thread and sweep: far below 2^32 */
     lane_phase(p, sm, iter, n, smask, obs_begin, obs_end, cap, c_jumps, c_attempts);
-    flush_block(p, sm, n, per_obs, c_attempts, c_jumps);
+    flush_block(p, sm, n, false, c_attempts, c_jumps);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.state->counters[PHT_CNT_NS_LANE], gtimer() - t0);
 }
 
@@ -868,7 +875,7 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
 
     for (uint32_t i = gtid; i < n_items; i += gsize) p.pend0[i] = i;
     if (gtid == 0) {
-        p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull; p.state->n_done = 0u;
+        p.state->n_pend[0] = n_items; p.state->n_pend[1] = 0u; p.state->unit_counter = 0ull;
         p.state->any_fail[0] = 0u; p.state->any_fail[1] = 0u;
     }
     grid.sync();
@@ -936,15 +943,9 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
             const bool mine = !global || it.owner == me;
             if (st == 2 && mine) { atomicAdd(&p.state->counters[PHT_CNT_ERRORS], 1ull); atomicOr(&p.state->error, 8); }
             if (failed && st == 0) atomicOr(&p.state->any_fail[par], 1u);
-            if (global) {
-                if (st == 1 && mine) {
-                    /* back into my own list for the replay */
-                    const uint32_t back = pend[item - me * PHT_GCAP];
-                    p.items[back] = it;
-                    p.done[atomicAdd(&p.state->n_done, 1u)] = back;
-                }
-            } else if (st == 1) p.done[atomicAdd(&p.state->n_done, 1u)] = item;
-            else if (st == 0) pend_next[atomicAdd(&p.state->n_pend[cur ^ 1], 1u)] = item;
+            /* a finished observation leaves its record for the replay kernel (the owner's list, the owner's position) */
+            if (st != 0 && mine) p.recs[it.pos] = (st == 1) ? make_uint4(it.cur_a, 0u, (it.flags & TI_CUROFF) ? RF_OFF : 0u, 0u) : make_uint4(0u, 0u, RF_SKIP, 0u);
+            if (st == 0 && !global) pend_next[atomicAdd(&p.state->n_pend[cur ^ 1], 1u)] = item;
         }
         if (gtid == 0) { if (!global) p.state->n_pend[cur] = 0u; p.state->unit_counter = 0ull; p.state->any_fail[par ^ 1u] = 0u; }
         grid.sync();
@@ -990,43 +991,57 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
         const unsigned long long t = gtimer();
         atomicAdd(&p.state->counters[global ? PHT_CNT_NS_GLOBAL : PHT_CNT_NS_TAIL], t - t_mark); t_mark = t;
     }
-    /* ---- replay the accepted attempt of every tail observation this rank owns */
-    grid.sync();
-    {
-        c_jumps += replay_done_list(p, sm, iter, n, p.state->n_done, gtid / 32u, nwarps);
-    }
     if (gtid == 0) {
         atomicAdd(&p.state->counters[PHT_CNT_TAIL_ROUNDS], (unsigned long long)rounds);
         if (global) atomicAdd(&p.state->counters[PHT_CNT_GLOBAL_ROUNDS], (unsigned long long)(rounds - g0));
     }
-    if (timekeeper) atomicAdd(&p.state->counters[PHT_CNT_NS_REPLAY], gtimer() - t_mark);
-    flush_block(p, sm, n, per_obs, c_attempts, c_jumps);
+    flush_block(p, sm, n, false, c_attempts, c_jumps);
+}
+
+/* Kernel 3: the exact replay of every observation's accepted attempt, with recording on (see replay_phase). */
+template <int NC>
+__global__ void __launch_bounds__(MHRS_THREADS, MHRS_REPLAY_MIN_BLOCKS) k_mhrs_replay(const __grid_constant__ SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MhrsSmem<NC> &sm = *reinterpret_cast<MhrsSmem<NC> *>(smem_raw);
+    const int n = p.n;
+    const uint32_t iter = p.state->iter;
+    const unsigned long long t0 = (blockIdx.x == 0 && threadIdx.x == 0) ? gtimer() : 0ull;
+    build_tables(p, sm, n, ModelLayout::make(n, p.m));
+    const bool per_obs = p.outB != nullptr;
+    const uint32_t obs_begin = per_obs ? (uint32_t)p.first : 0u;
+    const uint32_t obs_end = per_obs ? (uint32_t)(p.first + p.count) : (uint32_t)p.l_local;
+    unsigned c_jumps = 0;
+    replay_phase(p, sm, iter, n, obs_begin, obs_end, c_jumps);
+    flush_block(p, sm, n, !per_obs, 0u, c_jumps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&p.state->counters[PHT_CNT_NS_REPLAY], gtimer() - t0);
 }
 
 /* ------------------------------------------------------------------------------------------ host side */
 template <int NC>
-static int grid_blocks_of(int device, int *lane_blocks, int *tail_blocks) {
-    int a = 0, b = 0, sms = 0;
+static int grid_blocks_of(int device, int *lane_blocks, int *tail_blocks, int *replay_blocks) {
+    int a = 0, b = 0, c = 0, sms = 0;
     const size_t smem = sizeof(MhrsSmem<NC>);
     if (cudaFuncSetAttribute(k_mhrs_lanes<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_mhrs_tail<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_mhrs_lanes<NC>, MHRS_THREADS, smem) != cudaSuccess) return -1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_mhrs_tail<NC>, MHRS_THREADS, smem) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_mhrs_replay<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_mhrs_replay<NC>, MHRS_THREADS, smem) != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-    *lane_blocks = a * sms; *tail_blocks = b * sms;
-    return (a > 0 && b > 0) ? 0 : -1;
+    *lane_blocks = a * sms; *tail_blocks = b * sms; *replay_blocks = c * sms;
+    return (a > 0 && b > 0 && c > 0) ? 0 : -1;
 }
 /* grid sizes: every SM full of resident blocks of each kernel (persistent warps; the tail launch is cooperative) */
-int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks) {
-    if (n <= 8) return grid_blocks_of<8>(device, lane_blocks, tail_blocks);
-    if (n <= 16) return grid_blocks_of<16>(device, lane_blocks, tail_blocks);
-    return grid_blocks_of<32>(device, lane_blocks, tail_blocks);
+int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks, int *replay_blocks) {
+    if (n <= 8) return grid_blocks_of<8>(device, lane_blocks, tail_blocks, replay_blocks);
+    if (n <= 16) return grid_blocks_of<16>(device, lane_blocks, tail_blocks, replay_blocks);
+    return grid_blocks_of<32>(device, lane_blocks, tail_blocks, replay_blocks);
 }
 size_t pht_mhrs_smem_bytes(int n) {
     return n <= 8 ? sizeof(MhrsSmem<8>) : (n <= 16 ? sizeof(MhrsSmem<16>) : sizeof(MhrsSmem<32>));
 }
 
-cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, cudaStream_t st) {
+cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_blocks, int replay_blocks, cudaStream_t st) {
     SweepParams q = p;
     void *args[] = { &q };
     const size_t smem = pht_mhrs_smem_bytes(p.n);
@@ -1036,5 +1051,10 @@ cudaError_t pht_launch_mhrs(const SweepParams &p, int lane_blocks, int tail_bloc
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const void *fn = p.n <= 8 ? (const void *)k_mhrs_tail<8> : (p.n <= 16 ? (const void *)k_mhrs_tail<16> : (const void *)k_mhrs_tail<32>);
-    return cudaLaunchCooperativeKernel(fn, dim3(tail_blocks), dim3(MHRS_THREADS), args, smem, st);
+    e = cudaLaunchCooperativeKernel(fn, dim3(tail_blocks), dim3(MHRS_THREADS), args, smem, st);
+    if (e != cudaSuccess) return e;
+    if (p.n <= 8) k_mhrs_replay<8><<<replay_blocks, MHRS_THREADS, smem, st>>>(q);
+    else if (p.n <= 16) k_mhrs_replay<16><<<replay_blocks, MHRS_THREADS, smem, st>>>(q);
+    else k_mhrs_replay<32><<<replay_blocks, MHRS_THREADS, smem, st>>>(q);
+    return cudaGetLastError();
 }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(64) k_assemble(UpdateParams p) {
 
     for (int i = tid; i < stats_len(n); i += blockDim.x) p.stats[i] = 0;
     if (tid == 0) {
-        p.state->next_obs = 0ull; p.state->unit_counter = 0ull;
+        p.state->next_obs = 0ull; p.state->unit_counter = 0ull; p.state->replay_next = 0ull;
         p.state->n_items = 0u; p.state->n_pend[0] = 0u; p.state->n_pend[1] = 0u; p.state->n_done = 0u;
     }
     if (tid <= n) {
