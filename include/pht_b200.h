@@ -31,7 +31,7 @@ extern "C" {
  *   PHT_B200_SEED     (decimal/hex uint64; default: drawn from unif_rand())
  *   PHT_B200_DEVICE   (CUDA ordinal, default 0)
  *   PHT_B200_GRAPH    (0: launch the sweep's kernels directly instead of replaying a CUDA graph)
- *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail, default 256)
+ *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail; default 32..256 by shard size)
  *   PHT_B200_GPUS     (devices to fan out over, starting at PHT_B200_DEVICE; default: one per 2^19 observations, at most
  *                      all visible.  One host thread + one engine per device; the all-reduce of the statistics and the
  *                      global MHRS tail run through peer memory inside the sweep's kernels; the chain does not depend
@@ -77,7 +77,8 @@ typedef struct pht_config {
     int device;           /* CUDA ordinal */
     int rank, world;      /* this engine holds observations rank, rank+world, ... of the global set */
     int zbits;            /* fractional bits of the fixed-point sojourn totals (pht_choose_zbits) */
-    int mhrs_cap;         /* attempts a lane tries before handing an observation to the cooperative tail; 0 = default */
+    int mhrs_cap;         /* attempts a lane tries before handing an observation to the cooperative tail; 0 = default
+                             (256 for large shards, down to 32 for small ones: 8 x observations per resident lane) */
     int use_graph;        /* capture the sweep in a CUDA graph (1) or launch kernels directly (0) */
 } pht_config;
 
@@ -163,7 +164,8 @@ enum { PHT_CNT_PATHS = 0, PHT_CNT_ATTEMPTS, PHT_CNT_JUMPS, PHT_CNT_DENS_EVALS, P
        PHT_CNT_COUNT = 20 };
 int pht_engine_counters(pht_engine *e, unsigned long long *out);
 /* MHRS tail, per round number (accumulated since creation): ns searching, ns at the barrier after the search, ns
- * advancing, sum of pending observations, sum of attempts offered per observation; out: PHT_ROUND_TRACE x 5 words */
+ * advancing, sum of pending observations, sum of attempts offered per observation,
+ * attempts actually run in the round (all warps); out: PHT_ROUND_TRACE x 6 words */
 #define PHT_ROUND_TRACE 48
 int pht_engine_round_trace(pht_engine *e, unsigned long long *out);
 

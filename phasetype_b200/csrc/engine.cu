@@ -244,7 +244,8 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     e->T.assign(cfg->T, cfg->T + n1 * n1); e->C.assign(cfg->C, cfg->C + n1 * n1);
     e->nu.assign(cfg->nu, cfg->nu + m); e->zeta.assign(cfg->zeta, cfg->zeta + m);
     e->cfg.T = e->T.data(); e->cfg.C = e->C.data(); e->cfg.nu = e->nu.data(); e->cfg.zeta = e->zeta.data();
-    if (e->cfg.mhrs_cap <= 0) e->cfg.mhrs_cap = 256;
+    const bool auto_cap = e->cfg.mhrs_cap <= 0;
+    if (auto_cap) e->cfg.mhrs_cap = 256;
     e->l_local = l_local;
     e->L = ModelLayout::make(n, m);
 #define CUE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail("%s failed: %s", #call, cudaGetErrorString(e_)); pht_engine_destroy(e); return -1; } } while (0)
@@ -317,6 +318,20 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         CUE(cudaMalloc(&e->d_recs, ln * sizeof(uint4)));
         if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks, &e->replay_blocks) != 0) e->grid_blocks = 0;
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
+        if (auto_cap) {
+            /* Attempts a lane spends on one observation before it hands it to the tail.  A lane is a slow worker (one
+             * attempt is ~9 dependent jump-steps of ~0.9 us each with the SM full), so an observation that runs to the cap
+             * occupies its lane for cap x 8 us, and the lane phase cannot end sooner: 2 ms at 256 -- nothing against the
+             * 4.3 ms the lane phase of 10^7 observations takes anyway, twice the whole lane phase of a 1.25 x 10^6 shard
+             * (one GPU's share of the 8-GPU run).  But the tail is the slower searcher per attempt (24 warps per SM, whole
+             * warps per observation), so handing over early only pays at small shards.  Measured (tools/gpu_r2_capsweep.sh,
+             * ms per sweep at cap 256 / 64 / 32): 1.25e6 observations 3.57 / 3.07 / 3.20; 2.5e6: 5.05 / 5.07 / 5.43; 5e6:
+             * 7.45 / 8.16 / 9.02; 1e7: 13.9 / 15.5 / 17.3.  Rule: cap = 8 x observations per resident lane, as a power of
+             * two between 32 and 256.  Results do not depend on it. */
+            const double per_lane = (double)l_local / ((double)e->grid_blocks * 256.0);
+            int cap = 32; while (cap < 256 && (double)(cap * 2) <= 8.0 * per_lane) cap *= 2;
+            e->cfg.mhrs_cap = cap;
+        }
     }
     if (method_of(e->cfg) == PHT_METHOD_ECS) {
         std::vector<uint32_t> ie, ic;

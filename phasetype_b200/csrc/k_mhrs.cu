@@ -925,8 +925,14 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
         else { tv.items = p.xw->gitems[sp]; tv.pend = gl_cur ? p.glist + PHT_MAX_WORLD * PHT_GCAP : p.glist; tv.found = p.xw->gfound[par]; tv.P = Pg; }
         tv.K = K; tv.global = global; tv.parity = par;
         const unsigned long long tr0 = timekeeper ? gtimer() : 0ull;
+        const unsigned att0 = c_attempts;
         tail_search(tv, p, sm, iter, n, smask, nwarps, c_jumps, c_attempts);
         const unsigned long long tr1 = timekeeper ? gtimer() : 0ull;
+        if (rounds < PHT_ROUND_TRACE) {          /* attempts this round ran, over the whole grid (measurement aid) */
+            unsigned d = c_attempts - att0;
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if ((tid & 31) == 0 && d) atomicAdd(&p.state->round_trace[rounds][5], (unsigned long long)d);
+        }
         if (global) peer_barrier(grid, p, ++epoch); else grid.sync();
         const unsigned long long tr2 = timekeeper ? gtimer() : 0ull;
         /* ---- advance each pending observation's MH state machine (eq_Bladt_MHRS.c:65-101); in a global round every
