@@ -417,7 +417,7 @@ def main():
     # independent stream of the same model); for C5 it simulates 2.5 x 10^6 observations and tiles them to its share --
     # the paths still differ, they are keyed by the global observation index -- because simulating 10^8 32-phase
     # absorption times on the host would take longer than the whole bench.
-    if world >= 8 and args.config == 3 and not args.no_others:
+    if world >= int(os.environ.get("PHT_BENCH_BIGCFG_MIN_WORLD", "8")) and args.config == 3 and not args.no_others:
         oc = {}
         for cid, m2, l2, sim in ((4, "ECS", 10 ** 7, None), (5, "MHRS", 10 ** 8, 2500000)):
             per = l2 // world
