@@ -293,7 +293,7 @@ class Runner:
         W = work_per_path(method, wl.n, ev)
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
-        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail + k_mhrs_replay", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
+        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail + k_mhrs_replay", "DCS": "k_dcs_sweep | k_dcs_cplx", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
         cap = ncu_capture(method, l_local)
         issue = None
         mhz = (res.get("clocks") or {}).get("sm_mhz") or getattr(self, "sm_mhz", None)
@@ -464,19 +464,22 @@ def main():
         line["e2e"] = e2e
         # ---- the other two samplers on the same shape (N = 1 only; fewer sweeps)
         if world == 1 and not args.no_others:
-            # ECS runs on the headline workload itself (general dense S: complex eigenvalue pairs go through the real
-            # block form of the spectral formulas); DCS -- whose formulas, the reference's, need a real spectrum and
-            # which reports a complex one instead of sampling from it -- on the symmetrised variant of the same shape
+            # ECS and DCS run on the headline workload itself (general dense S: sweeps whose generator has complex eigenvalue
+            # pairs go through the real block form of the spectral formulas -- for DCS that is a separate, plain kernel,
+            # k_dcs_cplx); "DCS:symmetric" is DCS on the symmetrised variant of the same shape, where every sweep runs
+            # the reference's own arithmetic in the unit-machine kernel
             others = {}
-            for m2 in ("ECS", "DCS"):
+            for m2, sym in (("ECS", False), ("DCS", False), ("DCS", True)):
                 if m2 == method:
                     continue
-                wl_sym = synth.config(args.config, "MHRS" if m2 == "ECS" else m2, l=full_l)
-                r2 = R.timed(wl_sym, m2, np.ascontiguousarray(wl_sym.y), np.ascontiguousarray(wl_sym.censored), float(wl_sym.y.sum()), 5, 3)
+                wl_sym = synth.config(args.config, m2 if sym else "MHRS", l=full_l)
+                c2 = np.ascontiguousarray(wl_sym.censored if m2 != "DCS" else np.zeros_like(wl_sym.censored))
+                r2 = R.timed(wl_sym, m2, np.ascontiguousarray(wl_sym.y), c2, float(wl_sym.y.sum()), 5, 3)
                 rf = R.roofline(wl_sym, m2, r2, wl_sym.l, fma_rate)
-                others[m2] = {"value": wl_sym.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,
+                others[m2 + (":symmetric" if sym else "")] = {"value": wl_sym.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,
                               "workload": wl_sym.name, "steps": 5, "warmup": 3, "gpu_launches": r2["launches"],
                               "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "issue", "kernel", "kernel_ms", "work_per_path")}}
+                del wl_sym
             line["other_methods"] = others
             # ---- the other BASELINE shapes, each at the size BASELINE.json states for one GPU's share (fewer sweeps):
             # C2 = 4-phase Coxian, 10^6 exact observations; C4 = 16-phase tied-rate reliability structure, 10^7

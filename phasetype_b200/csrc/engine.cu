@@ -152,8 +152,8 @@ static int enqueue_paths(pht_engine *e, const SweepParams &p, const uint32_t *id
         e->launches += (lists_given ? (n_exact != 0) + (n_cens != 0) : (e->n_exact != 0) + (e->n_cens != 0)) - 1;
         break;
     case PHT_METHOD_MHRS: CU(pht_launch_mhrs(p, e->grid_blocks, e->tail_blocks, e->replay_blocks, e->stream)); e->launches += 2; break;
-    case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); break;
-    case PHT_METHOD_MHS_HOBOLTH: CU(pht_launch_dcs(p, e->grid_blocks, e->stream, true)); break;
+    case PHT_METHOD_DCS: CU(pht_launch_dcs(p, e->grid_blocks, e->stream)); e->launches++; break;           /* unit machine + complex-spectrum kernel */
+    case PHT_METHOD_MHS_HOBOLTH: CU(pht_launch_dcs(p, e->grid_blocks, e->stream, true)); e->launches++; break;
     case PHT_METHOD_MHS_ASLETT:
         /* every observation through one kernel: the window list in parity mode, else the whole shard (identity) */
         if (lists_given) CU(pht_launch_mhs_aslett(p, e->grid_blocks, idx_exact, n_exact, e->stream));
@@ -548,7 +548,7 @@ static int check_state(pht_engine *e) {
         return fail("device error word 0x%x (%s%s%s%s%s%s%s)", err, (err & 2) ? "sojourn total overflows the fixed-point range (lower PHT_B200_ZBITS); " : "",
                     (err & 4) ? "MHRS tail list overflow; " : "",
                     (err & 8) ? "an observation's survival probability is too small for rejection sampling (more than 4e9 attempts); " : "",
-                    (err & 16) ? "S has complex eigenvalues: the DCS sampler is not valid for it (ECS and MHRS are); " : "",
+                    (err & 16) ? "(unused) " : "",
                     (err & 32) ? "spectral decomposition failed; " : "",
                     (err & 64) ? "a peer GPU did not arrive at a barrier of the global MHRS tail; " : "",
                     (err & 128) ? "another rank of the run raised its error word; " : "");

@@ -3,7 +3,8 @@
 returns the real block form S = Q B Q^-1 (pht_eigen.h) and ECS evaluates exp(xS) through it.  There is nothing in the
 reference to be bit-identical to here, so the checks are (a) the decomposition itself against numpy, on the device,
 and (b) tier 2: conditional E[N_ij | y], E[Z_i | y] and exit-state probabilities of the CUDA sampler against the
-analytic Hobolth-Jensen values, for exact and for right-censored observations; (c) DCS still refuses such a spectrum."""
+analytic Hobolth-Jensen values, for exact and for right-censored observations (ECS) and for exact ones through DCS
+and the MH variants, whose DCS-family kernels switch to the block formulas of k_dcs_cplx on such a sweep."""
 import numpy as np
 import pytest
 
@@ -88,10 +89,42 @@ def test_ecs_chain_runs_on_the_general_dense_workload():
     assert np.abs(np.log(out[10:].mean(0) / wl.theta)).max() < 1.0
 
 
-def test_dcs_reports_a_complex_spectrum():
+@pytest.mark.parametrize("method,mhit", [(4, 1), (8, 30), (16, 30)])
+def test_dcs_family_tier2_on_a_complex_spectrum(method, mhit):
+    """DCS (method 4) and the two MH variants (8: Hobolth chains, 16: Aslett chains; enough proposals to reach the
+    conditional law given absorption AT y) on a generator with a complex pair: analytic conditional expectations."""
     import phasetype_b200 as pb
-    y = np.full(64, 1.0); cens = np.zeros(64, dtype=np.int32)
-    eng, *_ = _engine(4, y, cens)
-    with pytest.raises(pb.EngineError, match="complex eigenvalues"):
-        eng.run(1)
+    l, y0 = 400_000, 1.3
+    y = np.full(l, y0); cens = np.zeros(l, dtype=np.int32)
+    T, C, theta = util.general_model(R4, S4)
+    m = theta.shape[0]
+    eng = pb.Engine(4, T, C, np.full(m, 2.0), np.full(m, 2.0), y, cens, method=method, mhit=mhit, seed=23)
+    eng.set_theta(theta, next_iter=1)
+    N, B, zfix = eng.sweep_stats()
+    zbits = eng.zbits
+    cnt = eng.counters()
     eng.close()
+    n = 4
+    Nm = N.reshape(n, n, order="F") / l; zm = zfix / 2.0 ** zbits / l
+    S, s = util.assemble(T, C, theta, n)
+    Sm = S.reshape(n, n, order="F")
+    assert np.abs(np.linalg.eigvals(Sm).imag).max() > 0.5
+    Ez, EN, exit_p = hobolth_jensen(Sm, s, y0, False)
+    off = ~np.eye(n, dtype=bool)
+    assert B.sum() == l and cnt["nonfinite"] == 0
+    assert np.abs(zm - Ez).max() < 6e-3
+    assert np.abs(Nm[off] - EN[off]).max() < 1.2e-2
+    assert np.abs(np.diag(Nm) - exit_p).max() < 6e-3
+
+
+def test_dcs_chain_runs_on_the_general_dense_workload():
+    """BASELINE config 3 as written under DCS: the chain wanders through generators with and without complex pairs."""
+    import phasetype_b200 as pb
+    from phasetype_b200 import synth
+    wl = synth.config(3, "MHRS", l=20000)
+    cens = np.zeros_like(wl.censored)              # DCS ignores the flag; give it exact observations
+    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, cens, method=4, seed=3)
+    eng.set_theta(wl.theta, next_iter=1)
+    out = eng.run(20)
+    eng.close()
+    assert np.isfinite(out).all() and (out > 0).all()
