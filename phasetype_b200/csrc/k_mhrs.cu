@@ -361,10 +361,8 @@ __device__ __forceinline__ void replay_phase(const SweepParams &p, MhrsSmem<NC> 
  * What a search needs to know of its observation: y in FP32 in units of the largest mean sojourn (smax = max_j
  * scale[j]; the filter clock runs in those units so that its error constants are pure numbers), the part of the
  * per-step error bound that depends on y, the Philox word, and the censoring flag. */
-struct ObsF { float yn, c0y; uint32_t og; bool cens; };
-__device__ __forceinline__ void obs_set(ObsF &o, float yn, uint32_t og, bool cens) {
-    o.yn = yn; o.c0y = __fmaf_rn(1.2e-7f, yn, 4.5e-7f); o.og = og; o.cens = cens;
-}
+struct ObsF { float yn; uint32_t og; bool cens; };
+__device__ __forceinline__ void obs_set(ObsF &o, float yn, uint32_t og, bool cens) { o.yn = yn; o.og = og; o.cens = cens; }
 /* the filter walk of one attempt: FP32 clock t with error bound dacc, sub-stream a, next block b, scan row */
 struct Fast { float t, dacc; uint32_t a, b; int row; };
 
@@ -404,7 +402,8 @@ __device__ __forceinline__ void fast_step(Fast &f, const ObsF &o, const SweepPar
     const float L = (__uint_as_float(0x4b400000u + eb) - 12583071.0f) + lg2m;        /* (eb - 159) + lg2m: log2 of u */
     f.t = __fmaf_rn(L, sm.A[k], f.t);
     const float trunc = __uint_as_float((254u - eb) << 23);                           /* 2^-(exponent of w) >= 1 / w */
-    const float step_err = __fmaf_rn(trunc, 2.0f, __fmaf_rn(fabsf(L), 2.5e-7f, o.c0y));
+    const float c0y = __fmaf_rn(1.2e-7f, o.yn, 4.5e-7f);                              /* the part of the bound that depends on y */
+    const float step_err = __fmaf_rn(trunc, 2.0f, __fmaf_rn(fabsf(L), 2.5e-7f, c0y));
     const bool flagged = (w < 4096u) || (f.b >> 12) != 0u;
     f.dacc = flagged ? __int_as_float(0x7f800000) : f.dacc + step_err;
     const bool absd = (k == n);
@@ -517,13 +516,12 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
     /* per lane: the batch [f.a, a_end) of consecutive attempts of observation my_item it is working through */
     Fast f; fast_begin(f, 0u, n);
     ObsF mo; obs_set(mo, 0.0f, 0u, false);
-    const double inv_smax = sm.inv_smax;
-    double my_y = 0.0; uint32_t my_item = 0xFFFFFFFFu, a_end = 0u; bool active = false;
+    uint32_t my_item = 0xFFFFFFFFu, a_end = 0u; bool active = false;
     unsigned steps = 0;
     /* warp-uniform: the units this warp holds, and the pool being handed out */
     unsigned long long u_next = 0, u_end = 0, last_base = 0, remaining = total_units;
     bool out_of_units = false, finished = false;
-    uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; double y = 0.0; float yf = 0.0f; bool cens = false, first_off = false;
+    uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; float yf = 0.0f; bool cens = false, first_off = false;
     while (!finished) {
         /* ---- the search loop proper: no calls in here (the exact walker is asked from outside, see below) */
         bool want_exact = false, exact_off = false, survived = false; int kend = 0;
@@ -561,7 +559,7 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                         pool_end = pool_next + len;
                         if ((__ldcg(&tv.found[item]) >> 8) >= (unsigned long long)pool_next) {
                             have = true;
-                            y = it.y; yf = (float)(y * inv_smax); cens = (it.flags & TI_CENS) != 0u; og = it.og;
+                            yf = (float)(it.y * sm.inv_smax); cens = (it.flags & TI_CENS) != 0u; og = it.og;
                         } else pool_end = pool_next;
                     }
                 }
@@ -578,7 +576,7 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                     const uint32_t a0 = pool_next + (uint32_t)__popc(idle & ((1u << lane) - 1u)) * bsz;
                     if (!active && a0 < pool_end) {
                         a_end = a0 + bsz < pool_end ? a0 + bsz : pool_end;
-                        my_item = item; my_y = y; obs_set(mo, yf, og, cens);
+                        my_item = item; obs_set(mo, yf, og, cens);
                         fast_begin(f, a0, n);
                         /* the attempt that starts one draw into its sub-stream (after an MH accept test) is the exact walker's */
                         if (first_off && a0 == a_first) { want_exact = true; exact_off = true; } else active = true;
@@ -596,28 +594,28 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                 if (fw != FOUND_NONE) {
                     const uint32_t fa = (uint32_t)(fw >> 8);
                     if (pool_next < pool_end && fa < pool_end) { pool_end = pool_end < fa ? pool_end : fa; pool_next = pool_next < pool_end ? pool_next : pool_end; }
-                    if (my_item == item) { a_end = a_end < fa ? a_end : fa; if (f.a > fa) active = false; }
+                    if (my_item == item) { a_end = a_end < fa ? a_end : fa; if (active && f.a > fa) { active = false; c_jumps += f.b; } }
                 }
             }
             __syncwarp();           /* lanes that have just drawn a batch step together with the rest */
             if (active) {
                 bool fail, surv, amb; int k;
                 fast_step(f, mo, p, sm, iter, n, fail, surv, amb, k);
-                c_jumps++;
                 if (surv && !((smask >> k) & 1u)) { surv = false; fail = true; }     /* alive at y in a state that cannot exit: failed */
+                /* (jump-steps are counted when an attempt ends: f.b of them) */
                 if (fail) {
-                    c_attempts++;
+                    c_attempts++; c_jumps += f.b;
                     const uint32_t na = f.a + 1u;
                     if (na < a_end) fast_begin(f, na, n); else active = false;
-                } else if (surv) { c_attempts++; survived = true; kend = k; active = false; }
-                else if (amb) { want_exact = true; active = false; }
+                } else if (surv) { c_attempts++; c_jumps += f.b; survived = true; kend = k; active = false; }
+                else if (amb) { c_jumps += f.b; want_exact = true; active = false; }
             }
             if (__any_sync(FULL, survived || want_exact)) break;
         }
         if (finished) break;
         /* ---- attempts the filter could not decide (or that start off the block boundary): the exact walker */
         if (want_exact) {
-            const uint32_t res = exact_attempt(f.a, exact_off, my_y, mo.cens, mo.og, p, sm, iter, n, smask);
+            const uint32_t res = exact_attempt(f.a, exact_off, tv.items[my_item].y, mo.cens, mo.og, p, sm, iter, n, smask);
             c_jumps += res >> 16; c_attempts++;
             survived = res & 1u; kend = (int)((res >> 8) & 0xffu);
             if (!survived) {
@@ -640,7 +638,7 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
         if (smk) {
             const int src = __ffs(smk) - 1;
             const uint32_t s_item = __shfl_sync(FULL, my_item, src), s_a = __shfl_sync(FULL, f.a, src);
-            if (my_item == s_item) { a_end = a_end < s_a ? a_end : s_a; if (active && f.a > s_a) active = false; }
+            if (my_item == s_item) { a_end = a_end < s_a ? a_end : s_a; if (active && f.a > s_a) { active = false; c_jumps += f.b; } }
             if (s_item == item && pool_next < pool_end) {
                 pool_end = pool_end < s_a ? pool_end : s_a;
                 pool_next = pool_next < pool_end ? pool_next : pool_end;
@@ -738,11 +736,11 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
             if (run) {
                 bool fail;
                 fast_step(f, o, p, sm, iter, n, fail, surv, amb, k);
-                c_jumps++;
-                if (fail) { fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
+                if (fail) { c_jumps += f.b; fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
             }
         } while (!__any_sync(FULL, surv || amb || hand));
         /* ---- events, a few lanes at a time */
+        if (surv || amb) c_jumps += f.b;            /* the filter steps of the attempt that just ended (failed ones: above) */
         if (amb) {
             const uint32_t res = exact_attempt(f.a, false, p.y[pos], o.cens, o.og, p, sm, iter, n, ~0u);
             surv = res & 1u; k = (int)((res >> 8) & 0xffu); c_jumps += res >> 16;

@@ -96,7 +96,7 @@ def test_wrapper_argument_checks_follow_the_r_code():
         api.phtMCMC(x, 11, np.ones(11), np.ones(121), np.ones(11), 5)
 
 
-@pytest.mark.parametrize("kw,msg", [(dict(n=0), "outside 1.."), (dict(n=33), "outside 1.."), (dict(method=8), "unknown sampling method"),
+@pytest.mark.parametrize("kw,msg", [(dict(n=0), "outside 1.."), (dict(n=33), "outside 1.."), (dict(method=32), "unknown sampling method"),
                                     (dict(mhit=-1), "mhit"), (dict(rank=2, world=2), "bad shard"), (dict(zbits=60), "zbits")])
 def test_engine_rejects_bad_arguments_before_touching_the_device(kw, msg):
     a = dict(n=3, method=1, mhit=1, rank=0, world=1, zbits=30); a.update(kw)
