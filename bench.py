@@ -293,7 +293,7 @@ class Runner:
         W = work_per_path(method, wl.n, ev)
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
-        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail + k_mhrs_replay", "DCS": "k_dcs_sweep | k_dcs_cplx", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
+        kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail + k_mhrs_replay", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
         cap = ncu_capture(method, l_local)
         issue = None
         mhz = (res.get("clocks") or {}).get("sm_mhz") or getattr(self, "sm_mhz", None)
@@ -465,9 +465,9 @@ def main():
         # ---- the other two samplers on the same shape (N = 1 only; fewer sweeps)
         if world == 1 and not args.no_others:
             # ECS and DCS run on the headline workload itself (general dense S: sweeps whose generator has complex eigenvalue
-            # pairs go through the real block form of the spectral formulas -- for DCS that is a separate, plain kernel,
-            # k_dcs_cplx); "DCS:symmetric" is DCS on the symmetrised variant of the same shape, where every sweep runs
-            # the reference's own arithmetic in the unit-machine kernel
+            # pairs go through the real block form of the spectral formulas -- for DCS the CPLX instance of the same
+            # unit-machine kernel); "DCS:symmetric" is DCS on the symmetrised variant of the same shape, where every
+            # sweep runs the reference's own arithmetic
             others = {}
             for m2, sym in (("ECS", False), ("DCS", False), ("DCS", True)):
                 if m2 == method:

@@ -42,7 +42,7 @@ constexpr int kBatchUnroll = DCS_UNROLL;
 
 template <int THREADS>
 struct DcsSmem {
-    double *S, *Q, *Qinv, *evals, *s, *pi, *PIQ, *D;
+    double *S, *Q, *Qinv, *evals, *evi, *s, *pi, *PIQ, *D;
     double *X, *E, *P, *Z;
     unsigned long long *zlo; long long *zhi; unsigned int *Nacc, *Bacc, *deg;
     __device__ __forceinline__ void carve(unsigned char *raw, int n) {
@@ -53,20 +53,20 @@ struct DcsSmem {
         const int ld = n | 1;
         /* (Qinv has one more column, n: Q^-1 b of the MH variant's exit set, so that "column b" reads work for both) */
         S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += (n + 1) * ld; D = d; d += n * ld;
-        evals = d; d += n; s = d; d += n; pi = d; d += n; PIQ = d; d += n;
+        evals = d; d += n; evi = d; d += n; s = d; d += n; pi = d; d += n; PIQ = d; d += n;
         X = d; d += n * THREADS; E = d; d += n * THREADS; P = d; d += n * THREADS; Z = d; d += n * THREADS;
         zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
         Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n; deg = Bacc + n;
     }
     static size_t bytes(int n) {
-        return sizeof(double) * (size_t)(2 * n * n + (2 * n + 1) * (n | 1) + 4 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
+        return sizeof(double) * (size_t)(2 * n * n + (2 * n + 1) * (n | 1) + 5 * n + 4 * n * THREADS + 2 * n) + sizeof(unsigned int) * (size_t)(n * n + 2 * n);
     }
 };
 
 /* MH = false: the live DCS sampler.  MH = true: LJMA_MHsample_Hobolth (gt_Hobolth_DCS.c:268-355, method bit 8; nothing
  * in the reference calls it): no end-state draw, the chain is conditioned on being in the exit set {j : s_j > 0} at y
  * (w = Q^-1 b, kept as column n of the Qinv table), and the chains go through the MH wrapper of path_common.cuh. */
-template <int THREADS, bool MH>
+template <int THREADS, bool MH, bool CPLX>
 __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dcs_sweep(SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x, ld = n | 1;
@@ -74,14 +74,22 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     const ModelLayout ML = ModelLayout::make(n, p.m);
     DcsSmem<THREADS> sm; sm.carve(smem_raw, n);
     const uint32_t iter = p.state->iter;
-    /* complex pairs in the spectrum: the reference's formulas (this kernel) are not valid; k_dcs_cplx below takes the sweep */
+    /* complex pairs in the spectrum: the reference's formulas (CPLX = false) are not valid; the CPLX = true instance of
+     * this kernel takes the sweep (both are launched, the spectrum is known on the device only) */
     { bool cplx = false; for (int i = 0; i < n; i++) cplx = cplx || (p.model[ML.evals_im + i] != 0.0);
-      if (cplx) return; }
+      if (cplx != CPLX) return; }
+    /* CPLX: which eigen-indices open (pfirst) and close (psecond) a pair a -+ ib; warp-uniform bit masks */
+    uint32_t pfirst = 0u, psecond = 0u;
+    if (CPLX) {
+        for (int i = 0; i + 1 < n; i++)
+            if (!((psecond >> i) & 1u) && p.model[ML.evals_im + i] > 0.0) { pfirst |= 1u << i; psecond |= 1u << (i + 1); }
+    }
+    const uint32_t ppair = pfirst | psecond;
     for (int i = tid; i < n * n; i += THREADS) {
         sm.S[i] = p.model[ML.S + i]; sm.Q[i] = p.model[ML.Q + i]; sm.Qinv[(i % n) + (i / n) * ld] = p.model[ML.Qinv + i]; sm.Nacc[i] = 0u;
     }
     for (int i = tid; i < n; i += THREADS) {
-        sm.evals[i] = p.model[ML.evals + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
+        sm.evals[i] = p.model[ML.evals + i]; sm.evi[i] = p.model[ML.evals_im + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
         sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
     }
     __syncthreads();
@@ -98,7 +106,15 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     /* observation-independent tables: D[j][i] = ev_i - S_jj, the degenerate flags, and pi^T Q in reference-BLAS order */
     for (int e = tid; e < n * n; e += THREADS) {
         const int j = e / n, i = e % n;
-        sm.D[j * ld + i] = sm.evals[i] - sm.S[j + j * n];
+        if (!CPLX) sm.D[j * ld + i] = sm.evals[i] - sm.S[j + j * n];
+        else {
+            /* RECIPROCALS (nothing to be bit-identical to here): 1 / (ev_i - S_jj) for a real eigenvalue; for a pair in
+             * (i, i + 1) the complex 1 / (lam - S_jj) at lam = a - ib, real part in slot i, imaginary part in slot i + 1 */
+            const int base = ((psecond >> i) & 1u) ? i - 1 : i;
+            const double dr = sm.evals[base] - sm.S[j + j * n];
+            if ((ppair >> i) & 1u) { const double bi = sm.evi[base], den = dr * dr + bi * bi; sm.D[j * ld + i] = (base == i ? dr : bi) / den; }
+            else sm.D[j * ld + i] = 1.0 / dr;
+        }
     }
     for (int c = tid; c < n; c += THREADS) {
         double acc = 0.0;
@@ -107,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
         const double Sjj = sm.S[c + c * n];
         unsigned m = 0u;
         for (int i = 0; i < n; i++) m |= (fabs((sm.evals[i] - Sjj) / Sjj) < 1e-13) ? (1u << i) : 0u;
-        sm.deg[c] = m;
+        sm.deg[c] = m & ~ppair;
     }
     __syncthreads();
 
@@ -145,8 +161,21 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
         /* ---- the unit's exponential batch: exp(alpha ev_i + beta), into E for a JUMP unit, else into X */
         if (kind0 != K_IDLE) {
             double *dst = (kind0 == K_JUMP ? sm.E : sm.X) + tid;
+            if (!CPLX) {
 #pragma unroll kBatchUnroll
-            for (int i = 0; i < n; i++) dst[i * THREADS] = pht_exp(alpha * sm.evals[i] + beta);
+                for (int i = 0; i < n; i++) dst[i * THREADS] = pht_exp(alpha * sm.evals[i] + beta);
+            } else {
+                /* exp(alpha lam + beta) at lam = a - ib: real part in slot i, imaginary part in slot i + 1 */
+#pragma unroll 1
+                for (int i = 0; i < n; i++) {
+                    const double ex = pht_exp(alpha * sm.evals[i] + beta);
+                    if ((pfirst >> i) & 1u) {
+                        double sn, cs; sincos(alpha * sm.evi[i], &sn, &cs);
+                        dst[i * THREADS] = ex * cs; dst[(i + 1) * THREADS] = -(ex * sn);
+                        i++;
+                    } else dst[i * THREADS] = ex;
+                }
+            }
         }
         __syncwarp();
 
@@ -174,9 +203,30 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 const double Sjj = sm.S[j_r + j_r * n];
                 eS = pht_exp(Sjj * T_r);
                 Ei = sm.E[gi * THREADS + col];
-                val1 = sm.Q[j_r + gi * n] * Ei * sm.Qinv[gi + b_r * ld];                                      /* :118-121 */
+                if (!CPLX || !((ppair >> gi) & 1u)) val1 = sm.Q[j_r + gi * n] * Ei * sm.Qinv[gi + b_r * ld];  /* :118-121 */
+                else if ((pfirst >> gi) & 1u) {
+                    /* the pair's term of u^T exp(T B) v: Re(E) (u1 v1 + u2 v2) - Im(E) (u1 v2 - u2 v1) */
+                    const double u1 = sm.Q[j_r + gi * n], u2 = sm.Q[j_r + (gi + 1) * n];
+                    const double v1 = sm.Qinv[gi + b_r * ld], v2 = sm.Qinv[gi + 1 + b_r * ld];
+                    val1 = Ei * (u1 * v1 + u2 * v2) - sm.E[(gi + 1) * THREADS + col] * (u1 * v2 - u2 * v1);
+                }
             }
-            if (wn) sm.X[gi * THREADS + col] = sm.PIQ[gi] * sm.X[gi * THREADS + col];                        /* p = (pi^T Q) o exp(ev y) */
+            if (!CPLX) {
+                if (wn) sm.X[gi * THREADS + col] = sm.PIQ[gi] * sm.X[gi * THREADS + col];                    /* p = (pi^T Q) o exp(ev y) */
+            } else {
+                /* p = (pi^T Q) exp(y B): a pair's two components mix, so read both before anyone writes */
+                double nx = 0.0;
+                if (wn) {
+                    if ((ppair >> gi) & 1u) {
+                        const int base = ((psecond >> gi) & 1u) ? gi - 1 : gi;
+                        const double r1 = sm.PIQ[base], r2 = sm.PIQ[base + 1];
+                        const double xr = sm.X[base * THREADS + col], xi = sm.X[(base + 1) * THREADS + col];
+                        nx = (base == gi) ? r1 * xr + r2 * xi : r2 * xr - r1 * xi;
+                    } else nx = sm.PIQ[gi] * sm.X[gi * THREADS + col];
+                }
+                __syncwarp();
+                if (wn) sm.X[gi * THREADS + col] = nx;
+            }
             __syncwarp();
             if (wn) {                                                                                        /* (p^T Q^-1)_i s_i */
                 double acc = 0.0;
@@ -189,7 +239,18 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             for (int q = 0; q < n; q++) sum1 += __shfl_sync(FULL, val1, gbase + q);
             if (wj) {
                 const unsigned dg = sm.deg[j_r];
-                sm.X[gi * THREADS + col] = ((dg >> gi) & 1u) ? T_r * Ei : (Ei - eS) / sm.D[j_r * ld + gi];    /* :137-144 */
+                if (!CPLX) sm.X[gi * THREADS + col] = ((dg >> gi) & 1u) ? T_r * Ei : (Ei - eS) / sm.D[j_r * ld + gi];    /* :137-144 */
+                else if (!((ppair >> gi) & 1u))
+                    sm.X[gi * THREADS + col] = (((dg >> gi) & 1u) ? T_r * Ei : (Ei - eS) * sm.D[j_r * ld + gi]) * sm.Qinv[gi + b_r * ld];
+                else {
+                    /* component gi of J(T) v: J = (e^{lam T} - e^{S_jj T}) / (lam - S_jj) times v1 + i v2, as complex numbers */
+                    const int base = ((psecond >> gi) & 1u) ? gi - 1 : gi;
+                    const double Nr = sm.E[base * THREADS + col] - eS, Ni = sm.E[(base + 1) * THREADS + col];
+                    const double DR = sm.D[j_r * ld + base], DI = sm.D[j_r * ld + base + 1];
+                    const double Jr = Nr * DR - Ni * DI, Ji = Nr * DI + Ni * DR;
+                    const double v1 = sm.Qinv[base + b_r * ld], v2 = sm.Qinv[base + 1 + b_r * ld];
+                    sm.X[gi * THREADS + col] = (base == gi) ? Jr * v1 - Ji * v2 : Jr * v2 + Ji * v1;
+                }
             }
             if (wn) sm.P[gi * THREADS + col] = val1 / sum1;
             __syncwarp();
@@ -198,7 +259,8 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
                 if (gi != j_r) {                                                                              /* :148-159 */
                     double tmp = 0.0;
 #pragma unroll 1
-                    for (int q = 0; q < n; q++) tmp += sm.Q[gi + q * n] * sm.X[q * THREADS + col] * sm.Qinv[q + b_r * ld];
+                    for (int q = 0; q < n; q++) tmp += CPLX ? sm.Q[gi + q * n] * sm.X[q * THREADS + col]
+                                                             : sm.Q[gi + q * n] * sm.X[q * THREADS + col] * sm.Qinv[q + b_r * ld];
                     v = sm.S[j_r + gi * n] / sum1 * tmp;
                 }
                 sm.P[gi * THREADS + col] = v;
@@ -224,11 +286,30 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
             /* ---- one evaluation of the sojourn CDF at x = bb (gt_Hobolth_DCS.c:23-40), then Brent's bracket update */
             const unsigned dg = sm.deg[j];
             double tmp = 0.0;
+            if (!CPLX) {
 #pragma unroll 1
-            for (int i = 0; i < n; i++) {
-                const double Ei = sm.E[i * THREADS + tid];
-                const double Ji = ((dg >> i) & 1u) ? bb * Ei : (Ei - sm.X[i * THREADS + tid]) / sm.D[j * ld + i];
-                tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + b * ld];
+                for (int i = 0; i < n; i++) {
+                    const double Ei = sm.E[i * THREADS + tid];
+                    const double Ji = ((dg >> i) & 1u) ? bb * Ei : (Ei - sm.X[i * THREADS + tid]) / sm.D[j * ld + i];
+                    tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + b * ld];
+                }
+            } else {
+                /* Q[k, :] J(x) v with J's pair block (e^{lam T} - e^{lam (T - x) + S_jj x}) / (lam - S_jj) in complex arithmetic */
+#pragma unroll 1
+                for (int i = 0; i < n; i++) {
+                    const double Nr = sm.E[i * THREADS + tid] - sm.X[i * THREADS + tid];
+                    if ((pfirst >> i) & 1u) {
+                        const double Ni = sm.E[(i + 1) * THREADS + tid] - sm.X[(i + 1) * THREADS + tid];
+                        const double DR = sm.D[j * ld + i], DI = sm.D[j * ld + i + 1];
+                        const double Jr = Nr * DR - Ni * DI, Ji = Nr * DI + Ni * DR;
+                        const double v1 = sm.Qinv[i + b * ld], v2 = sm.Qinv[i + 1 + b * ld];
+                        tmp += sm.Q[k + i * n] * (Jr * v1 - Ji * v2) + sm.Q[k + (i + 1) * n] * (Jr * v2 + Ji * v1);
+                        i++;
+                    } else {
+                        const double Ji = ((dg >> i) & 1u) ? bb * sm.E[i * THREADS + tid] : Nr * sm.D[j * ld + i];
+                        tmp += sm.Q[k + i * n] * Ji * sm.Qinv[i + b * ld];
+                    }
+                }
             }
             fb = coef * tmp - u;
             c_evals++;
@@ -344,262 +425,19 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
     }
 }
 
-/* ------------------------------------------------------------------------------------------ complex spectra
- * SURVEY 8(f)2.  With complex eigenvalue pairs the reference's formulas are silently wrong (it keeps the real parts,
- * src/utility.c:116-121).  pht_eigen.h returns the real block form S = Q B Q^-1 (a pair a +- ib in positions (i, i+1)
- * is the block [[a, b], [-b, a]]), and every quantity of the sampler is a bilinear form u^T F(B) v with F block diagonal:
- *     P_ab            F = exp(T B)
- *     jump weights    F = J(T),   J(x) = int_0^x e^{S_jj u} exp((T - u) B) du
- *     sojourn CDF     F = J(x)
- * A 2x2 block [[p, q], [-q, p]] acts on (v1, v2) like the complex number p - iq on v1 + i v2, so the block of J(x) is
- * (e^{lam T} - e^{lam (T - x) + S_jj x}) / (lam - S_jj) at lam = a - ib, in real arithmetic below.  There is nothing in the
- * reference to be bit-identical to; the sampler is checked against the analytic conditional expectations (tier 2,
- * tests/test_complex_gpu.py).  One observation per lane, the whole path in the lane (this kernel runs only on sweeps
- * whose generator has a complex spectrum; the unit machine above stays the reference's arithmetic, bit for bit). */
-struct DcsCplxSmem {
-    double *S, *Q, *Qinv, *evals, *evi, *s, *pi, *Qb;
-    unsigned long long *zlo; long long *zhi; unsigned int *Nacc, *Bacc;
-    __device__ __forceinline__ void carve(unsigned char *raw, int n) {
-        double *d = reinterpret_cast<double *>(raw);
-        S = d; d += n * n; Q = d; d += n * n; Qinv = d; d += n * n;
-        evals = d; d += n; evi = d; d += n; s = d; d += n; pi = d; d += n; Qb = d; d += n;
-        zlo = reinterpret_cast<unsigned long long *>(d); d += n; zhi = reinterpret_cast<long long *>(d); d += n;
-        Nacc = reinterpret_cast<unsigned int *>(d); Bacc = Nacc + n * n;
-    }
-    static size_t bytes(int n) { return sizeof(double) * (size_t)(3 * n * n + 7 * n) + sizeof(unsigned int) * (size_t)(n * n + n); }
-};
-
-/* out = J(x) v  (x = T gives the jump weights' J(T)); degenerate real eigenvalues as gt_Hobolth_DCS.c:29,139 */
-static __device__ __noinline__ void cplx_J(double *out, const double *v, const double *ev, const double *evi, int n,
-                                           double T, double x, double Sjj) {
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        const double a = ev[i], b = evi[i];
-        if (b > 0.0 && i + 1 < n) {
-            double sT, cT, s2, c2;
-            const double eT = pht_exp(a * T), e2 = pht_exp(a * (T - x) + Sjj * x);
-            sincos(b * T, &sT, &cT); sincos(b * (T - x), &s2, &c2);
-            const double nr = eT * cT - e2 * c2, ni = -(eT * sT - e2 * s2);          /* numerator at lam = a - ib */
-            const double dr = a - Sjj, di = -b, den = dr * dr + di * di;
-            const double jr = (nr * dr + ni * di) / den, ji = (ni * dr - nr * di) / den;
-            const double pp = jr, qq = -ji;
-            const double v1 = v[i], v2 = v[i + 1];
-            out[i] = pp * v1 + qq * v2; out[i + 1] = pp * v2 - qq * v1;
-            i++;
-        } else {
-            double J;
-            if (fabs((a - Sjj) / Sjj) < 1e-13) J = x * pht_exp(a * T);
-            else J = (pht_exp(a * T) - pht_exp((T - x) * a + Sjj * x)) / (a - Sjj);
-            out[i] = J * v[i];
-        }
-    }
-}
-/* u^T exp(x B) v, u with stride su */
-static __device__ __noinline__ double cplx_bilinear(const double *u, int su, const double *v, const double *ev, const double *evi, int n, double x) {
-    double acc = 0.0;
-#pragma unroll 1
-    for (int i = 0; i < n; i++) {
-        const double b = evi[i], ex = pht_exp(ev[i] * x);
-        if (b > 0.0 && i + 1 < n) {
-            double sn, cs; sincos(b * x, &sn, &cs);
-            const double u1 = u[i * su], u2 = u[(i + 1) * su], v1 = v[i], v2 = v[i + 1];
-            acc += ex * (cs * (u1 * v1 + u2 * v2) + sn * (u1 * v2 - u2 * v1));
-            i++;
-        } else acc += (u[i * su] * ex) * v[i];
-    }
-    return acc;
-}
-
-template <bool MH>
-__global__ void __launch_bounds__(128) k_dcs_cplx(SweepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, tid = threadIdx.x;
-    const unsigned FULL = 0xffffffffu;
-    const ModelLayout ML = ModelLayout::make(n, p.m);
-    { bool cplx = false; for (int i = 0; i < n; i++) cplx = cplx || (p.model[ML.evals_im + i] != 0.0);
-      if (!cplx) return; }
-    DcsCplxSmem sm; sm.carve(smem_raw, n);
-    const uint32_t iter = p.state->iter;
-    for (int i = tid; i < n * n; i += 128) { sm.S[i] = p.model[ML.S + i]; sm.Q[i] = p.model[ML.Q + i]; sm.Qinv[i] = p.model[ML.Qinv + i]; sm.Nacc[i] = 0u; }
-    for (int i = tid; i < n; i += 128) {
-        sm.evals[i] = p.model[ML.evals + i]; sm.evi[i] = p.model[ML.evals_im + i]; sm.s[i] = p.model[ML.s + i]; sm.pi[i] = p.model[ML.pi + i];
-        sm.zlo[i] = 0ull; sm.zhi[i] = 0; sm.Bacc[i] = 0u;
-    }
-    __syncthreads();
-    uint32_t bmask = 0u;
-    if (MH) {
-        for (int i = 0; i < n; i++) bmask |= (sm.s[i] > 0.0) ? (1u << i) : 0u;
-        for (int i = tid; i < n; i += 128) {
-            double acc = 0.0;
-            for (int jj = 0; jj < n; jj++) acc += (1.0 * (((bmask >> jj) & 1u) ? 1.0 : 0.0)) * sm.Qinv[i + jj * n];
-            sm.Qb[i] = acc;
-        }
-    }
-    __syncthreads();
-    unsigned c_jumps = 0, c_evals = 0, c_paths = 0, c_fail = 0;
-    Dispenser disp; disp.init(p);
-    PathRng rng; rng.seek(0);
-    MhChain mh; mh.begin(false);
-    const double EPS = 2.220446049250313e-16;
-    double wk[PHT_NMAX], pw[PHT_NMAX], z[PHT_NMAX];
-    for (;;) {
-        /* wave by wave: the dispenser is a warp collective, so every lane comes back here together */
-        const unsigned long long o = disp.take(p, FULL, true);
-        if (__ballot_sync(FULL, o != ~0ull) == 0u) { if (disp.exhausted) break; else continue; }
-        if (o != ~0ull) {
-        const double y = p.y[o]; const long out_idx = (long)o - p.first;
-        rng.seek(p.obs_rank + (uint32_t)o * p.obs_world);
-        if (MH) mh.begin(p.cens[o] != 0);
-        for (;;) {                                              /* chains of this observation (one unless MH) */
-            const bool rec = !MH || mh.rec;
-            int b = 0;
-            const double *w = sm.Qb;
-            if (!MH) {
-                /* end state with weight (pi^T exp(yS))_i s_i (eq_AslettHobolth_DCS.c:11-51): r = pi^T Q, r exp(yB), then Q^-1 */
-#pragma unroll 1
-                for (int c = 0; c < n; c++) { double acc = 0.0; for (int i = 0; i < n; i++) acc += sm.Q[i + c * n] * sm.pi[i]; wk[c] = acc; }
-#pragma unroll 1
-                for (int i = 0; i < n; i++) {
-                    const double bb = sm.evi[i], ex = pht_exp(sm.evals[i] * y);
-                    if (bb > 0.0 && i + 1 < n) {
-                        double sn, cs; sincos(bb * y, &sn, &cs);
-                        const double r1 = wk[i], r2 = wk[i + 1];
-                        wk[i] = ex * (r1 * cs - r2 * sn); wk[i + 1] = ex * (r1 * sn + r2 * cs);
-                        i++;
-                    } else wk[i] = wk[i] * ex;
-                }
-                double sum = 0.0;
-#pragma unroll 1
-                for (int i = 0; i < n; i++) { double acc = 0.0; for (int q = 0; q < n; q++) acc += sm.Qinv[q + i * n] * wk[q]; pw[i] = acc * sm.s[i]; sum += pw[i]; }
-                const double target = rng.next(p, iter);
-                double sofar = 0.0; int q = 0;
-#pragma unroll 1
-                while (sofar < target && q <= n - 1) { sofar += pw[q] / sum; q++; }
-                b = q - 1 < 0 ? 0 : q - 1;
-                w = sm.Qinv + b * n;
-            }
-            int B;
-            {
-                const double target = rng.next(p, iter);
-                double sofar = 0.0; int q = 0;
-#pragma unroll 1
-                while (sofar < target && q <= n - 1) { sofar += sm.pi[q]; q++; }
-                B = q - 1 < 0 ? 0 : q - 1;
-            }
-#pragma unroll 1
-            for (int i = 0; i < n; i++) z[i] = 0.0;
-            double t = 0.0; int j = B;
-#pragma unroll 1
-            while (t < y) {
-                const double T = y - t, Sjj = sm.S[j + j * n];
-                const double Pab = cplx_bilinear(sm.Q + j, n, w, sm.evals, sm.evi, n, T);
-                if (MH ? (((bmask >> j) & 1u) != 0u) : (j == b)) {
-                    if (rng.next(p, iter) < pht_exp(Sjj * T) / Pab) { z[j] += T; if (rec) count_transition(p, n, sm.Nacc, out_idx, j, j); break; }
-                }
-                cplx_J(wk, w, sm.evals, sm.evi, n, T, T, Sjj);
-                double p_sum = 0.0;
-#pragma unroll 1
-                for (int i = 0; i < n; i++) {
-                    double v = 0.0;
-                    if (i != j) { double tmp = 0.0; for (int q = 0; q < n; q++) tmp += sm.Q[i + q * n] * wk[q]; v = sm.S[j + i * n] / Pab * tmp; }
-                    pw[i] = v; p_sum += v;
-                }
-                const double target = (p_sum == 0.0) ? 0.0 : p_sum * rng.next(p, iter);
-                int k;
-                { double sofar = 0.0; int q = 0;
-#pragma unroll 1
-                  while (sofar < target && q <= n - 1) { sofar += pw[q]; q++; }
-                  k = q - 1 < 0 ? 0 : q - 1; }
-                const double u = rng.next(p, iter);
-                const double coef = 1 / pw[k] * sm.S[j + k * n] / Pab;
-                /* Brent's zeroin on [0, T], f(0) = -u, f(T) = 1 - u, Tol = 0, Maxit = 1000 (utility.c:233-338) */
-                double ba = 0.0, bb = T, bc = 0.0, fa = -u, fb = 1.0 - u, fc = -u;
-                if (fa == 0.0) bb = ba;
-                bool done = (fa == 0.0) || (fb == 0.0);
-                int left = 1001;
-#pragma unroll 1
-                while (!done) {
-                    if (left-- == 0) { c_fail++; break; }
-                    const double prev_step = bb - ba;
-                    if (fabs(fc) < fabs(fb)) { ba = bb; bb = bc; bc = ba; fa = fb; fb = fc; fc = fa; }
-                    const double tol_act = 2 * EPS * fabs(bb);
-                    double new_step = (bc - bb) / 2;
-                    if (fabs(new_step) <= tol_act || fb == 0.0) break;
-                    if (fabs(prev_step) >= tol_act && fabs(fa) > fabs(fb)) {
-                        double pp, qq; const double cb = bc - bb;
-                        if (ba == bc) { const double t1 = fb / fa; pp = cb * t1; qq = 1.0 - t1; }
-                        else {
-                            qq = fa / fc; const double t1 = fb / fc, t2 = fb / fa;
-                            pp = t2 * (cb * qq * (qq - t1) - (bb - ba) * (t1 - 1.0));
-                            qq = (qq - 1.0) * (t1 - 1.0) * (t2 - 1.0);
-                        }
-                        if (pp > 0.0) qq = -qq; else pp = -pp;
-                        if (pp < (0.75 * cb * qq - fabs(tol_act * qq) / 2) && pp < fabs(prev_step * qq / 2)) new_step = pp / qq;
-                    }
-                    if (fabs(new_step) < tol_act) new_step = (new_step > 0.0) ? tol_act : -tol_act;
-                    ba = bb; fa = fb;
-                    bb += new_step;
-                    cplx_J(wk, w, sm.evals, sm.evi, n, T, bb, Sjj);
-                    double tmp = 0.0;
-#pragma unroll 1
-                    for (int q = 0; q < n; q++) tmp += sm.Q[k + q * n] * wk[q];
-                    fb = coef * tmp - u;
-                    c_evals++;
-                    if ((fb > 0 && fc > 0) || (fb < 0 && fc < 0)) { bc = ba; fc = fa; }
-                }
-                double jtime = bb;
-                int guard = 0;
-#pragma unroll 1
-                while (t + jtime >= y && guard++ < 2000) jtime = jtime / 2;
-                if (rec) count_transition(p, n, sm.Nacc, out_idx, j, k);
-                z[j] += jtime; t += jtime; j = k;
-                c_jumps++;
-            }
-            if (!MH || mh.chain_end<false>(j, sm.s, p.mhit, p, iter, rng.obs)) {
-                if (p.outB != nullptr) {
-                    p.outB[out_idx] = B;
-#pragma unroll 1
-                    for (int i = 0; i < n; i++) p.outz[out_idx * n + i] = z[i];
-                } else {
-                    atomicAdd(&sm.Bacc[B], 1u);
-                    const double zs = pht_u2d((uint64_t)(1023 + p.zbits) << 52);
-#pragma unroll 1
-                    for (int i = 0; i < n; i++) {
-                        const double v = z[i];
-                        if (v != 0.0) {
-                            if (!(v * zs < 4.0e18) || !(v * zs > -4.0e18)) atomicOr(&p.state->error, 2);
-                            pht_zfix_add(sm.zlo, sm.zhi, i, __double2ll_rn(v * zs));
-                        }
-                    }
-                }
-                c_paths++;
-                break;
-            }
-            rng.seek_sub(mh.chain, mh.off, p, iter);
-        }
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    block_flush<128>(p, n, sm.Nacc, sm.Bacc, sm.zlo, sm.zhi);
-    unsigned long long w_jumps = c_jumps, w_evals = c_evals, w_paths = c_paths, w_fail = c_fail;
-    for (int o = 16; o > 0; o >>= 1) {
-        w_jumps += __shfl_down_sync(FULL, w_jumps, o); w_evals += __shfl_down_sync(FULL, w_evals, o);
-        w_paths += __shfl_down_sync(FULL, w_paths, o); w_fail += __shfl_down_sync(FULL, w_fail, o);
-    }
-    if ((tid & 31) == 0) {
-        atomicAdd(&p.state->counters[PHT_CNT_JUMPS], w_jumps); atomicAdd(&p.state->counters[PHT_CNT_BRENT_EVALS], w_evals);
-        atomicAdd(&p.state->counters[PHT_CNT_PATHS], w_paths); atomicAdd(&p.state->counters[PHT_CNT_NONFINITE], w_fail);
-    }
-}
-
 static int dcs_threads(int n) { return n <= 16 ? 128 : 64; }
 
+/* the two instances (real spectrum: the reference's arithmetic; complex pairs: block formulas) share one grid size:
+ * the smaller of their occupancies (the CPLX body needs a few more registers) */
 template <int THREADS, bool MH>
 static cudaError_t dcs_occupancy(int n, int *per_sm) {
     const size_t smem = DcsSmem<THREADS>::bytes(n);
-    cudaError_t e = cudaFuncSetAttribute(k_dcs_sweep<THREADS, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_dcs_sweep<THREADS, MH>, THREADS, smem);
+    int a = 0, b = 0;
+    cudaError_t e = cudaFuncSetAttribute(k_dcs_sweep<THREADS, MH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dcs_sweep<THREADS, MH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_dcs_sweep<THREADS, MH, false>, THREADS, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_dcs_sweep<THREADS, MH, true>, THREADS, smem);
+    *per_sm = a < b ? a : b;
     return e;
 }
 int pht_dcs_grid_blocks(int device, int n, bool mh) {
@@ -611,19 +449,16 @@ int pht_dcs_grid_blocks(int device, int n, bool mh) {
     return per_sm * sms;
 }
 
-cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st, bool mh) {
-    if (dcs_threads(p.n) == 128) {
-        if (mh) k_dcs_sweep<128, true><<<grid_blocks, 128, DcsSmem<128>::bytes(p.n), st>>>(p);
-        else k_dcs_sweep<128, false><<<grid_blocks, 128, DcsSmem<128>::bytes(p.n), st>>>(p);
-    } else {
-        if (mh) k_dcs_sweep<64, true><<<grid_blocks, 64, DcsSmem<64>::bytes(p.n), st>>>(p);
-        else k_dcs_sweep<64, false><<<grid_blocks, 64, DcsSmem<64>::bytes(p.n), st>>>(p);
-    }
+template <int THREADS, bool MH>
+static cudaError_t dcs_launch_pair(const SweepParams &p, int grid_blocks, cudaStream_t st) {
+    /* the sweep's spectrum is known on the device only: exactly one of the two instances does the work, the other returns */
+    k_dcs_sweep<THREADS, MH, false><<<grid_blocks, THREADS, DcsSmem<THREADS>::bytes(p.n), st>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    /* the sweep's spectrum is known on the device only: exactly one of the two kernels does the work, the other returns */
-    const int cb = 148 * 4;
-    if (mh) k_dcs_cplx<true><<<cb, 128, DcsCplxSmem::bytes(p.n), st>>>(p);
-    else k_dcs_cplx<false><<<cb, 128, DcsCplxSmem::bytes(p.n), st>>>(p);
+    k_dcs_sweep<THREADS, MH, true><<<grid_blocks, THREADS, DcsSmem<THREADS>::bytes(p.n), st>>>(p);
     return cudaGetLastError();
+}
+cudaError_t pht_launch_dcs(const SweepParams &p, int grid_blocks, cudaStream_t st, bool mh) {
+    if (dcs_threads(p.n) == 128) return mh ? dcs_launch_pair<128, true>(p, grid_blocks, st) : dcs_launch_pair<128, false>(p, grid_blocks, st);
+    return mh ? dcs_launch_pair<64, true>(p, grid_blocks, st) : dcs_launch_pair<64, false>(p, grid_blocks, st);
 }

@@ -4,7 +4,7 @@ returns the real block form S = Q B Q^-1 (pht_eigen.h) and ECS evaluates exp(xS)
 reference to be bit-identical to here, so the checks are (a) the decomposition itself against numpy, on the device,
 and (b) tier 2: conditional E[N_ij | y], E[Z_i | y] and exit-state probabilities of the CUDA sampler against the
 analytic Hobolth-Jensen values, for exact and for right-censored observations (ECS) and for exact ones through DCS
-and the MH variants, whose DCS-family kernels switch to the block formulas of k_dcs_cplx on such a sweep."""
+and the MH variants, whose DCS-family kernels run their CPLX instance (block formulas in complex arithmetic) on such a sweep."""
 import numpy as np
 import pytest
 

@@ -8,7 +8,7 @@ method = sys.argv[1] if len(sys.argv) > 1 else "MHRS"
 l = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10 ** 6
 sweeps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 cid = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-wl = synth.config(cid, method, l=l)
+wl = synth.config(cid, "MHRS" if os.environ.get("GENERAL") else method, l=l)      # GENERAL=1: the unsymmetrised generator (complex spectra)
 eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method={"MHRS": 1, "ECS": 2, "DCS": 4}[method],
                 mhit=1, seed=1, use_graph=False, mhrs_cap=int(os.environ.get("CAP", "0")))
 eng.set_theta(wl.theta, 1)
