@@ -90,10 +90,10 @@ namespace cg = cooperative_groups;
 #define END_CAP 32u                 /* attempts a lane still tries once no observations are left */
 #endif
 #ifndef MHRS_REPLAY_MIN_BLOCKS
-#define MHRS_REPLAY_MIN_BLOCKS 3         /* replay kernel: 80 registers */
+#define MHRS_REPLAY_MIN_BLOCKS 4         /* replay kernel: 64 registers, 32 warps per SM (measured against 3 blocks at 80: 1.27 vs 1.42 ms per sweep of 1e7) */
 #endif
 #ifndef REPLAY_REFILL_MIN
-#define REPLAY_REFILL_MIN 8         /* idle lanes of a warp that trigger a refill from the record list */
+#define REPLAY_REFILL_MIN 16        /* idle lanes of a warp that trigger a refill from the record list */
 #endif
 #ifndef PREFETCH_MIN
 #define PREFETCH_MIN 8              /* empty prefetch slots in a warp that trigger a refill */
