@@ -329,7 +329,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
              * 7.45 / 8.16 / 9.02; 1e7: 13.9 / 15.5 / 17.3.  Rule: cap = 8 x observations per resident lane, as a power of
              * two between 32 and 256.  Results do not depend on it. */
             const double per_lane = (double)l_local / ((double)e->grid_blocks * 256.0);
-            int cap = 32; while (cap < 256 && (double)(cap * 2) <= 8.0 * per_lane) cap *= 2;
+            int cap = 32; while (cap < 1024 && (double)(cap * 2) <= 8.0 * per_lane) cap *= 2;
             e->cfg.mhrs_cap = cap;
         }
     }

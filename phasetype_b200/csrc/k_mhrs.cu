@@ -153,6 +153,7 @@ struct MhrsSmem {
     float A[R + 3];                             /* -ln2 * scale[k] / smax (entry n = 0: absorbed, the clock stands) */
     unsigned int paths_done;                    /* replays finished by this block */
     unsigned int scan[MHRS_WARPS + 1];          /* block-level compaction of the global list */
+    uint32_t pctr[MHRS_WARPS];                  /* tail: next attempt of each warp's current pool */
     /* per-lane state that is touched once or twice per observation lives here, not in registers: the prefetched
      * next observation and the MH bookkeeping */
     float pf_yf[MHRS_THREADS]; uint32_t pf_og[MHRS_THREADS], pf_pos[MHRS_THREADS];
@@ -513,24 +514,40 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
     const uint32_t W = tv.global ? p.obs_world : 1u;
     const uint32_t Pl = (tv.P + W - 1u) / W;
     const unsigned long long total_units = (unsigned long long)Pl * tv.K;
-    /* per lane: the batch [f.a, a_end) of consecutive attempts of observation my_item it is working through */
+    /* per lane: the attempt f.a of observation my_item it is walking.  Attempts are handed out ONE at a time from the
+     * warp's current pool through a counter in shared memory: a lane whose attempt has failed takes the next one inside
+     * its own branch (one ATOMS), so the warp-wide hand-out code -- which with whole-warp ballots ran on almost every
+     * iteration, some lane fails in most of them -- is left for the moment a pool runs out. */
     Fast f; fast_begin(f, 0u, n);
     ObsF mo; obs_set(mo, 0.0f, 0u, false);
-    uint32_t my_item = 0xFFFFFFFFu, a_end = 0u; bool active = false;
+    uint32_t my_item = 0xFFFFFFFFu; bool active = false;
     unsigned steps = 0;
-    /* warp-uniform: the units this warp holds, and the pool being handed out */
+    uint32_t *ctr = &sm.pctr[threadIdx.x >> 5];
+    if (lane == 0) *ctr = 0u;
+    __syncwarp();
+    /* warp-uniform: the units this warp holds, and the pool being handed out ([*ctr, pool_end) of observation `item`) */
     unsigned long long u_next = 0, u_end = 0, last_base = 0, remaining = total_units;
     bool out_of_units = false, finished = false;
-    uint32_t item = 0, og = 0, a_first = 0, pool_next = 0, pool_end = 0; float yf = 0.0f; bool cens = false, first_off = false;
+    uint32_t item = 0, og = 0, a_first = 0, pool_end = 0; float yf = 0.0f; bool cens = false, first_off = false;
     while (!finished) {
         /* ---- the search loop proper: no calls in here (the exact walker is asked from outside, see below) */
         bool want_exact = false, exact_off = false, survived = false; int kend = 0;
+        /* take the pool's next attempt (any lane, any time) */
+#define TAIL_GRAB() do { \
+            const uint32_t na_ = atomicAdd(ctr, 1u); \
+            if (na_ < pool_end) { \
+                my_item = item; obs_set(mo, yf, og, cens); fast_begin(f, na_, n); \
+                /* the attempt that starts one draw into its sub-stream (after an MH accept test) is the exact walker's */ \
+                if (first_off && na_ == a_first) { want_exact = true; exact_off = true; active = false; } else active = true; \
+            } else active = false; \
+        } while (0)
         for (;;) {
-            unsigned idle = __ballot_sync(FULL, !active);
+            const unsigned idle = __ballot_sync(FULL, !active);
             if (idle) {
-                if (pool_next >= pool_end && !out_of_units) {
+                uint32_t cur = *reinterpret_cast<volatile uint32_t *>(ctr);
+                if (cur >= pool_end && !out_of_units) {
                     /* take the next pool (skipping pools that an earlier survivor made moot) */
-                    bool have = false;
+                    bool have = false; uint32_t pstart = 0u;
                     while (!have) {
                         if (u_next >= u_end) {
                             remaining = total_units > last_base ? total_units - last_base : 0ull;
@@ -551,39 +568,26 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                         const uint32_t within = (uint32_t)(u_next - chunk * TAIL_CH), len = (uint32_t)(stop - u_next);
                         u_next = stop;
                         if (o >= tv.P) continue;
-                        item = tv.pend[o];
-                        const TailItem it = tv.items[item];
+                        const uint32_t it_idx = tv.pend[o];
+                        const TailItem it = tv.items[it_idx];
                         if (it.flags & TI_FIN) continue;
-                        a_first = it.a; first_off = (it.flags & TI_OFF) != 0u;
-                        pool_next = it.a + q * TAIL_CH + within;
-                        pool_end = pool_next + len;
-                        if ((__ldcg(&tv.found[item]) >> 8) >= (unsigned long long)pool_next) {
+                        pstart = it.a + q * TAIL_CH + within;
+                        if ((__ldcg(&tv.found[it_idx]) >> 8) >= (unsigned long long)pstart) {
                             have = true;
+                            item = it_idx; a_first = it.a; first_off = (it.flags & TI_OFF) != 0u;
+                            pool_end = pstart + len;
                             yf = (float)(it.y * sm.inv_smax); cens = (it.flags & TI_CENS) != 0u; og = it.og;
-                        } else pool_end = pool_next;
+                        }
+                    }
+                    if (have) {
+                        __syncwarp();
+                        if (lane == 0) *ctr = pstart;
+                        __syncwarp();
+                        cur = pstart;
                     }
                 }
-                if (idle == FULL && pool_next >= pool_end) { finished = true; break; }      /* nothing in flight, nothing left to hand out */
-                if (pool_next < pool_end) {
-                    /* idle lanes take a batch of consecutive attempts each (ballot only, no memory traffic): a small pool
-                     * is spread over them, a large one is handed out TAIL_BATCH attempts at a time */
-                    const uint32_t avail = pool_end - pool_next, nidle = __popc(idle);
-                    /* (towards the end of the round the batches shrink to single attempts, so the round does not end on
-                     * one lane working through a long batch while the grid waits) */
-                    const unsigned long long fair = remaining / (64ull * (unsigned long long)nwarps);
-                    const uint32_t bmax = fair >= TAIL_BATCH ? TAIL_BATCH : (fair < 1ull ? 1u : (uint32_t)fair);
-                    uint32_t bsz = (avail + nidle - 1u) / nidle; bsz = bsz > bmax ? bmax : bsz;
-                    const uint32_t a0 = pool_next + (uint32_t)__popc(idle & ((1u << lane) - 1u)) * bsz;
-                    if (!active && a0 < pool_end) {
-                        a_end = a0 + bsz < pool_end ? a0 + bsz : pool_end;
-                        my_item = item; obs_set(mo, yf, og, cens);
-                        fast_begin(f, a0, n);
-                        /* the attempt that starts one draw into its sub-stream (after an MH accept test) is the exact walker's */
-                        if (first_off && a0 == a_first) { want_exact = true; exact_off = true; } else active = true;
-                    }
-                    const uint32_t take = nidle * bsz;
-                    pool_next += take < avail ? take : avail;
-                }
+                if (cur >= pool_end) { if (idle == FULL) { finished = true; break; } }      /* nothing in flight, nothing left to hand out */
+                else if (!active) TAIL_GRAB();
             }
             /* Every FOUND_PERIOD steps, look whether someone (another warp, another GPU) has found a surviving attempt
              * of the pool's observation: everything above it is moot. */
@@ -593,35 +597,29 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
                 fw = __shfl_sync(FULL, fw, 0);
                 if (fw != FOUND_NONE) {
                     const uint32_t fa = (uint32_t)(fw >> 8);
-                    if (pool_next < pool_end && fa < pool_end) { pool_end = pool_end < fa ? pool_end : fa; pool_next = pool_next < pool_end ? pool_next : pool_end; }
-                    if (my_item == item) { a_end = a_end < fa ? a_end : fa; if (active && f.a > fa) { active = false; c_jumps += f.b; } }
+                    pool_end = pool_end < fa ? pool_end : fa;
+                    if (my_item == item && active && f.a > fa) { active = false; c_jumps += f.b; }
                 }
             }
-            __syncwarp();           /* lanes that have just drawn a batch step together with the rest */
+            __syncwarp();           /* lanes that have just taken an attempt step together with the rest */
             if (active) {
                 bool fail, surv, amb; int k;
                 fast_step(f, mo, p, sm, iter, n, fail, surv, amb, k);
                 if (surv && !((smask >> k) & 1u)) { surv = false; fail = true; }     /* alive at y in a state that cannot exit: failed */
                 /* (jump-steps are counted when an attempt ends: f.b of them) */
-                if (fail) {
-                    c_attempts++; c_jumps += f.b;
-                    const uint32_t na = f.a + 1u;
-                    if (na < a_end) fast_begin(f, na, n); else active = false;
-                } else if (surv) { c_attempts++; c_jumps += f.b; survived = true; kend = k; active = false; }
+                if (fail) { c_attempts++; c_jumps += f.b; TAIL_GRAB(); }
+                else if (surv) { c_attempts++; c_jumps += f.b; survived = true; kend = k; active = false; }
                 else if (amb) { c_jumps += f.b; want_exact = true; active = false; }
             }
             if (__any_sync(FULL, survived || want_exact)) break;
         }
+#undef TAIL_GRAB
         if (finished) break;
         /* ---- attempts the filter could not decide (or that start off the block boundary): the exact walker */
         if (want_exact) {
             const uint32_t res = exact_attempt(f.a, exact_off, tv.items[my_item].y, mo.cens, mo.og, p, sm, iter, n, smask);
             c_jumps += res >> 16; c_attempts++;
             survived = res & 1u; kend = (int)((res >> 8) & 0xffu);
-            if (!survived) {
-                const uint32_t na = f.a + 1u;
-                if (na < a_end) { fast_begin(f, na, n); active = true; }
-            }
         }
         /* ---- every survivor competes for "lowest surviving attempt" of its observation (on every rank in a global
          * round); the first one in the warp also calls off the later attempts of the same observation in flight here */
@@ -638,11 +636,8 @@ __device__ __forceinline__ void tail_search(const TailView &tv, const SweepParam
         if (smk) {
             const int src = __ffs(smk) - 1;
             const uint32_t s_item = __shfl_sync(FULL, my_item, src), s_a = __shfl_sync(FULL, f.a, src);
-            if (my_item == s_item) { a_end = a_end < s_a ? a_end : s_a; if (active && f.a > s_a) { active = false; c_jumps += f.b; } }
-            if (s_item == item && pool_next < pool_end) {
-                pool_end = pool_end < s_a ? pool_end : s_a;
-                pool_next = pool_next < pool_end ? pool_next : pool_end;
-            }
+            if (my_item == s_item && active && f.a > s_a) { active = false; c_jumps += f.b; }
+            if (s_item == item) pool_end = pool_end < s_a ? pool_end : s_a;
         }
         __syncwarp();
     }
