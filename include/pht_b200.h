@@ -165,7 +165,8 @@ enum { PHT_CNT_PATHS = 0, PHT_CNT_ATTEMPTS, PHT_CNT_JUMPS, PHT_CNT_DENS_EVALS, P
 int pht_engine_counters(pht_engine *e, unsigned long long *out);
 /* MHRS tail, per round number (accumulated since creation): ns searching, ns at the barrier after the search, ns
  * advancing, sum of pending observations, sum of attempts offered per observation,
- * attempts actually run in the round (all warps); out: PHT_ROUND_TRACE x 6 words */
+ * attempts actually run in the round (all warps), attempts the sequential sampler needs of it, jump-steps run;
+ * out: PHT_ROUND_TRACE x 8 words */
 #define PHT_ROUND_TRACE 48
 int pht_engine_round_trace(pht_engine *e, unsigned long long *out);
 

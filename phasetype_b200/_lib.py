@@ -213,10 +213,11 @@ class Engine:
         return out
 
     def round_trace(self):
-        """(48, 6) array: per tail round number, ns search / ns barrier / ns advance / sum of pending / sum of K / attempts run."""
-        t = np.zeros(48 * 6, dtype=np.uint64)
+        """(48, 8) array: per tail round number, ns search / ns barrier / ns advance / sum of pending / sum of K / attempts run /
+        attempts the sequential sampler needs of this round / jump-steps run."""
+        t = np.zeros(48 * 8, dtype=np.uint64)
         _check(lib().pht_engine_round_trace(self._h, t))
-        return t.reshape(48, 6)
+        return t.reshape(48, 8)
 
     def counters(self):
         c = np.zeros(N_CNT, dtype=np.uint64)

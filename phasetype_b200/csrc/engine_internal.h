@@ -115,7 +115,7 @@ struct DevState {
     unsigned long long counters[PHT_CNT_COUNT];
     /* measurement aid: per tail round (index = round number, accumulated over sweeps) the device-timer ns block 0 spent
      * searching / waiting at the barrier after the search / advancing, and the sum of pending items and of K */
-    unsigned long long round_trace[PHT_ROUND_TRACE][6];
+    unsigned long long round_trace[PHT_ROUND_TRACE][8];
 };
 
 struct SweepParams {

@@ -918,13 +918,16 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
         else { tv.items = p.xw->gitems[sp]; tv.pend = gl_cur ? p.glist + PHT_MAX_WORLD * PHT_GCAP : p.glist; tv.found = p.xw->gfound[par]; tv.P = Pg; }
         tv.K = K; tv.global = global; tv.parity = par;
         const unsigned long long tr0 = timekeeper ? gtimer() : 0ull;
-        const unsigned att0 = c_attempts;
+        const unsigned att0 = c_attempts, jmp0 = c_jumps;
         tail_search(tv, p, sm, iter, n, smask, nwarps, c_jumps, c_attempts);
         const unsigned long long tr1 = timekeeper ? gtimer() : 0ull;
         if (rounds < PHT_ROUND_TRACE) {          /* attempts this round ran, over the whole grid (measurement aid) */
             unsigned d = c_attempts - att0;
             for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
             if ((tid & 31) == 0 && d) atomicAdd(&p.state->round_trace[rounds][5], (unsigned long long)d);
+            unsigned dj = c_jumps - jmp0;
+            for (int o = 16; o > 0; o >>= 1) dj += __shfl_xor_sync(0xffffffffu, dj, o);
+            if ((tid & 31) == 0 && dj) atomicAdd(&p.state->round_trace[rounds][7], (unsigned long long)dj);
         }
         if (global) peer_barrier(grid, p, ++epoch); else grid.sync();
         const unsigned long long tr2 = timekeeper ? gtimer() : 0ull;
@@ -935,6 +938,10 @@ __global__ void __launch_bounds__(MHRS_THREADS, MHRS_TAIL_MIN_BLOCKS) k_mhrs_tai
             TailItem it = tv.items[item];
             if (it.flags & TI_FIN) continue;
             bool failed;
+            if (rounds < PHT_ROUND_TRACE && (!global || it.owner == me)) {      /* attempts the sequential sampler runs of this round's offer */
+                const unsigned long long fw = tv.found[item];
+                atomicAdd(&p.state->round_trace[rounds][6], fw == FOUND_NONE ? (unsigned long long)K : (unsigned long long)((uint32_t)(fw >> 8) - it.a + 1u));
+            }
             const int st = tail_advance(it, tv.found[item], K, p, s_model, iter, failed);
             tv.found[item] = FOUND_NONE;
             if (st != 0 && global) it.flags |= TI_FIN;

@@ -19,4 +19,4 @@ if os.environ.get("TRACE"):
     tr = eng.round_trace()
     for r in range(48):
         if tr[r, 4]:
-            print("round %2d: search %8.1f us  barrier %7.1f us  advance %7.1f us  P %9.1f  K %10.0f  attempts %11.0f  (%.1f per us)" % (r, tr[r, 0] / 1e3 / sweeps, tr[r, 1] / 1e3 / sweeps, tr[r, 2] / 1e3 / sweeps, tr[r, 3] / sweeps, tr[r, 4] / sweeps, tr[r, 5] / sweeps, tr[r, 5] / max(1.0, tr[r, 0] / 1e3)))
+            print("round %2d: search %8.1f us  barrier %7.1f us  advance %7.1f us  P %9.1f  K %10.0f  attempts %11.0f  (%.1f per us)  needed %11.0f  jumps/attempt %.1f" % (r, tr[r, 0] / 1e3 / sweeps, tr[r, 1] / 1e3 / sweeps, tr[r, 2] / 1e3 / sweeps, tr[r, 3] / sweeps, tr[r, 4] / sweeps, tr[r, 5] / sweeps, tr[r, 5] / max(1.0, tr[r, 0] / 1e3), tr[r, 6] / sweeps, tr[r, 7] / max(1.0, tr[r, 5])))
