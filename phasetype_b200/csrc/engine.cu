@@ -14,8 +14,10 @@
 #include <cstdarg>
 #include <cmath>
 #include <vector>
+#include <thread>
 #include <dlfcn.h>
 #include <unistd.h>
+#include <time.h>
 #include "engine_internal.h"
 
 /* ---------------------------------------------------------------- errors */
@@ -239,6 +241,15 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
 
+    /* PHT_B200_TIMING=1: stage times of the set-up on stderr (tools/e2e_breakdown.py) */
+    const bool timing = getenv("PHT_B200_TIMING") != nullptr;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto stage = [&](const char *what) {
+        if (!timing) return;
+        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[pht_engine_create] %-28s %8.3f ms\n", what, (t.tv_sec - ts0.tv_sec) * 1e3 + (t.tv_nsec - ts0.tv_nsec) * 1e-6);
+        ts0 = t;
+    };
     pht_engine *e = new pht_engine();
     e->cfg = *cfg;
     e->T.assign(cfg->T, cfg->T + n1 * n1); e->C.assign(cfg->C, cfg->C + n1 * n1);
@@ -256,13 +267,23 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     const size_t ln = (size_t)(l_local > 0 ? l_local : 1);
     CUE(cudaMalloc(&e->d_y, ln * sizeof(double)));
     CUE(cudaMalloc(&e->d_cens, ln));
+    stage("stream, events, 2 mallocs");
     if (l_local > 0) {
-        CUE(cudaMemcpyAsync(e->d_y, y_local, (size_t)l_local * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        /* (a pageable staging vector: pinning 10 MB per call cost more than the copy it would speed up) */
+        /* the int32 flags are repacked to bytes by two helper threads while this one feeds y to the copy engine (a copy
+         * from pageable memory occupies the calling thread): 7 ms each at 1e7 observations, now side by side.
+         * (a pageable staging vector: pinning 10 MB per call cost more than the copy it would speed up) */
         std::vector<uint8_t> hc((size_t)l_local);
-        for (long i = 0; i < l_local; i++) hc[i] = cens_local[i] != 0;
+        uint8_t *hcp = hc.data();
+        const long half = l_local / 2;
+        std::thread r0([=] { for (long i = 0; i < half; i++) hcp[i] = cens_local[i] != 0; });
+        std::thread r1([=] { for (long i = half; i < l_local; i++) hcp[i] = cens_local[i] != 0; });
+        const cudaError_t ey = cudaMemcpyAsync(e->d_y, y_local, (size_t)l_local * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+        r0.join(); r1.join();
+        CUE(ey);
+        stage("y upload | flag repack");
         CUE(cudaMemcpyAsync(e->d_cens, hc.data(), (size_t)l_local, cudaMemcpyHostToDevice, e->stream));
         CUE(cudaStreamSynchronize(e->stream));
+        stage("flag upload + sync");
         if (method_of(e->cfg) == PHT_METHOD_ECS) e->h_cens.swap(hc);
     }
 
@@ -285,6 +306,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     CUE(cudaMalloc(&e->d_cell_i, sizeof(int) * cell_i.size())); CUE(cudaMemcpy(e->d_cell_i, cell_i.data(), sizeof(int) * cell_i.size(), cudaMemcpyHostToDevice));
     CUE(cudaMalloc(&e->d_cell_j, sizeof(int) * cell_j.size())); CUE(cudaMemcpy(e->d_cell_j, cell_j.data(), sizeof(int) * cell_j.size(), cudaMemcpyHostToDevice));
 
+    stage("model buffers");
     if (cfg->world > 1) {
         /* this rank's exchange window: all-reduce slots (every method) and the global MHRS tail (flags 0, found words NONE) */
         CUE(cudaMalloc(&e->d_xw, sizeof(XchgWindow)));
@@ -307,15 +329,19 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         e->d_pend0 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
         e->d_pend1 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
         e->d_done = reinterpret_cast<uint32_t *>(arena);
+        stage("tail arena");
         /* the production layout: observations by decreasing y (k_sort.cu); parity hooks keep using the upload order */
         if (l_local > 1 && !getenv("PHT_B200_NO_SORT")) {
             CUE(cudaMalloc(&e->d_ys, ln * sizeof(double))); CUE(cudaMalloc(&e->d_cs, ln)); CUE(cudaMalloc(&e->d_perm, ln * sizeof(uint32_t)));
+            stage("sorted-layout mallocs");
             CUE(pht_sort_by_y_desc(e->d_y, e->d_cens, l_local, e->d_ys, e->d_cs, e->d_perm, e->stream));
+            stage("sort by y");
         }
         /* global tail: the canonical list */
         if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
         if (cfg->world > 1) CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
         CUE(cudaMalloc(&e->d_recs, ln * sizeof(uint4)));
+        stage("record list");
         if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks, &e->replay_blocks) != 0) e->grid_blocks = 0;
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
         if (auto_cap) {
@@ -358,6 +384,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     CUE(cudaMemcpyAsync(e->d_state, &st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
     CUE(cudaStreamSynchronize(e->stream));
 #undef CUE
+    stage("occupancy queries, state");
     *out = e;
     return 0;
 }

@@ -18,3 +18,7 @@ for rep in range(3):
     r = pb.ljma_gibbs(21, 1, 1, wl.n, wl.m, wl.nu, wl.zeta, wl.T, wl.C, wl.y, wl.censored, wl.theta, silent=True)
     t4 = time.perf_counter()
     print("rep %d: create %.3f s, 20 sweeps %.3f s, destroy %.3f s | LJMA_Gibbs(it=21) %.3f s" % (rep, t1 - t0, t2 - t1, t3 - t2, t4 - t3))
+os.environ["PHT_B200_TIMING"] = "1"
+t0 = time.perf_counter()
+r = pb.ljma_gibbs(21, 1, 1, wl.n, wl.m, wl.nu, wl.zeta, wl.T, wl.C, wl.y, wl.censored, wl.theta, silent=True)
+print("timed call: %.3f s" % (time.perf_counter() - t0))
