@@ -488,8 +488,11 @@ def main():
             # 8-GPU job: profiles/r2_configs.md)
             if args.config == 3:
                 oc = {}
-                for cid, m2, l2 in ((2, "MHRS", 10 ** 6), (2, "ECS", 10 ** 6), (2, "DCS", 10 ** 6), (4, "ECS", 10 ** 7), (5, "MHRS", 2500000)):
-                    wc = synth.config(cid, m2, l=l2)
+                # (C5 under ECS / DCS: the general 32-phase generator -- complex spectra, block formulas -- on a 10^5-observation
+                # sample: a sweep of the stated 10^8 observations is a minute of one GPU under these samplers)
+                for cid, m2, l2 in ((2, "MHRS", 10 ** 6), (2, "ECS", 10 ** 6), (2, "DCS", 10 ** 6), (4, "ECS", 10 ** 7), (5, "MHRS", 2500000),
+                                    (5, "ECS", 10 ** 5), (5, "DCS", 10 ** 5)):
+                    wc = synth.config(cid, "MHRS" if cid == 5 else m2, l=l2)
                     r2 = R.timed(wc, m2, np.ascontiguousarray(wc.y), np.ascontiguousarray(wc.censored), float(wc.y.sum()), 5, 3)
                     rf = R.roofline(wc, m2, r2, wc.l, fma_rate)
                     oc["C%d:%s" % (cid, m2)] = {"value": wc.l * 5 / (r2["total_ms"] * 1e-3), "unit": "paths/s", "ms_per_step": r2["total_ms"] / 5,

@@ -78,12 +78,15 @@ typedef struct pht_config {
     int rank, world;      /* this engine holds observations rank, rank+world, ... of the global set */
     int zbits;            /* fractional bits of the fixed-point sojourn totals (pht_choose_zbits) */
     int mhrs_cap;         /* attempts a lane tries before handing an observation to the cooperative tail; 0 = default
-                             (256 for large shards, down to 32 for small ones: 8 x observations per resident lane) */
+                             (8 x observations per resident lane, as a power of two between 32 and 1024) */
     int use_graph;        /* capture the sweep in a CUDA graph (1) or launch kernels directly (0) */
 } pht_config;
 
 const char *pht_last_error(void);
 int pht_device_count(void);
+/* The large per-call device buffers come from the devices' stream-ordered memory pools and stay cached there after
+ * a call (the next call reuses them; PHT_B200_NO_POOL=1 switches this off).  This hands the cached memory back. */
+int pht_release_device_memory(void);
 
 /* 62 - ceil(log2(16 * sum_y)): every per-state total fits an int64 with headroom */
 int pht_choose_zbits(double sum_y_global);

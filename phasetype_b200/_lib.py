@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PHT_B200_LIB") or os.path.join(HERE, "libpht_b200.so"
 
 # every symbol include/pht_b200.h declares (tests check the export list against the header)
 SYMBOLS = [
-    "LJMA_Gibbs", "pht_last_error", "pht_device_count", "pht_choose_zbits", "pht_engine_create",
+    "LJMA_Gibbs", "pht_last_error", "pht_device_count", "pht_release_device_memory", "pht_choose_zbits", "pht_engine_create",
     "pht_engine_destroy", "pht_comm_unique_id", "pht_engine_comm_init", "pht_engine_set_theta",
     "pht_engine_get_theta", "pht_engine_run", "pht_engine_enqueue", "pht_engine_sync", "pht_engine_last_ms",
     "pht_engine_sweep_stats", "pht_engine_paths", "pht_engine_set_spectral", "pht_engine_get_model",

@@ -135,6 +135,42 @@ static UpdateParams update_params(pht_engine *e, double *res, int res_rows) {
     return u;
 }
 
+/* ---- device memory for the large per-call buffers (observations, sorted layout, records, tail lists): stream-ordered
+ * allocations from the device's default pool, whose release threshold is raised so that the memory of a finished call
+ * is reused by the next one.  Two reasons: a call allocates ~0.5 GB, and once peer access is on (several GPUs in one
+ * process) every plain cudaMalloc/cudaFree also maps/unmaps the block on the peers -- 100..700 ms per call measured on
+ * 2 GPUs.  Pool memory is not peer-mapped; the exchange window, which must be, stays a plain allocation.
+ * PHT_B200_NO_POOL=1 goes back to cudaMalloc/cudaFree; pht_release_device_memory() hands the cached memory back. */
+static bool pool_off() { static const bool off = getenv("PHT_B200_NO_POOL") != nullptr; return off; }
+cudaError_t pht_dev_alloc(void **p, size_t bytes, cudaStream_t st) {
+    if (pool_off()) return cudaMalloc(p, bytes);
+    return cudaMallocAsync(p, bytes, st);
+}
+cudaError_t pht_dev_free(void *p, cudaStream_t st) {
+    if (!p) return cudaSuccess;
+    if (pool_off()) return cudaFree(p);
+    return cudaFreeAsync(p, st);
+}
+static void pool_keep(int dev) {
+    cudaMemPool_t pool;
+    if (!pool_off() && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+}
+extern "C" int pht_release_device_memory(void) {
+    int ndev = 0, cur = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaGetDevice(&cur);
+    for (int d = 0; d < ndev; d++) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) { cudaSetDevice(d); cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
+    }
+    cudaSetDevice(cur); cudaGetLastError();
+    return 0;
+}
+
 static int method_of(const pht_config &c) {       /* dispatch priority of src/PHT_MCMC_Aslett.c:325-337 */
     if (c.method & PHT_METHOD_MHRS) return PHT_METHOD_MHRS;
     if (c.method & PHT_METHOD_DCS) return PHT_METHOD_DCS;
@@ -209,8 +245,11 @@ extern "C" void pht_engine_destroy(pht_engine *e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (void *q : e->ipc_opened) cudaIpcCloseMemHandle(q);
-    void *bufs[] = { e->d_recs, e->d_ys, e->d_cs, e->d_perm, e->d_glist, e->d_xw, e->d_y, e->d_cens, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_beta, e->d_pires, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_res, e->d_inject, e->d_idx_exact, e->d_idx_cens, e->d_flush };
+    void *big[] = { e->d_recs, e->d_ys, e->d_cs, e->d_perm, e->d_y, e->d_cens, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_idx_exact, e->d_idx_cens };
+    for (void *b : big) pht_dev_free(b, e->stream);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void *bufs[] = { e->d_glist, e->d_xw, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
+                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_beta, e->d_pires, e->d_res, e->d_inject, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -265,8 +304,9 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
 
     /* observations: y as is, censoring flags repacked int32 -> uint8 (9 B per path in HBM) */
     const size_t ln = (size_t)(l_local > 0 ? l_local : 1);
-    CUE(cudaMalloc(&e->d_y, ln * sizeof(double)));
-    CUE(cudaMalloc(&e->d_cens, ln));
+    pool_keep(cfg->device);
+    CUE(pht_dev_alloc((void **)&e->d_y, ln * sizeof(double), e->stream));
+    CUE(pht_dev_alloc((void **)&e->d_cens, ln, e->stream));
     stage("stream, events, 2 mallocs");
     if (l_local > 0) {
         /* the int32 flags are repacked to bytes by two helper threads while this one feeds y to the copy engine (a copy
@@ -323,7 +363,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         if (const char *ev = getenv("PHT_B200_TAIL_SLOTS")) { const long v = atol(ev); if (v >= 1 && (size_t)v < slots) slots = (size_t)v; }
         e->item_cap = (uint32_t)slots;
         unsigned char *arena = nullptr;
-        CUE(cudaMalloc(&arena, slots * (sizeof(TailItem) + sizeof(unsigned long long) + 3 * sizeof(uint32_t))));
+        CUE(pht_dev_alloc((void **)&arena, slots * (sizeof(TailItem) + sizeof(unsigned long long) + 3 * sizeof(uint32_t)), e->stream));
         e->d_items = reinterpret_cast<TailItem *>(arena); arena += slots * sizeof(TailItem);
         e->d_found = reinterpret_cast<unsigned long long *>(arena); arena += slots * sizeof(unsigned long long);
         e->d_pend0 = reinterpret_cast<uint32_t *>(arena); arena += slots * sizeof(uint32_t);
@@ -332,7 +372,8 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         stage("tail arena");
         /* the production layout: observations by decreasing y (k_sort.cu); parity hooks keep using the upload order */
         if (l_local > 1 && !getenv("PHT_B200_NO_SORT")) {
-            CUE(cudaMalloc(&e->d_ys, ln * sizeof(double))); CUE(cudaMalloc(&e->d_cs, ln)); CUE(cudaMalloc(&e->d_perm, ln * sizeof(uint32_t)));
+            CUE(pht_dev_alloc((void **)&e->d_ys, ln * sizeof(double), e->stream)); CUE(pht_dev_alloc((void **)&e->d_cs, ln, e->stream));
+            CUE(pht_dev_alloc((void **)&e->d_perm, ln * sizeof(uint32_t), e->stream));
             stage("sorted-layout mallocs");
             CUE(pht_sort_by_y_desc(e->d_y, e->d_cens, l_local, e->d_ys, e->d_cs, e->d_perm, e->stream));
             stage("sort by y");
@@ -340,7 +381,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         /* global tail: the canonical list */
         if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
         if (cfg->world > 1) CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
-        CUE(cudaMalloc(&e->d_recs, ln * sizeof(uint4)));
+        CUE(pht_dev_alloc((void **)&e->d_recs, ln * sizeof(uint4), e->stream));
         stage("record list");
         if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks, &e->replay_blocks) != 0) e->grid_blocks = 0;
         if (e->grid_blocks <= 0) { fail("MHRS kernel does not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
@@ -363,9 +404,10 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         std::vector<uint32_t> ie, ic;
         for (long i = 0; i < l_local; i++) (e->h_cens[i] ? ic : ie).push_back((uint32_t)i);
         e->n_exact = ie.size(); e->n_cens = ic.size();
-        CUE(cudaMalloc(&e->d_idx_exact, sizeof(uint32_t) * (ie.size() + 1))); CUE(cudaMalloc(&e->d_idx_cens, sizeof(uint32_t) * (ic.size() + 1)));
-        if (!ie.empty()) CUE(cudaMemcpy(e->d_idx_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice));
-        if (!ic.empty()) CUE(cudaMemcpy(e->d_idx_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice));
+        CUE(pht_dev_alloc((void **)&e->d_idx_exact, sizeof(uint32_t) * (ie.size() + 1), e->stream)); CUE(pht_dev_alloc((void **)&e->d_idx_cens, sizeof(uint32_t) * (ic.size() + 1), e->stream));
+        if (!ie.empty()) CUE(cudaMemcpyAsync(e->d_idx_exact, ie.data(), sizeof(uint32_t) * ie.size(), cudaMemcpyHostToDevice, e->stream));
+        if (!ic.empty()) CUE(cudaMemcpyAsync(e->d_idx_cens, ic.data(), sizeof(uint32_t) * ic.size(), cudaMemcpyHostToDevice, e->stream));
+        CUE(cudaStreamSynchronize(e->stream));
         e->grid_blocks = pht_ecs_grid_blocks(cfg->device, n);
         if (e->grid_blocks <= 0) { fail("ECS kernels do not fit on the device: %s", cudaGetErrorString(cudaGetLastError())); pht_engine_destroy(e); return -1; }
     }

@@ -176,6 +176,9 @@ int pht_mhs_aslett_grid_blocks(int device, int n);
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st);
 int pht_mhrs_grid_blocks(int device, int n, int *lane_blocks, int *tail_blocks, int *replay_blocks);
 size_t pht_mhrs_smem_bytes(int n);
+/* large per-call buffers: stream-ordered pool allocations, cached across calls (engine.cu) */
+cudaError_t pht_dev_alloc(void **p, size_t bytes, cudaStream_t st);
+cudaError_t pht_dev_free(void *p, cudaStream_t st);
 cudaError_t pht_sort_by_y_desc(const double *y, const uint8_t *cens, long l, double *ys, uint8_t *cs, uint32_t *perm, cudaStream_t st);
 
 #endif

@@ -23,6 +23,7 @@
 #include <string.h>
 #include <stdint.h>
 #include <pthread.h>
+#include <time.h>
 #include "../../include/pht_b200.h"
 #include "pht_philox.h"
 
@@ -70,6 +71,7 @@ typedef struct {
     char err[512];
     pthread_mutex_t err_lock;
     int devices[MAX_GPUS];
+    double *ys[MAX_GPUS]; int *cs[MAX_GPUS]; int ys_ok;       /* the shards, dealt out by the rank threads together */
     /* inference of the start distribution (PHT_B200_BETA): prior, initial value, and the draws (IT x n, row-major) */
     int n; const double *beta, *pi0; double *pi_chain;
 } shared_t;
@@ -83,25 +85,37 @@ static void set_error(shared_t *sh, int rank, const char *msg) {
     pthread_mutex_unlock(&sh->err_lock);
 }
 
+static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+#define STAGE(what) do { if (timing) { const double t_ = now_ms(); fprintf(stderr, "[LJMA_Gibbs rank %d] %-24s %8.3f ms\n", rank, what, t_ - t_stage); t_stage = t_; } } while (0)
+
 /* One rank = one device.  Every collective step is bracketed by the thread barrier, and a rank that has failed keeps
  * walking through the barriers without touching its engine, so nobody waits for it in vain. */
 static void *rank_main(void *argp) {
     rank_arg *ra = (rank_arg *)argp; shared_t *sh = ra->sh; const int rank = ra->rank, world = sh->world;
     pht_engine *eng = NULL;
+    const int timing = getenv("PHT_B200_TIMING") != NULL && (rank == 0 || rank == world - 1);
+    double t_stage = now_ms();
     /* this rank's shard: observations rank, rank + world, ... */
     const long l_local = sh->l > rank ? (sh->l - rank + world - 1) / world : 0;
-    double *ys = NULL; int *cs = NULL;
     const double *yl = sh->y; const int *cl = sh->censored;
     if (world > 1) {
-        ys = (double *)malloc(sizeof(double) * (size_t)(l_local > 0 ? l_local : 1));
-        cs = (int *)malloc(sizeof(int) * (size_t)(l_local > 0 ? l_local : 1));
-        if (!ys || !cs) set_error(sh, rank, "out of memory");
-        else for (long k = 0; k < l_local; k++) { ys[k] = sh->y[rank + k * world]; cs[k] = sh->censored[rank + k * world]; }
-        yl = ys; cl = cs;
+        /* Every thread deals ITS contiguous slice of the caller's vectors out to all the shards (one sequential read of
+         * the input in total, instead of every rank striding through all of it), then the threads meet. */
+        if (sh->ys_ok) {
+            const long a = (long)((double)sh->l * rank / world), b = rank == world - 1 ? sh->l : (long)((double)sh->l * (rank + 1) / world);
+            int r = (int)(a % world); long k = a / world;
+            for (long i = a; i < b; i++) {
+                sh->ys[r][k] = sh->y[i]; sh->cs[r][k] = sh->censored[i];
+                if (++r == world) { r = 0; k++; }
+            }
+        } else set_error(sh, rank, "out of memory");
+        pthread_barrier_wait(&sh->bar);
+        yl = sh->ys[rank]; cl = sh->cs[rank];
     }
+    STAGE("shard gather");
     pht_config cfg = *sh->base; cfg.rank = rank; cfg.world = world; cfg.device = sh->devices[rank];
     if (!sh->failed && pht_engine_create(&eng, &cfg, yl, cl, l_local) != 0) set_error(sh, rank, pht_last_error());
-    free(ys); free(cs);
+    STAGE("engine create");
     if (world > 1) {
         /* The engines' exchange windows are attached to one another (direct peer pointers: one process): the per-sweep
          * all-reduce of the statistics and the global MHRS tail both run through them, inside the sweep's own kernels.
@@ -113,6 +127,7 @@ static void *rank_main(void *argp) {
         if (!sh->failed && pht_engine_peer_attach(eng, sh->handles) != 0) set_error(sh, rank, pht_last_error());
         pthread_barrier_wait(&sh->bar);
     }
+    STAGE("peer windows");
     if (!sh->failed && (sh->beta || sh->pi0) && pht_engine_set_pi(eng, sh->pi0, sh->beta) != 0) set_error(sh, rank, pht_last_error());
     if (!sh->failed && pht_engine_set_theta(eng, sh->theta, 1u) != 0) set_error(sh, rank, pht_last_error());
     double *rows = NULL;
@@ -141,7 +156,9 @@ static void *rank_main(void *argp) {
         }
     }
     free(rows);
+    STAGE("sweeps");
     if (eng) pht_engine_destroy(eng);
+    STAGE("engine destroy");
     return NULL;
 }
 
@@ -243,6 +260,13 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
     } else {
         pthread_t th[MAX_GPUS];
         pthread_barrier_init(&sh.bar, NULL, (unsigned)gpus);
+        sh.ys_ok = 1;
+        for (int r = 0; r < gpus; r++) {
+            const long lr = sh.l > r ? (sh.l - r + gpus - 1) / gpus : 0;
+            sh.ys[r] = (double *)malloc(sizeof(double) * (size_t)(lr > 0 ? lr : 1));
+            sh.cs[r] = (int *)malloc(sizeof(int) * (size_t)(lr > 0 ? lr : 1));
+            if (!sh.ys[r] || !sh.cs[r]) sh.ys_ok = 0;
+        }
         int started = 0;
         for (int r = 0; r < gpus; r++) {
             args[r].sh = &sh; args[r].rank = r;
@@ -256,6 +280,7 @@ void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, dou
         }
         for (int r = 0; r < gpus; r++) pthread_join(th[r], NULL);
         pthread_barrier_destroy(&sh.bar);
+        for (int r = 0; r < gpus; r++) { free(sh.ys[r]); free(sh.cs[r]); }
     }
     if (sh.failed) {
         /* mirrors the reference's print-and-carry-on error style (e.g. :334-337), but the rows that were not produced

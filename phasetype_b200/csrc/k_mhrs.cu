@@ -686,7 +686,7 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
                                            uint32_t obs_begin, uint32_t obs_end, uint32_t cap,
                                            unsigned &c_jumps, unsigned &c_attempts) {
     const unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     Fast f; fast_begin(f, 0u, n);
     ObsF o; obs_set(o, 0.0f, 0u, false);
     const double inv_smax = sm.inv_smax;

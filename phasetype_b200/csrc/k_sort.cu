@@ -24,16 +24,16 @@ __global__ void k_gather_u8(const uint8_t *src, const uint32_t *perm, uint8_t *d
 cudaError_t pht_sort_by_y_desc(const double *y, const uint8_t *cens, long l, double *ys, uint8_t *cs, uint32_t *perm, cudaStream_t st) {
     if (l <= 0) return cudaSuccess;
     uint32_t *idx = nullptr; void *tmp = nullptr; size_t tmp_bytes = 0;
-    cudaError_t e = cudaMalloc(&idx, sizeof(uint32_t) * (size_t)l);
+    cudaError_t e = pht_dev_alloc((void **)&idx, sizeof(uint32_t) * (size_t)l, st);
     if (e != cudaSuccess) return e;
     const int threads = 256; const unsigned blocks = (unsigned)((l + threads - 1) / threads);
     k_iota<<<blocks, threads, 0, st>>>(idx, l);
     e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, y, ys, idx, perm, (int)l, 0, 64, st);
-    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = pht_dev_alloc(&tmp, tmp_bytes ? tmp_bytes : 1, st);
     if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, y, ys, idx, perm, (int)l, 0, 64, st);
     if (e == cudaSuccess) { k_gather_u8<<<blocks, threads, 0, st>>>(cens, perm, cs, l); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (tmp) cudaFree(tmp);
-    cudaFree(idx);
+    pht_dev_free(tmp, st);
+    pht_dev_free(idx, st);
     return e;
 }
