@@ -147,11 +147,23 @@ def ref_kind():
     return "ref" if po.have_ref() else "oracle"
 
 
-def ncu_capture(method, l_local):
+def ncu_capture(method, l_local, general=False):
     """What the committed `ncu --set full` capture of this workload recorded for the path kernel (profiles/traffic.json,
-    written by tools/ncu_traffic.py): DRAM bytes and warp instructions per launch; {} when there is no capture."""
+    written by tools/ncu_traffic.py): DRAM bytes and warp instructions per launch; {} when there is no capture.
+    ECS / DCS on the general (unsymmetrised) generator were captured at 4 x 10^6 observations: their per-launch figures are
+    scaled by the observation count (both kernels stream the observations once and do per-path work) and say so."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if general:
+            for k, v in t.items():
+                parts = k.split(":")
+                if len(parts) == 3 and parts[0] == method and parts[1] == "general":
+                    f = l_local / float(parts[2])
+                    c = dict(v)
+                    c["dram_bytes_per_launch"] = v["dram_bytes_per_launch"] * f
+                    c["warp_instructions_per_launch"] = v["warp_instructions_per_launch"] * f
+                    c["source"] = "%s (captured at %s observations, scaled x %.2f)" % (v.get("source"), parts[2], f)
+                    return c
         return t.get("%s:%d" % (method, l_local)) or {}
     except Exception:
         return {}
@@ -294,7 +306,7 @@ class Runner:
         achieved = W * l_local / (res["kern_ms"] * 1e-3)
         hbm_peak, hbm_src = _peak_hbm()
         kernel = {"MHRS": "k_mhrs_lanes + k_mhrs_tail + k_mhrs_replay", "DCS": "k_dcs_sweep", "ECS": "k_ecs_exact + k_ecs_gt"}[method]
-        cap = ncu_capture(method, l_local)
+        cap = ncu_capture(method, l_local, general=(method != "MHRS" and "symmetric" not in wl.name and wl.name.startswith("C3")))
         issue = None
         mhz = (res.get("clocks") or {}).get("sm_mhz") or getattr(self, "sm_mhz", None)
         if cap.get("warp_instructions_per_launch") and mhz:
@@ -310,7 +322,11 @@ class Runner:
                 "kernel": kernel, "kernel_ms": res["kern_ms"], "kernel_share_of_step": res["share"],
                 "work_per_path": W, "events_per_path": ev,
                 "hbm": {"algorithmic_bytes_per_launch": 9 * l_local, "achieved_GBs": 9e-9 * l_local / (res["kern_ms"] * 1e-3),
-                        "peak_GBs": hbm_peak, "peak_source": hbm_src}}
+                        "peak_GBs": hbm_peak, "peak_source": hbm_src,
+                        # MHRS streams more than the 9 B per path of the observation itself BY DESIGN: the search kernels read y, flag and
+                        # the sort permutation (13 B) and write a 16-byte record, which the replay kernel reads back with y, flag and
+                        # permutation (29 B): 58 B per path, ~0.05 ms of HBM time in a sweep of > 10 ms
+                        "streamed_by_design_bytes_per_launch": (58 if method == "MHRS" else 9) * l_local}}
 
 
 # ----------------------------------------------------------------------------- main

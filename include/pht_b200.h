@@ -31,7 +31,7 @@ extern "C" {
  *   PHT_B200_SEED     (decimal/hex uint64; default: drawn from unif_rand())
  *   PHT_B200_DEVICE   (CUDA ordinal, default 0)
  *   PHT_B200_GRAPH    (0: launch the sweep's kernels directly instead of replaying a CUDA graph)
- *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail; default 32..256 by shard size)
+ *   PHT_B200_MHRS_CAP (attempts a lane tries before handing an observation to the cooperative tail; default 32..1024 by shard size)
  *   PHT_B200_GPUS     (devices to fan out over, starting at PHT_B200_DEVICE; default: one per 2^19 observations, at most
  *                      all visible.  One host thread + one engine per device; the all-reduce of the statistics and the
  *                      global MHRS tail run through peer memory inside the sweep's kernels; the chain does not depend
@@ -42,7 +42,10 @@ extern "C" {
  *                      the key so that a resumed run does not replay the streams of the run it continues)
  *   PHT_B200_BETA     (comma-separated Dirichlet prior of the start distribution, n values: switches its update on;
  *                      PHT_B200_PI0 = comma-separated initial pi, default e1; PHT_B200_PI_OUT = file that receives the
- *                      it x n draws as text, one row per iteration -- `res` has no columns for them) */
+ *                      it x n draws as text, one row per iteration -- `res` has no columns for them)
+ *   PHT_B200_NO_POOL  (1: plain cudaMalloc/cudaFree for the large per-call buffers instead of the devices' memory pools,
+ *                      which keep the memory cached between calls -- see pht_release_device_memory)
+ *   PHT_B200_TIMING   (1: stage times of the call's set-up on stderr) */
 void LJMA_Gibbs(int *it, int *mhit, int *method, int *n, int *m, double *nu, double *zeta,
                 int *T, double *C, double *y, int *l, int *censored, double *start,
                 int *silent, double *res);

@@ -553,7 +553,17 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
         }
         if (idle == FULL) { if (disp.exhausted) break; else continue; }
         __syncwarp();                       /* refilled and continuing lanes take the step together (see k_ecs_exact) */
-        if (active) {
+        /* A path is a few expensive sojourns before y (survival probability, ARMS draw, spectral next-state weights) and
+         * then ~1 / P(absorb) cheap ones after it (an exponential and a table scan).  One step per lane per pass of the
+         * outer loop made the ARMS code run with the lanes that happened to be before y: 7.7 of 32
+         * (profiles/r2f_ecs_general_4e6_ncu_full.md).  So: the first pass of this inner loop is the step of every lane -- all
+         * of them before y, see below -- and the further passes serve only lanes that are beyond y, until their paths end:
+         * at the next outer pass every active lane is before y again and the expensive code runs converged. */
+        bool first = true;
+        for (;;) {
+        const bool go = active && (first || !(t < y));
+        if (__ballot_sync(FULL, go) == 0u) break;
+        if (go) {
         /* ---- one step (gt_Aslett_DCS.c:339-384; censored = 1 unless MH) */
         const double lastt = t; const int lastj = j;
         const double Sjj = sm.S[j + j * n];
@@ -648,6 +658,9 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
             if (!MH || mh.rec) count_transition(p, n, sm.Nacc, out_idx, lastj, k);      /* :383 */
             j = k;
         }
+        }
+        first = false;
+        __syncwarp();
         }
     }
     ecs_finish(p, n, sm, c);
