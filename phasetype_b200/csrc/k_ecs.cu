@@ -556,7 +556,7 @@ __device__ __forceinline__ void ecs_gt_body(const SweepParams &p, const ObsList 
         /* A path is a few expensive sojourns before y (survival probability, ARMS draw, spectral next-state weights) and
          * then ~1 / P(absorb) cheap ones after it (an exponential and a table scan).  One step per lane per pass of the
          * outer loop made the ARMS code run with the lanes that happened to be before y: 7.7 of 32
-         * (profiles/r2f_ecs_general_4e6_ncu_full.md).  So: the first pass of this inner loop is the step of every lane -- all
+         * (profiles/r2f_ecs_general_4e6_before_ncu_full.md).  So: the first pass of this inner loop is the step of every lane -- all
          * of them before y, see below -- and the further passes serve only lanes that are beyond y, until their paths end:
          * at the next outer pass every active lane is before y again and the expensive code runs converged. */
         bool first = true;
