@@ -106,6 +106,9 @@ class Engine:
         y_local = np.ascontiguousarray(y_local, dtype=np.float64)
         cens_local = np.ascontiguousarray(cens_local, dtype=np.int32)
         self.l_local = int(y_local.shape[0])
+        if zbits is None and sum_y_global is None and int(world) > 1:
+            # every rank must use the same fixed-point scale: a per-rank guess from the local sum can differ near a power of two
+            raise EngineError("with several ranks pass sum_y_global (the sum of y over ALL ranks) or an explicit zbits")
         if zbits is None:
             zbits = L.pht_choose_zbits(float(sum_y_global if sum_y_global is not None else y_local.sum() * world))
         self.zbits = int(zbits)

@@ -455,7 +455,15 @@ extern "C" int pht_engine_comm_init(pht_engine *e, const void *id128) {
 }
 
 /* ---------------------------------------------------------------- peer exchange windows (MHRS global tail) */
-struct PeerHandle { unsigned long long pid; unsigned long long ptr; int device; int valid; cudaIpcMemHandle_t ipc; };
+struct PeerHandle { unsigned long long pid; unsigned long long ptr; int device; int valid; cudaIpcMemHandle_t ipc; unsigned long long cfg_hash; };
+/* what every rank of a run must agree on (the chain is one chain): key, shape, sampler, fixed-point scale, world size */
+static unsigned long long cfg_hash(const pht_config &c) {
+    unsigned long long h = 0xcbf29ce484222325ULL;
+    const unsigned long long v[] = { c.seed, (unsigned long long)c.n, (unsigned long long)c.m, (unsigned long long)c.method, (unsigned long long)c.mhit,
+                                     (unsigned long long)c.zbits, (unsigned long long)c.world };
+    for (unsigned long long x : v) for (int b = 0; b < 8; b++) { h ^= (x >> (8 * b)) & 0xffull; h *= 0x100000001b3ULL; }
+    return h;
+}
 static_assert(sizeof(PeerHandle) <= PHT_PEER_HANDLE_BYTES, "peer handle does not fit its ABI slot");
 
 extern "C" int pht_engine_peer_handle(pht_engine *e, void *handle) {
@@ -465,6 +473,7 @@ extern "C" int pht_engine_peer_handle(pht_engine *e, void *handle) {
     if (e->d_xw) {
         CU(cudaSetDevice(e->cfg.device));
         h.pid = (unsigned long long)getpid(); h.ptr = (unsigned long long)(uintptr_t)e->d_xw; h.device = e->cfg.device; h.valid = 1;
+        h.cfg_hash = cfg_hash(e->cfg);
         CU(cudaIpcGetMemHandle(&h.ipc, e->d_xw));
     }
     memcpy(handle, &h, sizeof(h));
@@ -478,6 +487,7 @@ extern "C" int pht_engine_peer_attach(pht_engine *e, const void *handles) {
     for (int r = 0; r < e->cfg.world; r++) {
         PeerHandle h; memcpy(&h, (const char *)handles + (size_t)r * PHT_PEER_HANDLE_BYTES, sizeof(h));
         if (!h.valid) return fail("rank %d offers no exchange window", r);
+        if (h.cfg_hash != cfg_hash(e->cfg)) return fail("rank %d runs a different configuration (seed, n, m, method, mhit, zbits or world differ from rank %d's): the ranks of a run share one chain", r, e->cfg.rank);
         if (r == e->cfg.rank) { e->xpeer[r] = e->d_xw; continue; }
         if (h.pid == (unsigned long long)getpid()) {
             /* same process (one host thread per GPU): the peer's pointer is valid here once peer access is on */

@@ -106,6 +106,12 @@ def test_engine_rejects_bad_arguments_before_touching_the_device(kw, msg):
                   mhit=a["mhit"], rank=a["rank"], world=a["world"], zbits=a["zbits"])
 
 
+def test_several_ranks_need_a_common_fixed_point_scale():
+    """A per-rank guess of zbits from the local sum of y can differ between ranks near a power of two."""
+    with pytest.raises(pb.EngineError, match="several ranks"):
+        pb.Engine(3, np.zeros(16, dtype=np.int32), np.ones(16), [1.0], [1.0], [1.0], [0], method=1, rank=0, world=2)
+
+
 def test_weak_scaling_shards_share_the_model():
     from phasetype_b200 import synth
     a = synth.config(3, "MHRS", l=500); b = synth.config(3, "MHRS", l=500, shard=1); c = synth.config(3, "MHRS", l=500, shard=1)

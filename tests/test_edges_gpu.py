@@ -119,3 +119,50 @@ def test_full_tail_lists_only_cost_speed(monkeypatch):
     got, want = _paths("MHRS", R, s, y, cens, mhit=2, cap=4)
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+def test_round_trace_counts_the_speculation():
+    """Per tail round the trace holds the attempts run next to the attempts the sequential sampler needs of that round's
+    offer: the parallel search can only run MORE (whatever completes beyond a survivor before it is known)."""
+    import phasetype_b200 as pb
+    wl = synth.config(2, "MHRS", l=20000)
+    eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=1, mhit=1, seed=3, mhrs_cap=4, use_graph=False)
+    eng.set_theta(wl.theta, next_iter=1)
+    eng.run(2)
+    tr = eng.round_trace(); cnt = eng.counters()
+    eng.close()
+    assert tr.shape == (48, 8)
+    used = tr[:, 4] > 0
+    assert used.sum() >= 2 and cnt["tail_rounds"] >= used.sum()
+    assert (tr[used, 6] > 0).all() and (tr[used, 5] >= tr[used, 6]).all()       # run >= needed > 0
+    assert (tr[used, 7] >= tr[used, 5]).all()                                   # an attempt is at least one jump-step
+    assert not tr[~used].any()
+
+
+def test_cached_device_memory_can_be_released_between_calls():
+    """The large buffers of a call stay cached in the device's memory pool; handing them back must not disturb the next call."""
+    import phasetype_b200 as pb
+    from phasetype_b200 import _lib
+    wl = synth.config(2, "MHRS", l=3000)
+    runs = []
+    for rep in range(3):
+        eng = pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y, wl.censored, method=1, mhit=1, seed=11)
+        eng.set_theta(wl.theta, next_iter=1)
+        runs.append(eng.run(3))
+        eng.close()
+        if rep == 0:
+            assert _lib.lib().pht_release_device_memory() == 0
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+
+
+def test_ranks_of_a_run_must_share_their_configuration():
+    """Two engines that claim to be ranks of one run but disagree on the fixed-point scale cannot be attached to one another."""
+    import phasetype_b200 as pb
+    wl = synth.config(2, "MHRS", l=2000)
+    engs = [pb.Engine(wl.n, wl.T, wl.C, wl.nu, wl.zeta, wl.y[r::2], wl.censored[r::2], method=1, mhit=1, seed=5, rank=r, world=2, zbits=30 + r)
+            for r in range(2)]
+    handles = b"".join(e.peer_handle() for e in engs)
+    with pytest.raises(pb.EngineError, match="different configuration"):
+        engs[0].peer_attach(handles)
+    for e in engs:
+        e.close()
