@@ -14,6 +14,7 @@
  */
 #include "engine_internal.h"
 #include "pht_philox.h"
+#define PHT_EIGEN_WARP 1          /* on the device the solver is run by one warp in lock step (pht_eigen.h) */
 #include "pht_eigen.h"
 
 __global__ void __launch_bounds__(64) k_assemble(UpdateParams p) {
@@ -159,29 +160,34 @@ __global__ void __launch_bounds__(64) k_spectral_inject(UpdateParams p, const do
     }
 }
 
-/* The engine's own solver (pht_eigen.h: Hessenberg + shifted QR + Gauss-Jordan), one thread working in shared
- * memory: O(10 n^3) dependent flops once per sweep, microseconds at n = 8 and about a millisecond at n = 32,
- * against sweeps of tens of milliseconds to seconds.  The other threads then form Q^-1 s and Q^-1 1. */
+/* The engine's own solver (pht_eigen.h: Hessenberg + shifted QR + Gauss-Jordan), one warp working in shared memory,
+ * once per sweep.  The block then forms Q^-1 s and Q^-1 1. */
 __global__ void __launch_bounds__(64) k_spectral_solve(UpdateParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n, tid = threadIdx.x;
     const ModelLayout L = ModelLayout::make(n, p.m);
     double *M = p.model;
+    /* the solver runs in shared memory, by warp 0 in lock step (pht_eigen.h: independent rows / columns dealt out over the
+     * lanes, scalar recurrences computed by all of them; bit-identical to the sequential host code): S is staged in, Q, Q^-1
+     * and the eigenvalues are written back by the whole block */
     double *w = reinterpret_cast<double *>(smem_raw);
-    if (tid == 0) {
-        const int st = pht_eigen_real(n, M + L.S, M + L.evals, M + L.Q, M + L.Qinv, w, w + n * n, w + 2 * n * n,
+    double *sS = w + 2 * n * n + 3 * n, *sQ = sS + n * n, *sQi = sQ + n * n, *sev = sQi + n * n;
+    for (int i = tid; i < n * n; i += blockDim.x) sS[i] = M[L.S + i];
+    __syncthreads();
+    if (tid < 32) {
+        const int st = pht_eigen_real(n, sS, sev, sQ, sQi, w, w + n * n, w + 2 * n * n,
                                       w + 2 * n * n + n, w + 2 * n * n + 2 * n);
         /* complex pairs (st & 2) are not an error: evals_im marks them and the samplers use the real block form */
-        if (st & 5) atomicOr(&p.state->error, 32);
-        const double *im = w + 2 * n * n + 2 * n;
-        for (int i = 0; i < n; i++) M[L.evals_im + i] = im[i];
+        if (tid == 0 && (st & 5)) atomicOr(&p.state->error, 32);
     }
     __syncthreads();
+    for (int i = tid; i < n * n; i += blockDim.x) { M[L.Q + i] = sQ[i]; M[L.Qinv + i] = sQi[i]; }
     if (tid < n) {
         const int i = tid;
+        M[L.evals + i] = sev[i]; M[L.evals_im + i] = w[2 * n * n + 2 * n + i];
         double ys = 0.0, y1 = 0.0;
         for (int j = 0; j < n; j++) {
-            const double a = M[L.Qinv + i + j * n];
+            const double a = sQi[i + j * n];
             ys += (1.0 * M[L.s + j]) * a;
             y1 += (1.0 * 1.0) * a;
         }
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(64) k_spectral_solve(UpdateParams p) {
 
 cudaError_t pht_launch_spectral(const UpdateParams &p, const double *inject, cudaStream_t st) {
     if (inject != nullptr) k_spectral_inject<<<1, 64, 0, st>>>(p, inject);
-    else k_spectral_solve<<<1, 64, sizeof(double) * (2 * p.n * p.n + 3 * p.n), st>>>(p);
+    else k_spectral_solve<<<1, 64, sizeof(double) * (5 * p.n * p.n + 4 * p.n), st>>>(p);
     return cudaGetLastError();
 }
 

@@ -46,6 +46,24 @@ PHT_HD void pht_cdiv(double ar, double ai, double br, double bi, double *cr, dou
     }
 }
 
+/* On the device the solver is run by ONE WARP in lock step (k_spectral_solve defines PHT_EIGEN_WARP): every lane follows
+ * the same control flow on the same shared-memory data -- the scalar recurrences of the algorithm are computed redundantly
+ * by all 32 lanes -- and the loops whose iterations are independent (one row, one column, one diagonal element each) are
+ * dealt out over the lanes.  Every element still sees exactly the operations, in exactly the order, of the sequential
+ * code, so the result is the host's, bit for bit (tests/test_model_gpu.py).  Rules that keep the lanes consistent:
+ * shared data is written either inside a dealt-out loop or by lane 0 alone (PHT_E_ONE), with a warp barrier between
+ * any write and the reads that depend on it (PHT_E_SYNC), and loop bodies use their own temporaries, never the uniform
+ * scalars.  On the host the three macros are the plain loop, nothing and nothing. */
+#if defined(__CUDA_ARCH__) && defined(PHT_EIGEN_WARP)
+#define PHT_E_FOR(v, lo, hi) for (int v = (lo) + (int)(threadIdx.x & 31u); v <= (hi); v += 32)
+#define PHT_E_SYNC() __syncwarp()
+#define PHT_E_ONE if ((threadIdx.x & 31u) == 0u)
+#else
+#define PHT_E_FOR(v, lo, hi) for (int v = (lo); v <= (hi); v++)
+#define PHT_E_SYNC() do { } while (0)
+#define PHT_E_ONE
+#endif
+
 PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, double *Qinv,
                           double *H, double *V, double *ort, double *d, double *e) {
     const double eps = 2.220446049250313e-16;
@@ -53,7 +71,8 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
     const int low = 0, high = nn - 1;
 #define HH(i, j) H[(i) * nn + (j)]
 #define VV(i, j) V[(i) * nn + (j)]
-    for (int i = 0; i < nn; i++) for (int j = 0; j < nn; j++) HH(i, j) = S[i + j * nn];
+    PHT_E_FOR(i, 0, nn - 1) for (int j = 0; j < nn; j++) HH(i, j) = S[i + j * nn];
+    PHT_E_SYNC();
 
     /* ---- orthes: Householder reduction to upper Hessenberg form */
     for (int m = low + 1; m <= high - 1; m++) {
@@ -61,44 +80,53 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
         for (int i = m; i <= high; i++) scale = scale + PHT_EABS(HH(i, m - 1));
         if (scale != 0.0) {
             double h = 0.0;
-            for (int i = high; i >= m; i--) { ort[i] = HH(i, m - 1) / scale; h += ort[i] * ort[i]; }
+            for (int i = high; i >= m; i--) { const double oi = HH(i, m - 1) / scale; h += oi * oi; }
+            const double om0 = HH(m, m - 1) / scale;
             double g = PHT_ESQRT(h);
-            if (ort[m] > 0) g = -g;
-            h = h - ort[m] * g;
-            ort[m] = ort[m] - g;
-            for (int j = m; j < nn; j++) {
+            if (om0 > 0) g = -g;
+            h = h - om0 * g;
+            const double om = om0 - g;
+            PHT_E_SYNC();
+            PHT_E_FOR(i, m, high) ort[i] = (i == m) ? om : HH(i, m - 1) / scale;
+            PHT_E_SYNC();
+            PHT_E_FOR(j, m, nn - 1) {
                 double f = 0.0;
                 for (int i = high; i >= m; i--) f += ort[i] * HH(i, j);
                 f = f / h;
                 for (int i = m; i <= high; i++) HH(i, j) -= f * ort[i];
             }
-            for (int i = 0; i <= high; i++) {
+            PHT_E_SYNC();
+            PHT_E_FOR(i, 0, high) {
                 double f = 0.0;
                 for (int j = high; j >= m; j--) f += ort[j] * HH(i, j);
                 f = f / h;
                 for (int j = m; j <= high; j++) HH(i, j) -= f * ort[j];
             }
-            ort[m] = scale * ort[m];
-            HH(m, m - 1) = scale * g;
+            PHT_E_SYNC();
+            PHT_E_ONE { ort[m] = scale * om; HH(m, m - 1) = scale * g; }
+            PHT_E_SYNC();
         }
     }
     /* ---- ortran: accumulate the transformations */
-    for (int i = 0; i < nn; i++) for (int j = 0; j < nn; j++) VV(i, j) = (i == j) ? 1.0 : 0.0;
+    PHT_E_FOR(i, 0, nn - 1) for (int j = 0; j < nn; j++) VV(i, j) = (i == j) ? 1.0 : 0.0;
+    PHT_E_SYNC();
     for (int m = high - 1; m >= low + 1; m--) {
         if (HH(m, m - 1) != 0.0) {
-            for (int i = m + 1; i <= high; i++) ort[i] = HH(i, m - 1);
-            for (int j = m; j <= high; j++) {
+            PHT_E_FOR(i, m + 1, high) ort[i] = HH(i, m - 1);
+            PHT_E_SYNC();
+            PHT_E_FOR(j, m, high) {
                 double g = 0.0;
                 for (int i = m; i <= high; i++) g += ort[i] * VV(i, j);
                 g = (g / ort[m]) / HH(m, m - 1);
                 for (int i = m; i <= high; i++) VV(i, j) += g * ort[i];
             }
+            PHT_E_SYNC();
         }
     }
 
     /* ---- hqr2: eigenvalues and Schur vectors by the shifted QR algorithm */
     int n = nn - 1;
-    double exshift = 0.0, p = 0, q = 0, r = 0, s = 0, z = 0, t, w, x, y;
+    double exshift = 0.0, p = 0, q = 0, r = 0, s = 0, z = 0, w, x, y;
     double norm = 0.0;
     for (int i = 0; i < nn; i++)
         for (int j = (i - 1 > 0 ? i - 1 : 0); j < nn; j++) norm = norm + PHT_EABS(HH(i, j));
@@ -112,33 +140,40 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
             l--;
         }
         if (l == n) {                                   /* one root */
-            HH(n, n) = HH(n, n) + exshift;
-            d[n] = HH(n, n); e[n] = 0.0;
+            const double hnn = HH(n, n) + exshift;
+            PHT_E_SYNC();
+            PHT_E_ONE { HH(n, n) = hnn; d[n] = hnn; e[n] = 0.0; }
+            PHT_E_SYNC();
             n--; iter = 0;
         } else if (l == n - 1) {                        /* two roots */
             w = HH(n, n - 1) * HH(n - 1, n);
             p = (HH(n - 1, n - 1) - HH(n, n)) / 2.0;
             q = p * p + w;
             z = PHT_ESQRT(PHT_EABS(q));
-            HH(n, n) = HH(n, n) + exshift;
-            HH(n - 1, n - 1) = HH(n - 1, n - 1) + exshift;
-            x = HH(n, n);
+            const double hnn = HH(n, n) + exshift, hn1 = HH(n - 1, n - 1) + exshift;
+            PHT_E_SYNC();
+            PHT_E_ONE { HH(n, n) = hnn; HH(n - 1, n - 1) = hn1; }
+            x = hnn;
             if (q >= 0) {                               /* real pair */
                 z = (p >= 0) ? p + z : p - z;
-                d[n - 1] = x + z;
-                d[n] = d[n - 1];
-                if (z != 0.0) d[n] = x - w / z;
-                e[n - 1] = 0.0; e[n] = 0.0;
+                const double d1 = x + z;
+                double d2 = d1;
+                if (z != 0.0) d2 = x - w / z;
+                PHT_E_ONE { d[n - 1] = d1; d[n] = d2; e[n - 1] = 0.0; e[n] = 0.0; }
                 x = HH(n, n - 1);
                 s = PHT_EABS(x) + PHT_EABS(z);
                 p = x / s; q = z / s;
                 r = PHT_ESQRT(p * p + q * q);
                 p = p / r; q = q / r;
-                for (int j = n - 1; j < nn; j++) { z = HH(n - 1, j); HH(n - 1, j) = q * z + p * HH(n, j); HH(n, j) = q * HH(n, j) - p * z; }
-                for (int i = 0; i <= n; i++) { z = HH(i, n - 1); HH(i, n - 1) = q * z + p * HH(i, n); HH(i, n) = q * HH(i, n) - p * z; }
-                for (int i = low; i <= high; i++) { z = VV(i, n - 1); VV(i, n - 1) = q * z + p * VV(i, n); VV(i, n) = q * VV(i, n) - p * z; }
+                PHT_E_SYNC();
+                PHT_E_FOR(j, n - 1, nn - 1) { const double zz = HH(n - 1, j); HH(n - 1, j) = q * zz + p * HH(n, j); HH(n, j) = q * HH(n, j) - p * zz; }
+                PHT_E_SYNC();
+                PHT_E_FOR(i, 0, n) { const double zz = HH(i, n - 1); HH(i, n - 1) = q * zz + p * HH(i, n); HH(i, n) = q * HH(i, n) - p * zz; }
+                PHT_E_FOR(i, low, high) { const double zz = VV(i, n - 1); VV(i, n - 1) = q * zz + p * VV(i, n); VV(i, n) = q * VV(i, n) - p * zz; }
+                PHT_E_SYNC();
             } else {                                    /* complex pair */
-                d[n - 1] = x + p; d[n] = x + p; e[n - 1] = z; e[n] = -z;
+                PHT_E_ONE { d[n - 1] = x + p; d[n] = x + p; e[n - 1] = z; e[n] = -z; }
+                PHT_E_SYNC();
                 status |= 2;
             }
             n = n - 2; iter = 0;
@@ -147,7 +182,9 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
             if (l < n) { y = HH(n - 1, n - 1); w = HH(n, n - 1) * HH(n - 1, n); }
             if (iter == 10) {                           /* Wilkinson's ad hoc shift */
                 exshift += x;
-                for (int i = low; i <= n; i++) HH(i, i) -= x;
+                PHT_E_SYNC();
+                PHT_E_FOR(i, low, n) HH(i, i) -= x;
+                PHT_E_SYNC();
                 s = PHT_EABS(HH(n, n - 1)) + PHT_EABS(HH(n - 1, n - 2));
                 x = y = 0.75 * s;
                 w = -0.4375 * s * s;
@@ -159,7 +196,9 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
                     s = PHT_ESQRT(s);
                     if (y < x) s = -s;
                     s = x - w / ((y - x) / 2.0 + s);
-                    for (int i = low; i <= n; i++) HH(i, i) -= s;
+                    PHT_E_SYNC();
+                    PHT_E_FOR(i, low, n) HH(i, i) -= s;
+                    PHT_E_SYNC();
                     exshift += s;
                     x = y = w = 0.964;
                 }
@@ -180,7 +219,9 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
                     eps * (PHT_EABS(p) * (PHT_EABS(HH(m - 1, m - 1)) + PHT_EABS(z) + PHT_EABS(HH(m + 1, m + 1))))) break;
                 m--;
             }
-            for (int i = m + 2; i <= n; i++) { HH(i, i - 2) = 0.0; if (i > m + 2) HH(i, i - 3) = 0.0; }
+            PHT_E_SYNC();
+            PHT_E_FOR(i, m + 2, n) { HH(i, i - 2) = 0.0; if (i > m + 2) HH(i, i - 3) = 0.0; }
+            PHT_E_SYNC();
             for (int k = m; k <= n - 1; k++) {          /* double QR step on rows l:n, columns m:n */
                 const int notlast = (k != n - 1);
                 if (k != m) {
@@ -192,35 +233,43 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
                 s = PHT_ESQRT(p * p + q * q + r * r);
                 if (p < 0) s = -s;
                 if (s != 0) {
-                    if (k != m) HH(k, k - 1) = -s * x;
-                    else if (l != m) HH(k, k - 1) = -HH(k, k - 1);
+                    const double hk = (k != m) ? -s * x : -HH(k, k - 1);
+                    PHT_E_SYNC();
+                    PHT_E_ONE { if (k != m || l != m) HH(k, k - 1) = hk; }
                     p = p + s; x = p / s; y = q / s; z = r / s; q = q / p; r = r / p;
-                    for (int j = k; j < nn; j++) {
-                        p = HH(k, j) + q * HH(k + 1, j);
-                        if (notlast) { p = p + r * HH(k + 2, j); HH(k + 2, j) = HH(k + 2, j) - p * z; }
-                        HH(k, j) = HH(k, j) - p * x;
-                        HH(k + 1, j) = HH(k + 1, j) - p * y;
+                    PHT_E_FOR(j, k, nn - 1) {
+                        double pp = HH(k, j) + q * HH(k + 1, j);
+                        if (notlast) { pp = pp + r * HH(k + 2, j); HH(k + 2, j) = HH(k + 2, j) - pp * z; }
+                        HH(k, j) = HH(k, j) - pp * x;
+                        HH(k + 1, j) = HH(k + 1, j) - pp * y;
                     }
+                    PHT_E_SYNC();
                     const int imax = (n < k + 3) ? n : k + 3;
-                    for (int i = 0; i <= imax; i++) {
-                        p = x * HH(i, k) + y * HH(i, k + 1);
-                        if (notlast) { p = p + z * HH(i, k + 2); HH(i, k + 2) = HH(i, k + 2) - p * r; }
-                        HH(i, k) = HH(i, k) - p;
-                        HH(i, k + 1) = HH(i, k + 1) - p * q;
+                    PHT_E_FOR(i, 0, imax) {
+                        double pp = x * HH(i, k) + y * HH(i, k + 1);
+                        if (notlast) { pp = pp + z * HH(i, k + 2); HH(i, k + 2) = HH(i, k + 2) - pp * r; }
+                        HH(i, k) = HH(i, k) - pp;
+                        HH(i, k + 1) = HH(i, k + 1) - pp * q;
                     }
-                    for (int i = low; i <= high; i++) {
-                        p = x * VV(i, k) + y * VV(i, k + 1);
-                        if (notlast) { p = p + z * VV(i, k + 2); VV(i, k + 2) = VV(i, k + 2) - p * r; }
-                        VV(i, k) = VV(i, k) - p;
-                        VV(i, k + 1) = VV(i, k + 1) - p * q;
+                    PHT_E_FOR(i, low, high) {
+                        double pp = x * VV(i, k) + y * VV(i, k + 1);
+                        if (notlast) { pp = pp + z * VV(i, k + 2); VV(i, k + 2) = VV(i, k + 2) - pp * r; }
+                        VV(i, k) = VV(i, k) - pp;
+                        VV(i, k + 1) = VV(i, k + 1) - pp * q;
                     }
+                    PHT_E_SYNC();
                 }
             }
         }
     }
 
-    /* ---- back-substitution: eigenvectors of the quasi-triangular form */
+    /* ---- back-substitution: eigenvectors of the quasi-triangular form.  Column n's solve reads the triangle to its left,
+     * which the solves of the columns to its left overwrite: inherently one after the other, so one lane does it (a few per
+     * cent of the solver's work). */
+    PHT_E_SYNC();
     if (norm != 0.0 && !(status & 1)) {
+        PHT_E_ONE {
+        double t;
         for (n = nn - 1; n >= 0; n--) {
             p = d[n]; q = e[n];
             if (q > 0.0) continue;                      /* first column of a complex pair: done together with the second */
@@ -291,18 +340,24 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
                 }
             }
         }
-        /* back transformation to the eigenvectors of the original matrix */
-        for (int j = nn - 1; j >= low; j--)
-            for (int i = low; i <= high; i++) {
-                z = 0.0;
+        }
+        PHT_E_SYNC();
+        /* back transformation to the eigenvectors of the original matrix: row i of V only needs row i of V, and column j
+         * only columns <= j, so with j running downwards inside the row the rows are independent */
+        PHT_E_FOR(i, low, high) {
+            for (int j = nn - 1; j >= low; j--) {
+                double zz = 0.0;
                 const int kmax = (j < high) ? j : high;
-                for (int k = low; k <= kmax; k++) z = z + VV(i, k) * HH(k, j);
-                VV(i, j) = z;
+                for (int k = low; k <= kmax; k++) zz = zz + VV(i, k) * HH(k, j);
+                VV(i, j) = zz;
             }
+        }
+        PHT_E_SYNC();
     }
 
-    /* ---- outputs: unit-norm columns, then Q^-1 by Gauss-Jordan with partial pivoting (H is free now) */
-    for (int k = 0; k < nn; k++) {
+    /* ---- outputs: unit-norm columns, then Q^-1 by Gauss-Jordan with partial pivoting (H is free now: a column of H is
+     * overwritten only after the same lane has read it as V's column, and nobody else reads H here) */
+    PHT_E_FOR(k, 0, nn - 1) {
         double nrm = 0.0;
         for (int i = 0; i < nn; i++) nrm += VV(i, k) * VV(i, k);
         /* the two columns of a complex pair are one complex vector: one common factor, or S [p q] = [p q] B breaks */
@@ -313,24 +368,34 @@ PHT_HD int pht_eigen_real(int nn, const double *S, double *evals, double *Q, dou
         evals[k] = d[k];
         for (int i = 0; i < nn; i++) { const double v = VV(i, k) / nrm; Q[i + k * nn] = v; HH(i, k) = v; }
     }
-    for (int i = 0; i < nn; i++) for (int j = 0; j < nn; j++) VV(i, j) = (i == j) ? 1.0 : 0.0;       /* V becomes the inverse */
+    PHT_E_SYNC();
+    PHT_E_FOR(i, 0, nn - 1) for (int j = 0; j < nn; j++) VV(i, j) = (i == j) ? 1.0 : 0.0;       /* V becomes the inverse */
+    PHT_E_SYNC();
     for (int c = 0; c < nn; c++) {
         int piv = c; double best = PHT_EABS(HH(c, c));
         for (int i = c + 1; i < nn; i++) { const double a = PHT_EABS(HH(i, c)); if (a > best) { best = a; piv = i; } }
         if (!(best > 0.0)) { status |= 4; continue; }
-        if (piv != c) for (int j = 0; j < nn; j++) {
-            double tmp = HH(c, j); HH(c, j) = HH(piv, j); HH(piv, j) = tmp;
-            tmp = VV(c, j); VV(c, j) = VV(piv, j); VV(piv, j) = tmp;
+        PHT_E_SYNC();
+        if (piv != c) {
+            PHT_E_FOR(j, 0, nn - 1) {
+                double tmp = HH(c, j); HH(c, j) = HH(piv, j); HH(piv, j) = tmp;
+                tmp = VV(c, j); VV(c, j) = VV(piv, j); VV(piv, j) = tmp;
+            }
+            PHT_E_SYNC();
         }
         const double dinv = 1.0 / HH(c, c);
-        for (int j = 0; j < nn; j++) { HH(c, j) = HH(c, j) * dinv; VV(c, j) = VV(c, j) * dinv; }
-        for (int i = 0; i < nn; i++) {
+        PHT_E_SYNC();
+        PHT_E_FOR(j, 0, nn - 1) { HH(c, j) = HH(c, j) * dinv; VV(c, j) = VV(c, j) * dinv; }
+        PHT_E_SYNC();
+        PHT_E_FOR(i, 0, nn - 1) {
             if (i == c) continue;
             const double f = HH(i, c);
             if (f != 0.0) for (int j = 0; j < nn; j++) { HH(i, j) -= f * HH(c, j); VV(i, j) -= f * VV(c, j); }
         }
+        PHT_E_SYNC();
     }
-    for (int i = 0; i < nn; i++) for (int j = 0; j < nn; j++) Qinv[i + j * nn] = VV(i, j);
+    PHT_E_FOR(i, 0, nn - 1) for (int j = 0; j < nn; j++) Qinv[i + j * nn] = VV(i, j);
+    PHT_E_SYNC();
 #undef HH
 #undef VV
     return status;
