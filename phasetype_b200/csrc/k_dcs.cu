@@ -33,12 +33,8 @@
 #ifndef DCS_WARPS_PER_SM
 #define DCS_WARPS_PER_SM 20          /* launch bound: resident warps per SM the register allocation must allow */
 #endif
-#ifndef DCS_UNROLL
-#define DCS_UNROLL 2                 /* independent exp chains in flight per lane in the batch */
-#endif
 
 enum { K_IDLE = 0, K_NEW = 1, K_JUMP = 2, K_BRENT = 3 };
-constexpr int kBatchUnroll = DCS_UNROLL;
 
 template <int THREADS>
 struct DcsSmem {
@@ -162,18 +158,40 @@ __global__ void __launch_bounds__(THREADS, DCS_WARPS_PER_SM * 32 / THREADS) k_dc
         if (kind0 != K_IDLE) {
             double *dst = (kind0 == K_JUMP ? sm.E : sm.X) + tid;
             if (!CPLX) {
-#pragma unroll kBatchUnroll
-                for (int i = 0; i < n; i++) dst[i * THREADS] = pht_exp(alpha * sm.evals[i] + beta);
+                /* four at a time: the same bits as pht_exp, the dependent chains interleaved (pht_math.h) */
+#pragma unroll 1
+                for (int i = 0; i < n; i += 4) {
+                    double e0, e1, e2, e3;
+                    pht_exp4(alpha * sm.evals[i] + beta, (i + 1 < n) ? alpha * sm.evals[i + 1] + beta : 0.0,
+                             (i + 2 < n) ? alpha * sm.evals[i + 2] + beta : 0.0, (i + 3 < n) ? alpha * sm.evals[i + 3] + beta : 0.0, e0, e1, e2, e3);
+                    dst[i * THREADS] = e0;
+                    if (i + 1 < n) dst[(i + 1) * THREADS] = e1;
+                    if (i + 2 < n) dst[(i + 2) * THREADS] = e2;
+                    if (i + 3 < n) dst[(i + 3) * THREADS] = e3;
+                }
             } else {
                 /* exp(alpha lam + beta) at lam = a - ib: real part in slot i, imaginary part in slot i + 1 */
+                /* (the exponentials four at a time, interleaved -- a pair's second slot gets one it does not need -- then the
+                 * rotations of the pairs) */
 #pragma unroll 1
-                for (int i = 0; i < n; i++) {
-                    const double ex = pht_exp(alpha * sm.evals[i] + beta);
-                    if ((pfirst >> i) & 1u) {
+                for (int i = 0; i < n; i += 4) {
+                    double e0, e1, e2, e3;
+                    pht_exp4(alpha * sm.evals[i] + beta, (i + 1 < n) ? alpha * sm.evals[i + 1] + beta : 0.0,
+                             (i + 2 < n) ? alpha * sm.evals[i + 2] + beta : 0.0, (i + 3 < n) ? alpha * sm.evals[i + 3] + beta : 0.0, e0, e1, e2, e3);
+                    dst[i * THREADS] = e0;
+                    if (i + 1 < n) dst[(i + 1) * THREADS] = e1;
+                    if (i + 2 < n) dst[(i + 2) * THREADS] = e2;
+                    if (i + 3 < n) dst[(i + 3) * THREADS] = e3;
+                }
+                {
+                    uint32_t pf = pfirst;
+#pragma unroll 1
+                    while (pf) {
+                        const int i = __ffs(pf) - 1; pf &= pf - 1u;
+                        const double ex = dst[i * THREADS];
                         double sn, cs; sincos(alpha * sm.evi[i], &sn, &cs);
                         dst[i * THREADS] = ex * cs; dst[(i + 1) * THREADS] = -(ex * sn);
-                        i++;
-                    } else dst[i * THREADS] = ex;
+                    }
                 }
             }
         }

@@ -94,8 +94,16 @@ static __device__ __noinline__ double ecs_dens_exact(const double *pq, const dou
                                                      double y_t, double Sjj, double d) {      /* eq_Aslett_ECS.c:150-171 */
     double term1 = 0.0;
     const double a = y_t - d;
-#pragma unroll 2
-    for (int i = 0; i < n; i++) term1 += (pq[i * ECS_THREADS] * pht_exp(evals[i] * a)) * qinv_s[i];
+    /* four exponentials at a time (pht_exp4: the same bits, the dependent chains interleaved); the sum keeps its order */
+#pragma unroll 1
+    for (int i = 0; i < n; i += 4) {
+        double e0, e1, e2, e3;
+        pht_exp4(evals[i] * a, (i + 1 < n) ? evals[i + 1] * a : 0.0, (i + 2 < n) ? evals[i + 2] * a : 0.0, (i + 3 < n) ? evals[i + 3] * a : 0.0, e0, e1, e2, e3);
+        term1 += (pq[i * ECS_THREADS] * e0) * qinv_s[i];
+        if (i + 1 < n) term1 += (pq[(i + 1) * ECS_THREADS] * e1) * qinv_s[i + 1];
+        if (i + 2 < n) term1 += (pq[(i + 2) * ECS_THREADS] * e2) * qinv_s[i + 2];
+        if (i + 3 < n) term1 += (pq[(i + 3) * ECS_THREADS] * e3) * qinv_s[i + 3];
+    }
     return pht_log(term1) + Sjj * d;
 }
 static __device__ __noinline__ double ecs_dens_gt(const double *pq, const double *evals, const double *qinv_1, int n,
@@ -104,8 +112,15 @@ static __device__ __noinline__ double ecs_dens_gt(const double *pq, const double
     double r1 = 1.0;
     if (x1 > 0) {
         r1 = 0.0;
-#pragma unroll 2
-        for (int i = 0; i < n; i++) r1 += pq[i * ECS_THREADS] * pht_exp(x1 * evals[i]) * qinv_1[i];
+#pragma unroll 1
+        for (int i = 0; i < n; i += 4) {
+            double e0, e1, e2, e3;
+            pht_exp4(x1 * evals[i], (i + 1 < n) ? x1 * evals[i + 1] : 0.0, (i + 2 < n) ? x1 * evals[i + 2] : 0.0, (i + 3 < n) ? x1 * evals[i + 3] : 0.0, e0, e1, e2, e3);
+            r1 += pq[i * ECS_THREADS] * e0 * qinv_1[i];
+            if (i + 1 < n) r1 += pq[(i + 1) * ECS_THREADS] * e1 * qinv_1[i + 1];
+            if (i + 2 < n) r1 += pq[(i + 2) * ECS_THREADS] * e2 * qinv_1[i + 2];
+            if (i + 3 < n) r1 += pq[(i + 3) * ECS_THREADS] * e3 * qinv_1[i + 3];
+        }
     }
     double dens;                                     /* dexp(d, scale, log = TRUE) */
     if (scale <= 0.0) dens = pht_u2d(0x7ff8000000000000ULL);
