@@ -95,6 +95,12 @@ namespace cg = cooperative_groups;
 #ifndef REPLAY_REFILL_MIN
 #define REPLAY_REFILL_MIN 16        /* idle lanes of a warp that trigger a refill from the record list */
 #endif
+#ifndef EV_MIN
+#define EV_MIN 8u                   /* lane kernel: lanes with an event that make the warp leave the step loop ... */
+#endif
+#ifndef EV_WAIT
+#define EV_WAIT 16u                 /* ... or steps the first of them has waited (lane kernel per sweep of 1e7, ms: 1/1 4.82, 3/4 4.58, 5/8 4.44, 8/16 4.38, 16/32 4.50) */
+#endif
 #ifndef PREFETCH_MIN
 #define PREFETCH_MIN 8              /* empty prefetch slots in a warp that trigger a refill */
 #endif
@@ -726,14 +732,21 @@ __device__ __forceinline__ void lane_phase(const SweepParams &p, MhrsSmem<NC> &s
         /* ---- the search loop proper: steps until some lane has something to report.  No calls, nothing but the
          * filter walk, in here; a failed attempt restarts on the next sub-stream on the spot. */
         bool surv = false, amb = false, hand = false; int k = 0;
-        const bool run = (fl & LF_RUN) != 0u;
+        bool go = (fl & LF_RUN) != 0u;
+        /* A lane that has something to report stops walking, but the warp only leaves the loop for the (divergent, ~100
+         * instructions at 2 lanes) event code once EV_MIN lanes are waiting or the first of them has waited EV_WAIT steps:
+         * events come every ~150 steps per lane, so the wait costs a lane a few per cent and the event code runs a third as often. */
+        unsigned waited = 0u, ev;
         do {
-            if (run) {
+            if (go) {
                 bool fail;
                 fast_step(f, o, p, sm, iter, n, fail, surv, amb, k);
                 if (fail) { c_jumps += f.b; fast_begin(f, f.a + 1u, n); c_attempts++; hand = f.a >= a_lim; }
+                go = !(surv || amb || hand);
             }
-        } while (!__any_sync(FULL, surv || amb || hand));
+            ev = __ballot_sync(FULL, !go);
+            waited += ((ev & running) != 0u) ? 1u : 0u;
+        } while (ev != 0xffffffffu && (unsigned)__popc(ev & running) < EV_MIN && waited < EV_WAIT);
         /* ---- events, a few lanes at a time */
         if (surv || amb) c_jumps += f.b;            /* the filter steps of the attempt that just ended (failed ones: above) */
         if (amb) {
