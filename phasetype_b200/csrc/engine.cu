@@ -236,22 +236,35 @@ static int enqueue_sweep(pht_engine *e, double *res, int res_rows, bool time_ker
 
 extern "C" void pht_engine_destroy(pht_engine *e) {
     if (!e) return;
+    const bool timing = getenv("PHT_B200_TIMING") != nullptr;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto stage = [&](const char *what) {
+        if (!timing) return;
+        struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[pht_engine_destroy] %-27s %8.3f ms\n", what, (t.tv_sec - ts0.tv_sec) * 1e3 + (t.tv_nsec - ts0.tv_nsec) * 1e-6);
+        ts0 = t;
+    };
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     /* the graph holds captured NCCL work: it must go before the communicator it refers to */
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    stage("sync, graph");
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (cudaEvent_t ev : e->kev) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     for (void *q : e->ipc_opened) cudaIpcCloseMemHandle(q);
-    void *big[] = { e->d_recs, e->d_ys, e->d_cs, e->d_perm, e->d_y, e->d_cens, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_idx_exact, e->d_idx_cens };
+    stage("events, ipc");
+    void *big[] = { e->d_recs, e->d_ys, e->d_cs, e->d_perm, e->d_y, e->d_cens, e->d_items /* arena: found, pend0, pend1, done live inside */, e->d_idx_exact, e->d_idx_cens,
+                    e->d_glist, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta, e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_pires, e->d_res };
     for (void *b : big) pht_dev_free(b, e->stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *bufs[] = { e->d_glist, e->d_xw, e->d_model, e->d_stats, e->d_state, e->d_T, e->d_C, e->d_nu, e->d_zeta,
-                     e->d_var_ptr, e->d_cell_i, e->d_cell_j, e->d_beta, e->d_pires, e->d_res, e->d_inject, e->d_flush };
+    stage("pool frees");
+    void *bufs[] = { e->d_xw /* mapped by the peers: a plain allocation */, e->d_beta, e->d_inject, e->d_flush };
     for (void *b : bufs) if (b) cudaFree(b);
+    stage("plain frees");
     if (e->stream) cudaStreamDestroy(e->stream);
+    stage("stream");
     delete e;
 }
 
@@ -277,8 +290,11 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device available (this library has no CPU path)"); }
     if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d not present (%d devices)", cfg->device, ndev);
     CU(cudaSetDevice(cfg->device));
-    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, cfg->device));
-    if (prop.major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    /* (cudaGetDeviceProperties takes 2-13 ms per call here; two attributes take microseconds) */
+    int cc_major = 0, cc_minor = 0;
+    CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+    CU(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, cfg->device));
+    if (cc_major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, cc_major, cc_minor);
 
     /* PHT_B200_TIMING=1: stage times of the set-up on stderr (tools/e2e_breakdown.py) */
     const bool timing = getenv("PHT_B200_TIMING") != nullptr;
@@ -335,17 +351,21 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
     { std::vector<int> fill(var_ptr.begin(), var_ptr.end() - 1);
       for (int i = 0; i < n1; i++) for (int j = 0; j < n1; j++) { int v = e->T[i + j * n1]; if (v) { int c = fill[v - 1]++; cell_i[c] = i; cell_j[c] = j; } } }
 
-    CUE(cudaMalloc(&e->d_model, sizeof(double) * e->L.total)); CUE(cudaMemsetAsync(e->d_model, 0, sizeof(double) * e->L.total, e->stream));
-    CUE(cudaMalloc(&e->d_stats, sizeof(long long) * stats_len(n))); CUE(cudaMemsetAsync(e->d_stats, 0, sizeof(long long) * stats_len(n), e->stream));
-    CUE(cudaMalloc(&e->d_state, sizeof(DevState))); CUE(cudaMemsetAsync(e->d_state, 0, sizeof(DevState), e->stream));
-    CUE(cudaMalloc(&e->d_T, sizeof(int) * n1 * n1)); CUE(cudaMemcpy(e->d_T, e->T.data(), sizeof(int) * n1 * n1, cudaMemcpyHostToDevice));
-    CUE(cudaMalloc(&e->d_C, sizeof(double) * n1 * n1)); CUE(cudaMemcpy(e->d_C, e->C.data(), sizeof(double) * n1 * n1, cudaMemcpyHostToDevice));
-    CUE(cudaMalloc(&e->d_nu, sizeof(double) * m)); CUE(cudaMemcpy(e->d_nu, e->nu.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
-    CUE(cudaMalloc(&e->d_zeta, sizeof(double) * m)); CUE(cudaMemcpy(e->d_zeta, e->zeta.data(), sizeof(double) * m, cudaMemcpyHostToDevice));
-    CUE(cudaMalloc(&e->d_var_ptr, sizeof(int) * (m + 1))); CUE(cudaMemcpy(e->d_var_ptr, var_ptr.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice));
-    CUE(cudaMalloc(&e->d_cell_i, sizeof(int) * cell_i.size())); CUE(cudaMemcpy(e->d_cell_i, cell_i.data(), sizeof(int) * cell_i.size(), cudaMemcpyHostToDevice));
-    CUE(cudaMalloc(&e->d_cell_j, sizeof(int) * cell_j.size())); CUE(cudaMemcpy(e->d_cell_j, cell_j.data(), sizeof(int) * cell_j.size(), cudaMemcpyHostToDevice));
-
+    /* the small buffers too come from the pool (a plain cudaFree per buffer cost up to 66 ms per call inside a process that
+     * holds other allocations: PHT_B200_TIMING); the host vectors they are filled from live until the synchronize below */
+#define SMALL(ptr, bytes) CUE(pht_dev_alloc((void **)&(ptr), (bytes), e->stream))
+    SMALL(e->d_model, sizeof(double) * e->L.total); CUE(cudaMemsetAsync(e->d_model, 0, sizeof(double) * e->L.total, e->stream));
+    SMALL(e->d_stats, sizeof(long long) * stats_len(n)); CUE(cudaMemsetAsync(e->d_stats, 0, sizeof(long long) * stats_len(n), e->stream));
+    SMALL(e->d_state, sizeof(DevState)); CUE(cudaMemsetAsync(e->d_state, 0, sizeof(DevState), e->stream));
+    SMALL(e->d_T, sizeof(int) * n1 * n1); CUE(cudaMemcpyAsync(e->d_T, e->T.data(), sizeof(int) * n1 * n1, cudaMemcpyHostToDevice, e->stream));
+    SMALL(e->d_C, sizeof(double) * n1 * n1); CUE(cudaMemcpyAsync(e->d_C, e->C.data(), sizeof(double) * n1 * n1, cudaMemcpyHostToDevice, e->stream));
+    SMALL(e->d_nu, sizeof(double) * m); CUE(cudaMemcpyAsync(e->d_nu, e->nu.data(), sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+    SMALL(e->d_zeta, sizeof(double) * m); CUE(cudaMemcpyAsync(e->d_zeta, e->zeta.data(), sizeof(double) * m, cudaMemcpyHostToDevice, e->stream));
+    SMALL(e->d_var_ptr, sizeof(int) * (m + 1)); CUE(cudaMemcpyAsync(e->d_var_ptr, var_ptr.data(), sizeof(int) * (m + 1), cudaMemcpyHostToDevice, e->stream));
+    SMALL(e->d_cell_i, sizeof(int) * cell_i.size()); CUE(cudaMemcpyAsync(e->d_cell_i, cell_i.data(), sizeof(int) * cell_i.size(), cudaMemcpyHostToDevice, e->stream));
+    SMALL(e->d_cell_j, sizeof(int) * cell_j.size()); CUE(cudaMemcpyAsync(e->d_cell_j, cell_j.data(), sizeof(int) * cell_j.size(), cudaMemcpyHostToDevice, e->stream));
+#undef SMALL
+    CUE(cudaStreamSynchronize(e->stream));
     stage("model buffers");
     if (cfg->world > 1) {
         /* this rank's exchange window: all-reduce slots (every method) and the global MHRS tail (flags 0, found words NONE) */
@@ -380,7 +400,7 @@ extern "C" int pht_engine_create(pht_engine **out, const pht_config *cfg, const 
         }
         /* global tail: the canonical list */
         if (const char *ev = getenv("PHT_B200_KSWITCH")) { const long v = atol(ev); if (v >= 512 && v <= (1l << 24)) e->k_switch = (uint32_t)v; }
-        if (cfg->world > 1) CUE(cudaMalloc(&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP));      /* double buffered */
+        if (cfg->world > 1) CUE(pht_dev_alloc((void **)&e->d_glist, sizeof(uint32_t) * 2 * PHT_MAX_WORLD * PHT_GCAP, e->stream));      /* double buffered */
         CUE(pht_dev_alloc((void **)&e->d_recs, ln * sizeof(uint4), e->stream));
         stage("record list");
         if (pht_mhrs_grid_blocks(cfg->device, n, &e->grid_blocks, &e->tail_blocks, &e->replay_blocks) != 0) e->grid_blocks = 0;
@@ -574,10 +594,12 @@ extern "C" int pht_engine_pi_rows(pht_engine *e, int rows, double *out) {
 
 static int ensure_res(pht_engine *e, int rows) {
     if (rows <= e->res_rows) return 0;
-    if (e->d_res) { CU(cudaFree(e->d_res)); e->d_res = nullptr; }
-    CU(cudaMalloc(&e->d_res, sizeof(double) * (size_t)rows * e->cfg.m));
-    if (e->d_pires) { CU(cudaFree(e->d_pires)); e->d_pires = nullptr; }
-    CU(cudaMalloc(&e->d_pires, sizeof(double) * (size_t)rows * e->cfg.n));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->d_res) { CU(pht_dev_free(e->d_res, e->stream)); e->d_res = nullptr; }
+    CU(pht_dev_alloc((void **)&e->d_res, sizeof(double) * (size_t)rows * e->cfg.m, e->stream));
+    if (e->d_pires) { CU(pht_dev_free(e->d_pires, e->stream)); e->d_pires = nullptr; }
+    CU(pht_dev_alloc((void **)&e->d_pires, sizeof(double) * (size_t)rows * e->cfg.n, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     e->res_rows = rows;
     return 0;
 }
