@@ -88,6 +88,19 @@ static void set_error(shared_t *sh, int rank, const char *msg) {
 static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
 #define STAGE(what) do { if (timing) { const double t_ = now_ms(); fprintf(stderr, "[LJMA_Gibbs rank %d] %-24s %8.3f ms\n", rank, what, t_ - t_stage); t_stage = t_; } } while (0)
 
+/* deal observations [a, b) of the caller's vectors out to the shards: observation i -> shard i mod world, position i / world */
+#define DEAL_THREADS 8
+typedef struct { shared_t *sh; long a, b; } deal_arg;
+static void *deal_main(void *argp) {
+    deal_arg *d = (deal_arg *)argp; shared_t *sh = d->sh; const int world = sh->world;
+    int r = (int)(d->a % world); long k = d->a / world;
+    for (long i = d->a; i < d->b; i++) {
+        sh->ys[r][k] = sh->y[i]; sh->cs[r][k] = sh->censored[i];
+        if (++r == world) { r = 0; k++; }
+    }
+    return NULL;
+}
+
 /* One rank = one device.  Every collective step is bracketed by the thread barrier, and a rank that has failed keeps
  * walking through the barriers without touching its engine, so nobody waits for it in vain. */
 static void *rank_main(void *argp) {
@@ -102,12 +115,16 @@ static void *rank_main(void *argp) {
         /* Every thread deals ITS contiguous slice of the caller's vectors out to all the shards (one sequential read of
          * the input in total, instead of every rank striding through all of it), then the threads meet. */
         if (sh->ys_ok) {
+            /* (with few ranks a slice is tens of megabytes: helper threads share it, DEAL_THREADS in all) */
             const long a = (long)((double)sh->l * rank / world), b = rank == world - 1 ? sh->l : (long)((double)sh->l * (rank + 1) / world);
-            int r = (int)(a % world); long k = a / world;
-            for (long i = a; i < b; i++) {
-                sh->ys[r][k] = sh->y[i]; sh->cs[r][k] = sh->censored[i];
-                if (++r == world) { r = 0; k++; }
+            int helpers = DEAL_THREADS / world; if (helpers < 1) helpers = 1; if (helpers > 8) helpers = 8;
+            deal_arg da[8]; pthread_t dth[8]; int started[8];
+            for (int h = 0; h < helpers; h++) {
+                da[h].sh = sh; da[h].a = a + (b - a) * h / helpers; da[h].b = (h == helpers - 1) ? b : a + (b - a) * (h + 1) / helpers;
+                started[h] = (h > 0) && pthread_create(&dth[h], NULL, deal_main, &da[h]) == 0;
             }
+            deal_main(&da[0]);
+            for (int h = 1; h < helpers; h++) { if (started[h]) pthread_join(dth[h], NULL); else deal_main(&da[h]); }
         } else set_error(sh, rank, "out of memory");
         pthread_barrier_wait(&sh->bar);
         yl = sh->ys[rank]; cl = sh->cs[rank];
