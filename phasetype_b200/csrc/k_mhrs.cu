@@ -228,7 +228,7 @@ __device__ __forceinline__ bool walk_step(Walk &w, double y, bool cens, uint32_t
     const double *c = sm.cum + row * R;
     /* reference scan `while (sofar < target) sofar += p[k++]` = number of leading running sums below the target
      * among the first `last`.  The guide entry counts the sums <= bucket floor < uA. */
-    int k = sm.guide[row * GUIDE + (hiA >> (32 - GUIDE_BITS))];
+    int k = sm.guide[row * GUIDE + (hiA >> (32 - GUIDE_BITS))] & 0x7f;
     while (k < last && c[k] < uA) k++;
     const bool cont = (k < n) && (w.t < y || cens);                /* gt_Bladt_MHRS.c:75,111 */
     const bool ended = !fresh && !cont;
@@ -399,9 +399,10 @@ __device__ __forceinline__ void fast_step(Fast &f, const ObsF &o, const SweepPar
     const pht_u32x4 r = philox_block(f.b, f.a, o.og, iter, p);
     f.b++;
     const unsigned long long x = (((unsigned long long)r.v[1] << 32) | r.v[0]) >> 12;
-    int k = sm.guide[f.row * GUIDE + (r.v[1] >> (32 - GUIDE_BITS))];
-    const unsigned long long *th = sm.thr + f.row * R;
-    while (x >= th[k]) k++;
+    const unsigned g = sm.guide[f.row * GUIDE + (r.v[1] >> (32 - GUIDE_BITS))];
+    int k = (int)(g & 0x7fu);
+    /* bit 7: no threshold of the row falls inside the bucket, the guide entry IS the answer (24 of 25 look-ups at 8 phases) */
+    if (!(g & 0x80u)) { const unsigned long long *th = sm.thr + f.row * R; while (x >= th[k]) k++; }
     const uint32_t w = r.v[3];
     const uint32_t wb = __float_as_uint(__uint2float_rn(w));
     const uint32_t eb = wb >> 23;                                                     /* 127 + exponent of w */
@@ -466,7 +467,9 @@ __device__ __forceinline__ void build_tables(const SweepParams &p, MhrsSmem<NC> 
         const double floor_u = (double)b * (1.0 / GUIDE);
         int k = 0;
         while (k < last && sm.cum[row * R + k] <= floor_u) k++;
-        sm.guide[e] = (unsigned char)k;
+        /* bit 7: every x of the bucket, [b, b + 1) 2^(52 - GUIDE_BITS), is below the next threshold */
+        const bool pure = sm.thr[row * R + k] >= ((unsigned long long)(b + 1) << (52 - GUIDE_BITS));
+        sm.guide[e] = (unsigned char)(k | (pure ? 0x80 : 0));
     }
     __syncthreads();
 }
